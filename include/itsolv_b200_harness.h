@@ -1,0 +1,101 @@
+/*
+ * C ABI of the solver harness: runs the reference's own solver drivers
+ * (molpro::linalg::itsolv::LinearEigensystemDavidson / LinearEquationsDavidson / NonLinearEquationsDIIS,
+ * reference src/molpro/linalg/itsolv/{LinearEigensystemDavidson,LinearEquationsDavidson,NonLinearEquationsDIIS}.h)
+ * through IterativeSolver::solve() (IterativeSolverTemplate.h:322-408) on the synthetic banded operator, with
+ * DistrArrayCUDA as the R/Q container and ArrayHandlerCUDA as the handler set.
+ *
+ * The same two structs are consumed by the CPU oracle build of the reference (oracle/ref_driver.cpp), so a parity
+ * test hands one spec to both sides and compares the two results.
+ */
+#ifndef ITSOLV_B200_HARNESS_H
+#define ITSOLV_B200_HARNESS_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  ITSOLV_KIND_DAVIDSON = 0, /* LinearEigensystemDavidson */
+  ITSOLV_KIND_LINEQ = 1,    /* LinearEquationsDavidson   */
+  ITSOLV_KIND_DIIS = 2      /* NonLinearEquationsDIIS    */
+};
+enum {
+  ITSOLV_PROBLEM_BANDED = 0, /* synthetic banded symmetric operator, SURVEY.md section 8(d) */
+  ITSOLV_PROBLEM_EXAMPLE = 1 /* dense matrix of the reference's examples/ExampleProblem.h:8 (small n only) */
+};
+#define ITSOLV_MAX_ROOTS 64
+
+typedef struct itsolv_solve_spec {
+  int64_t n;                    /* global vector length */
+  int32_t kind;                 /* ITSOLV_KIND_* */
+  int32_t problem;              /* ITSOLV_PROBLEM_* */
+  int32_t nroots;               /* roots sought, or number of right-hand sides; ignored for DIIS */
+  int32_t nbuffers;             /* R vectors handed to solve(); 0 means nroots */
+  int32_t half_bandwidth;       /* b: A(i,j) != 0 for |i-j| <= b */
+  int32_t hermitian;            /* set_hermiticity() */
+  double eps;                   /* off-diagonal scale */
+  double convergence_threshold; /* set_convergence_threshold() */
+  int32_t max_iter;             /* set_max_iter() */
+  int32_t max_size_qspace;      /* <= 0: unlimited */
+  int32_t reset_D;              /* <= 0: library default (never) */
+  int32_t max_p;                /* P-space size for solve(); 0: none */
+  int32_t verbosity;            /* 0..3 as IterativeSolver::set_verbosity(int) */
+  int32_t trace;                /* record every dot/gemm_inner result for parity checks */
+  int32_t explicit_csr;         /* banded operator: 1 = stored CSR arrays, 0 = entries generated in the kernel */
+  int32_t reserved;
+} itsolv_solve_spec;
+
+typedef struct itsolv_solve_result {
+  int32_t converged;
+  int32_t iterations; /* statistics().iterations */
+  int32_t nroots;
+  int32_t nwork_final;
+  double eigenvalues[ITSOLV_MAX_ROOTS]; /* Davidson only */
+  double errors[ITSOLV_MAX_ROOTS];
+  double seconds_solve;   /* host wall time of solve() alone */
+  double seconds_action;  /* of which inside Problem::action/residual */
+  double seconds_precond; /* of which inside Problem::precondition */
+  int64_t r_creations, q_creations, p_creations, d_creations;
+  /* handler call counts and algorithmic bytes accumulated by the CUDA handlers; zero for the oracle */
+  int64_t n_dot, n_axpy, n_scal, n_copy, n_fill, n_gemm_inner, n_gemm_outer;
+  double handler_bytes;
+  double handler_device_seconds;
+  int64_t kernel_launches;
+} itsolv_solve_result;
+
+/* One trace record = one handler call that returned numbers to the host. op: 'd' dot, 'g' gemm_inner. */
+typedef struct itsolv_trace_entry {
+  int32_t op, rows, cols, reserved;
+  int64_t offset; /* into the value array */
+} itsolv_trace_entry;
+
+/*
+ * Run one solve on the calling rank's GPU (all ranks of the communicator call it collectively).
+ * solutions: optional host buffer, nroots * n_local doubles, receives this rank's rows of each solution vector.
+ * Returns 0 on success, non-zero on error (message via itsolv_last_error()).
+ */
+int itsolv_harness_solve(const itsolv_solve_spec* spec, itsolv_solve_result* result, double* solutions);
+
+/*
+ * End-to-end entry: the caller owns the operator on the HOST as CSR (row_ptr[n_local+1], col[nnz] global column
+ * indices, val[nnz]) plus its diagonal; the call uploads it, solves, and downloads eigenvalues and solution vectors.
+ */
+int itsolv_harness_solve_host_csr(const itsolv_solve_spec* spec, const int64_t* row_ptr, const int32_t* col,
+                                  const double* val, const double* diag, itsolv_solve_result* result,
+                                  double* solutions);
+
+size_t itsolv_harness_trace_entries(void);
+size_t itsolv_harness_trace_values(void);
+void itsolv_harness_trace_read(itsolv_trace_entry* entries, double* values);
+
+/* Host subspace algebra entry points (restated helper, reference helper-implementation.h:318-543), exported for tests */
+int itsolv_host_eigenproblem(const double* matrix, const double* metric, size_t dimension, int hermitian,
+                             double svd_threshold, double* eigenvalues, double* eigenvectors, size_t* nfound);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

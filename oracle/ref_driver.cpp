@@ -1,0 +1,419 @@
+// TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+//
+// Builds the UNMODIFIED reference templates (included from /root/reference/src where they lie) with the reference's
+// own CPU path — std::vector<double> containers and ArrayHandlerIterable / ArrayHandlerIterableSparse
+// (reference src/molpro/linalg/array/ArrayHandlerIterable.h:34-128, ArrayHandlerIterableSparse.h:20-84,
+// array/util/gemm.h:257-279) — into oracle/_ref/libitsolv_ref.so, and exposes it through a flat C ABI so that
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference arm can call it.
+// Nothing under iterative_solver_b200/ links or loads this library.
+//
+// Two things here are not reference code:
+//   * the host dense algebra the solver templates call (eigenproblem, svd_system, ...): the reference implements it
+//     over Eigen/LAPACKE, neither present; iterative_solver_b200/host/helper_lapack.cpp restates it over LAPACK;
+//   * the synthetic banded operator (BandedProblemHost below), the CPU twin of the harness' CUDA operator.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../iterative_solver_b200/harness/solve_driver.h"
+
+#include <ExampleProblem.h> // reference examples/ExampleProblem.h
+#include <molpro/linalg/array/ArrayHandlerIterable.h>
+#include <molpro/linalg/array/ArrayHandlerIterableSparse.h>
+#include <molpro/linalg/array/ArrayHandlerSparse.h>
+#include <molpro/linalg/array/util/Distribution.h>
+#include <molpro/linalg/itsolv/subspace/gram_schmidt.h>
+
+namespace {
+using Vec = std::vector<double>;
+using PMap = std::map<size_t, double>;
+namespace la = molpro::linalg::array;
+namespace its = molpro::linalg::itsolv;
+using itsolv_b200::harness::now_seconds;
+using itsolv_b200::harness::trace;
+
+thread_local std::string g_error;
+
+//! The reference handler plus a record of every number it returns to the solver.
+class TracingIterable : public la::ArrayHandlerIterable<Vec, Vec> {
+public:
+  using Base = la::ArrayHandlerIterable<Vec, Vec>;
+  double dot(const Vec& x, const Vec& y) override {
+    double d = Base::dot(x, y);
+    trace().record('d', 1, 1, &d);
+    return d;
+  }
+  Matrix<double> gemm_inner(const CVecRef<Vec>& xx, const CVecRef<Vec>& yy) override {
+    // gemm_inner_default with the non-virtual dot, so that only the Gram matrix is recorded
+    auto mat = Matrix<double>({xx.size(), yy.size()});
+    for (size_t i = 0; i < mat.rows(); ++i)
+      for (size_t j = 0; j < mat.cols(); ++j)
+        mat(i, j) = Base::dot(xx.at(i).get(), yy.at(j).get());
+    trace().record('g', mat.rows(), mat.cols(), mat.data().data());
+    return mat;
+  }
+};
+
+class TracingIterableSparse : public la::ArrayHandlerIterableSparse<Vec, PMap> {
+public:
+  using Base = la::ArrayHandlerIterableSparse<Vec, PMap>;
+  double dot(const Vec& x, const PMap& y) override {
+    double d = Base::dot(x, y);
+    trace().record('d', 1, 1, &d);
+    return d;
+  }
+  Matrix<double> gemm_inner(const CVecRef<Vec>& xx, const CVecRef<PMap>& yy) override {
+    auto mat = Matrix<double>({xx.size(), yy.size()});
+    for (size_t i = 0; i < mat.rows(); ++i)
+      for (size_t j = 0; j < mat.cols(); ++j)
+        mat(i, j) = Base::dot(xx.at(i).get(), yy.at(j).get());
+    trace().record('g', mat.rows(), mat.cols(), mat.data().data());
+    return mat;
+  }
+};
+
+inline double band_entry(int64_t i, int64_t j, double eps) {
+  return i == j ? double(i + 1) : eps * double(1 + ((i + j) % 7));
+}
+
+/*!
+ * CPU twin of the harness operator: A(i,i) = i+1, A(i,j) = eps*(1 + (i+j) mod 7) for 0 < |i-j| <= b.
+ * Row sums run over ascending j with a separate multiply and add, the order the CUDA kernel uses.
+ */
+class BandedProblemHost : public its::Problem<Vec> {
+public:
+  BandedProblemHost(int64_t n, int b, double eps) : n(n), b(b), eps(eps) {}
+  const int64_t n;
+  const int b;
+  const double eps;
+  mutable double seconds_action = 0, seconds_precond = 0;
+
+  void apply(const Vec& v, Vec& a) const {
+    for (int64_t i = 0; i < n; ++i) {
+      double acc = 0;
+      const int64_t lo = std::max<int64_t>(0, i - b), hi = std::min<int64_t>(n - 1, i + b);
+      for (int64_t j = lo; j <= hi; ++j) {
+        const double t = band_entry(i, j, eps) * v[j];
+        acc = acc + t;
+      }
+      a[i] = acc;
+    }
+  }
+  void action(const CVecRef<Vec>& parameters, const VecRef<Vec>& actions) const override {
+    const double t0 = now_seconds();
+    for (size_t k = 0; k < parameters.size(); ++k)
+      apply(parameters[k].get(), actions[k].get());
+    seconds_action += now_seconds() - t0;
+  }
+  bool diagonals(Vec& d) const override {
+    for (int64_t i = 0; i < n; ++i)
+      d[i] = double(i + 1);
+    return true;
+  }
+  void precondition(const VecRef<Vec>& residual, const std::vector<double>& shift, const Vec& diagonals) const override {
+    const double t0 = now_seconds();
+    its::precondition_default(residual, shift, diagonals); // reference IterativeSolver.h:46-55
+    seconds_precond += now_seconds() - t0;
+  }
+  //! residual of the quadratic form used for DIIS: r = A (v - 1), value = (v-1).r / 2 (cf. examples/ExampleProblem.h:24-34)
+  double residual(const Vec& v, Vec& a) const override {
+    const double t0 = now_seconds();
+    Vec shifted(v.size());
+    for (size_t i = 0; i < v.size(); ++i)
+      shifted[i] = v[i] - 1;
+    apply(shifted, a);
+    double value = 0;
+    for (size_t i = 0; i < v.size(); ++i)
+      value += 0.5 * a[i] * shifted[i];
+    seconds_action += now_seconds() - t0;
+    return value;
+  }
+  std::vector<double> pp_action_matrix(const std::vector<PMap>& pparams) const override {
+    std::vector<double> result(pparams.size() * pparams.size(), 0);
+    size_t ij = 0;
+    for (const auto& pi : pparams)
+      for (const auto& pj : pparams) {
+        for (const auto& pie : pi)
+          for (const auto& pje : pj)
+            if (std::llabs(int64_t(pje.first) - int64_t(pie.first)) <= b)
+              result[ij] += band_entry(pje.first, pie.first, eps) * pje.second * pie.second;
+        ij++;
+      }
+    return result;
+  }
+  void p_action(const std::vector<std::vector<double>>& p_coefficients, const CVecRef<PMap>& pparams,
+                const VecRef<Vec>& actions) const override {
+    for (size_t k = 0; k < p_coefficients.size(); k++) {
+      auto& a = actions[k].get();
+      for (size_t pindex = 0; pindex < pparams.size(); pindex++)
+        for (const auto& pie : pparams[pindex].get()) {
+          const double coeff = pie.second * p_coefficients[k][pindex];
+          const int64_t c = int64_t(pie.first);
+          for (int64_t i = std::max<int64_t>(0, c - b); i <= std::min<int64_t>(n - 1, c + b); ++i) {
+            const double t = band_entry(i, c, eps) * coeff;
+            a[i] = a[i] + t;
+          }
+        }
+    }
+  }
+  static double rhs_solution(int k, int64_t i) { return 1.0 + double((i + k) % (k + 3)) / double(k + 3); }
+  void make_rhs(int k, Vec& out) const {
+    Vec u(n);
+    for (int64_t i = 0; i < n; ++i)
+      u[i] = rhs_solution(k, i);
+    apply(u, out);
+  }
+};
+
+//! The reference's own example problem (examples/ExampleProblem.h:6-44), plus what the driver template expects.
+class ExampleProblemHost : public ExampleProblem {
+public:
+  explicit ExampleProblemHost(size_t n) : ExampleProblem(n) {}
+  mutable double seconds_action = 0, seconds_precond = 0;
+  void make_rhs(int k, Vec& out) const {
+    Vec u(n);
+    for (size_t i = 0; i < n; ++i)
+      u[i] = BandedProblemHost::rhs_solution(k, int64_t(i));
+    ExampleProblem::action(its::cwrap_arg(u), its::wrap_arg(out));
+  }
+};
+
+template <class ProblemT>
+struct HostBackend {
+  using R = Vec;
+  ProblemT& prob;
+  size_t n;
+  std::shared_ptr<its::ArrayHandlers<Vec, Vec, PMap>> h;
+  HostBackend(ProblemT& p, size_t n) : prob(p), n(n) {
+    auto dense = std::make_shared<TracingIterable>();
+    auto sparse = std::make_shared<TracingIterableSparse>();
+    h = std::make_shared<its::ArrayHandlers<Vec, Vec, PMap>>(dense, dense, std::make_shared<la::ArrayHandlerSparse<PMap, PMap>>(),
+                                                             dense, sparse, dense, sparse);
+  }
+  auto handlers() { return h; }
+  Vec make_vector() { return Vec(n, 0.0); }
+  void export_local(const Vec& v, double* out) { std::copy(v.begin(), v.end(), out); }
+  size_t n_local() { return n; }
+  ProblemT& problem() { return prob; }
+  void synchronize() {}
+};
+
+Vec to_vec(const double* p, size_t n) { return Vec(p, p + n); }
+PMap to_map(const int64_t* idx, const double* val, int nnz) {
+  PMap m;
+  for (int i = 0; i < nnz; ++i)
+    m[size_t(idx[i])] = val[i];
+  return m;
+}
+} // namespace
+
+extern "C" {
+
+const char* ref_last_error() { return g_error.c_str(); }
+
+//! Reference solve() on std::vector containers; same spec/result structs as the product harness.
+int ref_solve(const itsolv_solve_spec* spec, itsolv_solve_result* result, double* solutions) {
+  try {
+    if (spec->problem == ITSOLV_PROBLEM_EXAMPLE) {
+      ExampleProblemHost problem(spec->n);
+      HostBackend<ExampleProblemHost> backend(problem, spec->n);
+      return itsolv_b200::harness::run_solve(*spec, backend, *result, solutions);
+    }
+    BandedProblemHost problem(spec->n, spec->half_bandwidth, spec->eps);
+    HostBackend<BandedProblemHost> backend(problem, spec->n);
+    return itsolv_b200::harness::run_solve(*spec, backend, *result, solutions);
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return 1;
+  }
+}
+
+size_t ref_trace_entries() { return trace().entries.size(); }
+size_t ref_trace_values() { return trace().values.size(); }
+void ref_trace_read(itsolv_trace_entry* entries, double* values) {
+  std::copy(trace().entries.begin(), trace().entries.end(), entries);
+  std::copy(trace().values.begin(), trace().values.end(), values);
+}
+
+void ref_banded_apply(int64_t n, int b, double eps, const double* v, double* a) {
+  BandedProblemHost p(n, b, eps);
+  Vec vv = to_vec(v, n), aa(n);
+  p.apply(vv, aa);
+  std::copy(aa.begin(), aa.end(), a);
+}
+
+/* ---- the handler contract, called on the reference's ArrayHandlerIterable (vectors are packed row after row) ---- */
+
+double ref_handler_dot(size_t n, const double* x, const double* y) {
+  la::ArrayHandlerIterable<Vec, Vec> h;
+  return h.dot(to_vec(x, n), to_vec(y, n));
+}
+void ref_handler_axpy(size_t n, double alpha, const double* x, double* y) {
+  la::ArrayHandlerIterable<Vec, Vec> h;
+  Vec yy = to_vec(y, n);
+  h.axpy(alpha, to_vec(x, n), yy);
+  std::copy(yy.begin(), yy.end(), y);
+}
+void ref_handler_scal(size_t n, double alpha, double* x) {
+  la::ArrayHandlerIterable<Vec, Vec> h;
+  Vec xx = to_vec(x, n);
+  h.scal(alpha, xx);
+  std::copy(xx.begin(), xx.end(), x);
+}
+void ref_handler_gemm_inner(int k, int m, size_t n, const double* X, const double* Y, double* out) {
+  la::ArrayHandlerIterable<Vec, Vec> h;
+  std::vector<Vec> xs, ys;
+  for (int i = 0; i < k; ++i)
+    xs.push_back(to_vec(X + size_t(i) * n, n));
+  for (int j = 0; j < m; ++j)
+    ys.push_back(to_vec(Y + size_t(j) * n, n));
+  auto mat = h.gemm_inner(its::cwrap(xs), its::cwrap(ys));
+  std::copy(mat.data().begin(), mat.data().end(), out);
+}
+void ref_handler_gemm_outer(int k, int m, size_t n, const double* alpha, const double* X, double* Y) {
+  la::ArrayHandlerIterable<Vec, Vec> h;
+  std::vector<Vec> xs, ys;
+  for (int i = 0; i < k; ++i)
+    xs.push_back(to_vec(X + size_t(i) * n, n));
+  for (int j = 0; j < m; ++j)
+    ys.push_back(to_vec(Y + size_t(j) * n, n));
+  Matrix<double> a(Vec(alpha, alpha + size_t(k) * m), {size_t(k), size_t(m)});
+  h.gemm_outer(a, its::cwrap(xs), its::wrap(ys));
+  for (int j = 0; j < m; ++j)
+    std::copy(ys[j].begin(), ys[j].end(), Y + size_t(j) * n);
+}
+int ref_handler_select(size_t nsel, size_t n, const double* x, int max, int ignore_sign, int64_t* idx, double* val) {
+  la::ArrayHandlerIterable<Vec, Vec> h;
+  auto sel = h.select(nsel, to_vec(x, n), max != 0, ignore_sign != 0);
+  int c = 0;
+  for (const auto& s : sel) {
+    idx[c] = int64_t(s.first);
+    val[c] = s.second;
+    ++c;
+  }
+  return c;
+}
+int ref_handler_select_max_dot(size_t nsel, size_t n, const double* x, const double* y, int64_t* idx, double* val) {
+  la::ArrayHandlerIterable<Vec, Vec> h;
+  auto sel = h.select_max_dot(nsel, to_vec(x, n), to_vec(y, n));
+  int c = 0;
+  for (const auto& s : sel) {
+    idx[c] = int64_t(s.first);
+    val[c] = s.second;
+    ++c;
+  }
+  return c;
+}
+//! precondition_default for iterable containers, reference IterativeSolver.h:46-55
+void ref_precondition_default(int w, size_t n, double* r, const double* shift, const double* diag) {
+  std::vector<Vec> rs;
+  for (int i = 0; i < w; ++i)
+    rs.push_back(to_vec(r + size_t(i) * n, n));
+  its::precondition_default(its::wrap(rs), std::vector<double>(shift, shift + w), to_vec(diag, n));
+  for (int i = 0; i < w; ++i)
+    std::copy(rs[i].begin(), rs[i].end(), r + size_t(i) * n);
+}
+//! subspace::util::modified_gram_schmidt, reference subspace/gram_schmidt.h:128-145
+int ref_modified_gram_schmidt(int nvec, size_t n, double* data, double thresh, int* null_idx) {
+  la::ArrayHandlerIterable<Vec, Vec> h;
+  std::vector<Vec> ps;
+  for (int i = 0; i < nvec; ++i)
+    ps.push_back(to_vec(data + size_t(i) * n, n));
+  auto w = its::wrap(ps);
+  auto nulls = its::subspace::util::modified_gram_schmidt(w, h, thresh);
+  for (int i = 0; i < nvec; ++i)
+    std::copy(ps[i].begin(), ps[i].end(), data + size_t(i) * n);
+  for (size_t i = 0; i < nulls.size(); ++i)
+    null_idx[i] = int(nulls[i]);
+  return int(nulls.size());
+}
+
+/* ---- dense x sparse (P-space) handler: ArrayHandlerIterableSparse<vector, map>; maps are CSR-packed ---- */
+
+void ref_sparse_copy(size_t n, double* x, int nnz, const int64_t* idx, const double* val) {
+  la::ArrayHandlerIterableSparse<Vec, PMap> h;
+  Vec xx = to_vec(x, n);
+  h.copy(xx, to_map(idx, val, nnz));
+  std::copy(xx.begin(), xx.end(), x);
+}
+void ref_sparse_gemm_inner(int k, int m, size_t n, const double* X, const int* map_ptr, const int64_t* idx,
+                           const double* val, double* out) {
+  la::ArrayHandlerIterableSparse<Vec, PMap> h;
+  std::vector<Vec> xs;
+  std::vector<PMap> ps;
+  for (int i = 0; i < k; ++i)
+    xs.push_back(to_vec(X + size_t(i) * n, n));
+  for (int j = 0; j < m; ++j)
+    ps.push_back(to_map(idx + map_ptr[j], val + map_ptr[j], map_ptr[j + 1] - map_ptr[j]));
+  auto mat = h.gemm_inner(its::cwrap(xs), its::cwrap(ps));
+  std::copy(mat.data().begin(), mat.data().end(), out);
+}
+//! alphas is (number of maps) x (number of dense vectors): rows <-> xx (maps), columns <-> yy (dense)
+void ref_sparse_gemm_outer(int nmap, int ndense, size_t n, const double* alpha, const int* map_ptr, const int64_t* idx,
+                           const double* val, double* Y) {
+  la::ArrayHandlerIterableSparse<Vec, PMap> h;
+  std::vector<Vec> ys;
+  std::vector<PMap> ps;
+  for (int j = 0; j < ndense; ++j)
+    ys.push_back(to_vec(Y + size_t(j) * n, n));
+  for (int i = 0; i < nmap; ++i)
+    ps.push_back(to_map(idx + map_ptr[i], val + map_ptr[i], map_ptr[i + 1] - map_ptr[i]));
+  Matrix<double> a(Vec(alpha, alpha + size_t(nmap) * ndense), {size_t(nmap), size_t(ndense)});
+  h.gemm_outer(a, its::cwrap(ps), its::wrap(ys));
+  for (int j = 0; j < ndense; ++j)
+    std::copy(ys[j].begin(), ys[j].end(), Y + size_t(j) * n);
+}
+
+//! util::make_distribution_spread_remainder, reference array/util/Distribution.h:99-110; borders has nproc+1 entries
+void ref_distribution(size_t n, int nproc, int64_t* borders) {
+  auto d = la::util::make_distribution_spread_remainder<size_t>(n, nproc);
+  for (int i = 0; i <= nproc; ++i)
+    borders[i] = int64_t(d.chunk_borders()[i]);
+}
+
+/*
+ * Per-op timing of the reference CPU handler (bench.py cpu_baseline): op 0 dot, 1 axpy, 2 scal, 3 gemm_inner[k x m],
+ * 4 gemm_outer[k x m]. Vectors are allocated and filled outside the timed region. Returns seconds per call.
+ */
+double ref_time_handler_op(int op, size_t n, int k, int m, int reps) {
+  la::ArrayHandlerIterable<Vec, Vec> h;
+  std::vector<Vec> xs(std::max(k, 1), Vec(n)), ys(std::max(m, 1), Vec(n));
+  for (size_t v = 0; v < xs.size(); ++v)
+    for (size_t i = 0; i < n; ++i)
+      xs[v][i] = 1.0 / double(1 + (i + v) % 97);
+  for (size_t v = 0; v < ys.size(); ++v)
+    for (size_t i = 0; i < n; ++i)
+      ys[v][i] = 1.0 / double(1 + (i + 3 * v) % 89);
+  Matrix<double> alpha({size_t(std::max(k, 1)), size_t(std::max(m, 1))});
+  alpha.fill(1e-3);
+  volatile double sink = 0;
+  const double t0 = now_seconds();
+  for (int r = 0; r < reps; ++r) {
+    switch (op) {
+    case 0:
+      sink = sink + h.dot(xs[0], ys[0]);
+      break;
+    case 1:
+      h.axpy(1e-3, xs[0], ys[0]);
+      break;
+    case 2:
+      h.scal(1.0000001, ys[0]);
+      break;
+    case 3:
+      sink = sink + h.gemm_inner(its::cwrap(xs), its::cwrap(ys))(0, 0);
+      break;
+    case 4:
+      h.gemm_outer(alpha, its::cwrap(xs), its::wrap(ys));
+      break;
+    default:
+      return -1;
+    }
+  }
+  return (now_seconds() - t0) / reps;
+}
+
+} // extern "C"
