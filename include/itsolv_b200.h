@@ -1,0 +1,158 @@
+/*
+ * itsolv_b200 — C ABI of the B200 (sm_100a) vector backend for molpro::linalg::itsolv.
+ *
+ * Every entry point below is what the reference's ArrayHandler contract
+ * (reference src/molpro/linalg/array/ArrayHandler.h:184-222) needs from a device: plain pointers and sizes, no C++
+ * types, no allocation on the hot path, no CPU fallback. The C++ host layer (iterative_solver_b200/host/
+ * ArrayHandlerCUDA.h) is a thin adaptor from the contract's containers to these calls; a foreign host (C, Fortran,
+ * Python ctypes) can bind them directly.
+ *
+ * Conventions
+ *   - all vectors are FP64, device resident, LOCAL shards of length n (rows owned by the calling rank);
+ *   - "xx"/"yy" are HOST arrays of DEVICE pointers (the Q/R vectors are separate allocations,
+ *     reference itsolv/subspace/QSpace.h:157), 1 <= k,m <= ITSOLV_MAX_PANEL per call;
+ *   - small matrices (Gram results, alphas, shifts) are HOST, row-major, exactly the layout of the reference's
+ *     Matrix<double> (reference itsolv/subspace/Matrix.h:59);
+ *   - calls that return numbers to the host (dot, gemm_inner, select) finish the work on the context's stream,
+ *     all-reduce over the context's communicator when one is attached (the reference's MPI_Allreduce sites,
+ *     array/util/gemm.h:179-182, DistrArray.cpp:134-136) and synchronise; every other call is asynchronous on the stream;
+ *   - return value 0 = success; otherwise itsolv_last_error() describes the failure (thread local).
+ */
+#ifndef ITSOLV_B200_H
+#define ITSOLV_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ITSOLV_MAX_PANEL 128     /* vectors per side of one gemm_inner / gemm_outer launch */
+#define ITSOLV_UNIQUE_ID_BYTES 128
+
+typedef struct itsolv_ctx itsolv_ctx;
+
+/* ---- context: one per process/GPU. Owns a stream, the partial-sum workspace, pinned result buffers ---- */
+int itsolv_ctx_create(int device, itsolv_ctx** ctx);
+/* as above but all work is issued on the caller's cudaStream_t (e.g. torch's current stream) */
+int itsolv_ctx_create_on_stream(int device, void* cuda_stream, itsolv_ctx** ctx);
+void itsolv_ctx_destroy(itsolv_ctx* ctx);
+const char* itsolv_last_error(void);
+void* itsolv_ctx_stream(itsolv_ctx* ctx);
+int itsolv_ctx_device(itsolv_ctx* ctx);
+int itsolv_ctx_synchronize(itsolv_ctx* ctx);
+/* tuning knob (also read from the environment variable ITSOLV_<NAME> at context creation); returns previous value */
+int itsolv_ctx_set_option(itsolv_ctx* ctx, const char* name, int value);
+
+/* ---- accounting: launches of this library's kernels, algorithmic bytes and, when profiling is
+ * enabled, device time measured with CUDA events on the context's stream around every call ---- */
+typedef struct itsolv_counters {
+  int64_t launches;
+  int64_t n_dot, n_axpy, n_scal, n_copy, n_fill, n_gemm_inner, n_gemm_outer, n_precondition, n_select, n_sparse;
+  double bytes;          /* algorithmic bytes of all calls */
+  double device_seconds; /* only while profiling */
+  double bytes_gemm_inner, seconds_gemm_inner;
+  double bytes_gemm_outer, seconds_gemm_outer;
+  double bytes_blas1, seconds_blas1;
+} itsolv_counters;
+void itsolv_ctx_counters(itsolv_ctx* ctx, itsolv_counters* out);
+void itsolv_ctx_reset_counters(itsolv_ctx* ctx);
+void itsolv_ctx_set_profiling(itsolv_ctx* ctx, int enabled);
+/* CUDA-event stopwatch on the context's stream */
+int itsolv_ctx_timer_start(itsolv_ctx* ctx);
+int itsolv_ctx_timer_stop(itsolv_ctx* ctx, double* milliseconds);
+
+/* ---- memory: stream-ordered pool (no cudaMalloc/cudaFree on the hot path; the reference churns 2w Q vectors per
+ * iteration, itsolv/subspace/QSpace.h:80-84) ---- */
+int itsolv_alloc(itsolv_ctx* ctx, size_t n, double** out);
+int itsolv_free(itsolv_ctx* ctx, double* p);
+int itsolv_upload(itsolv_ctx* ctx, double* dst_device, const double* src_host, size_t n);   /* synchronous */
+int itsolv_download(itsolv_ctx* ctx, double* dst_host, const double* src_device, size_t n); /* synchronous */
+int itsolv_mem_info(itsolv_ctx* ctx, size_t* free_bytes, size_t* total_bytes);
+
+/* ---- communicator: row-sharded vectors, one rank per GPU; replaces the reference's MPI communicator
+ * (array/DistrArray.h:100,109). The unique id is created on rank 0 and broadcast by the host (torch.distributed, MPI, ...) ---- */
+int itsolv_comm_unique_id(void* id /* ITSOLV_UNIQUE_ID_BYTES */);
+int itsolv_comm_init(itsolv_ctx* ctx, int rank, int nranks, const void* id);
+int itsolv_comm_rank(itsolv_ctx* ctx);
+int itsolv_comm_size(itsolv_ctx* ctx);
+int itsolv_comm_barrier(itsolv_ctx* ctx);
+/* in-place sum / max of a small HOST array over all ranks (through a device staging buffer) */
+int itsolv_comm_allreduce_host(itsolv_ctx* ctx, double* values, size_t count, int op_max);
+/* exchange of `count` doubles with the neighbouring ranks (harness halo): send_lo goes to rank-1, send_hi to rank+1 */
+int itsolv_comm_halo_exchange(itsolv_ctx* ctx, const double* send_lo, const double* send_hi, double* recv_lo,
+                              double* recv_hi, size_t count);
+/* chunk borders of util::make_distribution_spread_remainder (reference array/util/Distribution.h:99-110); borders[nranks+1] */
+void itsolv_distribution(size_t n, int nranks, int64_t* borders);
+
+/* ---- BLAS-1 part of the contract (reference ArrayHandler.h:186-190; CPU path ArrayHandlerIterable.h:46-82) ---- */
+int itsolv_fill_f64(itsolv_ctx* ctx, double alpha, double* x, size_t n);
+int itsolv_scal_f64(itsolv_ctx* ctx, double alpha, double* x, size_t n);
+int itsolv_copy_f64(itsolv_ctx* ctx, double* dst, const double* src, size_t n);
+/* y[i] = y[i] + alpha*x[i], product and sum rounded separately as the reference's std::transform does */
+int itsolv_axpy_f64(itsolv_ctx* ctx, double alpha, const double* x, double* y, size_t n);
+int itsolv_dot_f64(itsolv_ctx* ctx, const double* x, const double* y, size_t n, double* result);
+
+/* ---- panel contractions (reference ArrayHandler.h:195,200; CPU path array/util/gemm.h:157-203, 258-279) ---- */
+/* out[i*m+j] = sum_r xx[i][r]*yy[j][r]; each HBM byte of the k+m vectors is read once */
+int itsolv_gemm_inner_f64(itsolv_ctx* ctx, const double* const* xx, int k, const double* const* yy, int m, size_t n,
+                          double* out);
+/* yy[j] += sum_i alpha[i*m+j]*xx[i] (i ascending, as the reference's loop); beta_zero!=0: yy[j] = sum (yy not read) */
+int itsolv_gemm_outer_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* xx,
+                          double* const* yy, size_t n, int beta_zero);
+
+/* ---- Davidson diagonal preconditioner (reference itsolv/IterativeSolver.h:46-55):
+ * r_k[i] = r_k[i] / (diag[i] - shift[k] + 1e-15), w vectors in one pass over diag ---- */
+int itsolv_precondition_f64(itsolv_ctx* ctx, double* const* r, int w, const double* diag, const double* shift, size_t n);
+
+/* ---- select / select_max_dot (reference array/util/select.h:28-55, ArrayHandler.h:212,222): the nsel entries that are
+ * largest under the reference's (key, index) pair ordering, key = max ? v : -v (|v| when ignore_sign); for
+ * select_max_dot pass y != NULL: v = |x[i]*y[i]|, max. Indices are global (global_offset + local). With a communicator
+ * the candidates of all ranks are merged, every rank receives the same list. Output sorted by index. ---- */
+int itsolv_select_f64(itsolv_ctx* ctx, const double* x, const double* y, size_t n, size_t global_offset, size_t nsel,
+                      int max, int ignore_sign, int64_t* indices, double* values, int* nfound);
+/* host-side merge used by the call above; exported for tests: candidates (idx,val) from all ranks -> best nsel */
+int itsolv_select_merge(const int64_t* idx, const double* val, size_t ncand, size_t nsel, int max, int ignore_sign,
+                        int64_t* out_idx, double* out_val);
+
+/* ---- dense x sparse (P-space) ops (reference ArrayHandlerIterableSparse.h:35-63, ArrayHandlerDistrSparse.h:30-65,
+ * array/util/gemm.h:207-253). Sparse vectors are std::map<size_t,double> packed CSR-like on the HOST:
+ * map_ptr[nmap+1], idx[] GLOBAL indices, val[]; entries outside [global_offset, global_offset+n) are skipped ---- */
+/* x = 0; x[idx-global_offset] = val */
+int itsolv_sparse_copy_f64(itsolv_ctx* ctx, double* x, size_t n, size_t global_offset, int nnz, const int64_t* idx,
+                           const double* val);
+/* out[i*nmap+j] = sum_e xx[i][idx_e]*val_e over map j */
+int itsolv_sparse_gemm_inner_f64(itsolv_ctx* ctx, const double* const* xx, int k, size_t n, size_t global_offset,
+                                 int nmap, const int32_t* map_ptr, const int64_t* idx, const double* val, double* out);
+/* yy[j][idx_e] += alpha[i*ndense+j]*val_e for every entry e of map i (alpha is nmap x ndense) */
+int itsolv_sparse_gemm_outer_f64(itsolv_ctx* ctx, const double* alpha, int nmap, int ndense, const int32_t* map_ptr,
+                                 const int64_t* idx, const double* val, double* const* yy, size_t n,
+                                 size_t global_offset);
+
+/* ---- harness operator kernels (the user's Problem::action, reference itsolv/IterativeSolver.h:100; not part of the
+ * measured subspace path). Synthetic banded operator of SURVEY.md section 8(d):
+ * A(i,i)=i+1, A(i,j)=eps*(1+((i+j) mod 7)) for 0<|i-j|<=b. x_lo/x_hi: b halo rows from the neighbouring shards
+ * (NULL at the global ends). ---- */
+int itsolv_banded_apply_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offset, size_t n, int b, double eps,
+                            const double* x, const double* x_lo, const double* x_hi, double* y);
+/* stored CSR, 64-bit row pointers, columns global and within b of the local range */
+int itsolv_csr_apply_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offset, size_t n, int b, const int64_t* row_ptr,
+                         const int32_t* col, const double* val, const double* x, const double* x_lo, const double* x_hi,
+                         double* y);
+/* d[i] = row_offset+i+1 ; fills a vector with f(global index): kind 0 = diagonal, 1 = rhs_solution(k) (harness RHS generator) */
+int itsolv_banded_fill_f64(itsolv_ctx* ctx, int kind, int k, int64_t row_offset, size_t n, double* out);
+/* P-space part of the action (reference Problem::p_action, itsolv/IterativeSolver.h:160-171; example
+ * examples/ExampleProblemDistrArray.h:100-116): actions[k] += sum_p pcoef[k*nP+p] * A * P_p for the banded operator */
+int itsolv_banded_p_action_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offset, size_t n, int b, double eps,
+                               int nact, double* const* actions, int nP, const int32_t* map_ptr, const int64_t* idx,
+                               const double* val, const double* pcoef);
+/* dense toy operator of the reference's examples/ExampleProblem.h:8 (single rank, small n): y = M x,
+ * M(i,j) = i==j ? i+1 : 0.001*((i+j) mod n) */
+int itsolv_example_apply_f64(itsolv_ctx* ctx, size_t n, const double* x, double* y);
+/* out[i] = x[i] + c */
+int itsolv_shift_f64(itsolv_ctx* ctx, double c, const double* x, double* out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -72,24 +72,59 @@ typedef struct itsolv_trace_entry {
   int64_t offset; /* into the value array */
 } itsolv_trace_entry;
 
-/*
- * Run one solve on the calling rank's GPU (all ranks of the communicator call it collectively).
- * solutions: optional host buffer, nroots * n_local doubles, receives this rank's rows of each solution vector.
- * Returns 0 on success, non-zero on error (message via itsolv_last_error()).
- */
-int itsolv_harness_solve(const itsolv_solve_spec* spec, itsolv_solve_result* result, double* solutions);
+struct itsolv_ctx; /* include/itsolv_b200.h */
 
 /*
- * End-to-end entry: the caller owns the operator on the HOST as CSR (row_ptr[n_local+1], col[nnz] global column
- * indices, val[nnz]) plus its diagonal; the call uploads it, solves, and downloads eigenvalues and solution vectors.
+ * Run one solve on the context's GPU (all ranks of the context's communicator call it collectively).
+ * solutions: optional host buffer, nroots * n_local doubles, receives this rank's rows of each solution vector.
+ * Returns 0 on success, non-zero on error (message via itsolv_harness_last_error()).
  */
-int itsolv_harness_solve_host_csr(const itsolv_solve_spec* spec, const int64_t* row_ptr, const int32_t* col,
-                                  const double* val, const double* diag, itsolv_solve_result* result,
-                                  double* solutions);
+int itsolv_harness_solve(struct itsolv_ctx* ctx, const itsolv_solve_spec* spec, itsolv_solve_result* result,
+                         double* solutions);
+
+/*
+ * End-to-end entry: the caller owns the operator on the HOST as CSR (row_ptr[n_local+1] relative to this rank's first
+ * row, col[nnz] global column indices within half_bandwidth of the local rows, val[nnz]) plus its diagonal; the call
+ * uploads it, solves with the stored-CSR SpMV, and downloads eigenvalues/errors and the solution vectors.
+ */
+int itsolv_harness_solve_host_csr(struct itsolv_ctx* ctx, const itsolv_solve_spec* spec, const int64_t* row_ptr,
+                                  const int32_t* col, const double* val, const double* diag,
+                                  itsolv_solve_result* result, double* solutions);
+const char* itsolv_harness_last_error(void);
 
 size_t itsolv_harness_trace_entries(void);
 size_t itsolv_harness_trace_values(void);
 void itsolv_harness_trace_read(itsolv_trace_entry* entries, double* values);
+
+/*
+ * The handler contract exercised through the C++ plugin classes (DistrArrayCUDA + ArrayHandlerCUDA /
+ * ArrayHandlerCUDASparse) with HOST buffers: vectors are packed row after row (X is k*n doubles, GLOBAL length n;
+ * each rank uploads its own shard and, for outputs, writes back its own rows only). These mirror, call for call, the
+ * ref_handler_* entry points of the oracle build (oracle/ref_driver.cpp), so a parity test runs the same inputs through both.
+ */
+int itsolv_handler_blas1(struct itsolv_ctx* ctx, int op /*0 dot 1 axpy 2 scal 3 fill 4 copy*/, size_t n, double alpha,
+                         const double* x, double* y, double* result);
+int itsolv_handler_gemm_inner(struct itsolv_ctx* ctx, int k, int m, size_t n, const double* X, const double* Y,
+                              int y_is_x, double* out);
+int itsolv_handler_gemm_outer(struct itsolv_ctx* ctx, int k, int m, size_t n, const double* alpha, const double* X,
+                              double* Y);
+int itsolv_handler_select(struct itsolv_ctx* ctx, size_t nsel, size_t n, const double* x, const double* y_or_null,
+                          int max, int ignore_sign, int64_t* idx, double* val);
+/* Problem::precondition of the harness problem (reference IterativeSolver.h:135-137) */
+int itsolv_handler_precondition(struct itsolv_ctx* ctx, int w, size_t n, double* r, const double* shift,
+                                const double* diag);
+/* the reference's own subspace::util::modified_gram_schmidt (subspace/gram_schmidt.h:128-145) run on the CUDA handler */
+int itsolv_handler_modified_gram_schmidt(struct itsolv_ctx* ctx, int nvec, size_t n, double* data, double thresh,
+                                         int* null_idx);
+int itsolv_handler_sparse_copy(struct itsolv_ctx* ctx, size_t n, double* x, int nnz, const int64_t* idx,
+                               const double* val);
+int itsolv_handler_sparse_gemm_inner(struct itsolv_ctx* ctx, int k, int m, size_t n, const double* X,
+                                     const int32_t* map_ptr, const int64_t* idx, const double* val, double* out);
+int itsolv_handler_sparse_gemm_outer(struct itsolv_ctx* ctx, int nmap, int ndense, size_t n, const double* alpha,
+                                     const int32_t* map_ptr, const int64_t* idx, const double* val, double* Y);
+/* harness operator on host vectors (single rank: whole vector; multi rank: global x in, this rank's rows of y out) */
+int itsolv_harness_banded_apply(struct itsolv_ctx* ctx, int64_t n, int b, double eps, int explicit_csr, const double* x,
+                                double* y);
 
 /* Host subspace algebra entry points (restated helper, reference helper-implementation.h:318-543), exported for tests */
 int itsolv_host_eigenproblem(const double* matrix, const double* metric, size_t dimension, int hermitian,

@@ -1,0 +1,188 @@
+"""Python face of the C ABI (include/itsolv_b200.h): a Context bound to one GPU and thin methods that pass device
+pointers of torch tensors to the CUDA kernels. torch is used for device memory and streams only; every operation below
+runs in libitsolv_b200.so, and raises if that library or a Blackwell GPU is missing."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _native as N
+
+
+class BackendError(RuntimeError):
+    pass
+
+
+def _ptr(t) -> int:
+    """device pointer of a torch tensor (float64, contiguous, 1-D) or a raw integer address"""
+    if isinstance(t, int):
+        return t
+    if t.dtype.__str__() != "torch.float64" or not t.is_cuda or not t.is_contiguous():
+        raise TypeError("expected a contiguous CUDA float64 tensor")
+    return t.data_ptr()
+
+
+def _ptr_array(ts: Sequence) -> C.Array:
+    arr = (C.c_void_p * max(1, len(ts)))()
+    for i, t in enumerate(ts):
+        arr[i] = _ptr(t)
+    return arr
+
+
+def _dbl(a: np.ndarray):
+    return a.ctypes.data_as(N.c_double_p)
+
+
+class Context:
+    """One per process and GPU: stream, workspaces, optional NCCL communicator (row-sharded vectors)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = N.kernels()
+        h = C.c_void_p()
+        rc = (self.lib.itsolv_ctx_create(device, C.byref(h)) if stream is None else
+              self.lib.itsolv_ctx_create_on_stream(device, C.c_void_p(stream), C.byref(h)))
+        if rc:
+            raise BackendError(self.lib.itsolv_last_error().decode())
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.itsolv_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc:
+            raise BackendError(self.lib.itsolv_last_error().decode())
+
+    # ---- plumbing
+    @property
+    def stream(self) -> int:
+        return int(self.lib.itsolv_ctx_stream(self.handle) or 0)
+
+    def synchronize(self):
+        self._check(self.lib.itsolv_ctx_synchronize(self.handle))
+
+    def set_option(self, name: str, value: int) -> int:
+        return self.lib.itsolv_ctx_set_option(self.handle, name.encode(), int(value))
+
+    def counters(self) -> N.Counters:
+        c = N.Counters()
+        self.lib.itsolv_ctx_counters(self.handle, C.byref(c))
+        return c
+
+    def reset_counters(self):
+        self.lib.itsolv_ctx_reset_counters(self.handle)
+
+    def set_profiling(self, on: bool):
+        self.lib.itsolv_ctx_set_profiling(self.handle, 1 if on else 0)
+
+    def timer_start(self):
+        self._check(self.lib.itsolv_ctx_timer_start(self.handle))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._check(self.lib.itsolv_ctx_timer_stop(self.handle, C.byref(ms)))
+        return ms.value
+
+    def init_comm(self, rank: int, nranks: int, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, N.UNIQUE_ID_BYTES)
+        self._check(self.lib.itsolv_comm_init(self.handle, rank, nranks, buf))
+
+    def unique_id(self) -> bytes:
+        buf = C.create_string_buffer(N.UNIQUE_ID_BYTES)
+        self._check(self.lib.itsolv_comm_unique_id(buf))
+        return buf.raw
+
+    @property
+    def rank(self) -> int:
+        return self.lib.itsolv_comm_rank(self.handle)
+
+    @property
+    def nranks(self) -> int:
+        return self.lib.itsolv_comm_size(self.handle)
+
+    def allreduce_host(self, values: np.ndarray, op_max: bool = False) -> np.ndarray:
+        v = np.ascontiguousarray(values, dtype=np.float64).copy()
+        self._check(self.lib.itsolv_comm_allreduce_host(self.handle, _dbl(v), v.size, 1 if op_max else 0))
+        return v
+
+    # ---- the contract
+    def fill(self, alpha: float, x):
+        self._check(self.lib.itsolv_fill_f64(self.handle, alpha, _ptr(x), x.numel()))
+
+    def scal(self, alpha: float, x):
+        self._check(self.lib.itsolv_scal_f64(self.handle, alpha, _ptr(x), x.numel()))
+
+    def copy(self, dst, src):
+        self._check(self.lib.itsolv_copy_f64(self.handle, _ptr(dst), _ptr(src), src.numel()))
+
+    def axpy(self, alpha: float, x, y):
+        self._check(self.lib.itsolv_axpy_f64(self.handle, alpha, _ptr(x), _ptr(y), x.numel()))
+
+    def dot(self, x, y) -> float:
+        r = C.c_double()
+        self._check(self.lib.itsolv_dot_f64(self.handle, _ptr(x), _ptr(y), x.numel(), C.byref(r)))
+        return r.value
+
+    def gemm_inner(self, xx: Sequence, yy: Sequence, n: int | None = None) -> np.ndarray:
+        k, m = len(xx), len(yy)
+        out = np.zeros((k, m))
+        if k == 0 or m == 0:
+            return out
+        n = xx[0].numel() if n is None else n
+        self._check(self.lib.itsolv_gemm_inner_f64(self.handle, _ptr_array(xx), k, _ptr_array(yy), m, n, _dbl(out)))
+        return out
+
+    def gemm_outer(self, alpha: np.ndarray, xx: Sequence, yy: Sequence, beta_zero: bool = False, n: int | None = None):
+        k, m = len(xx), len(yy)
+        a = np.ascontiguousarray(alpha, dtype=np.float64).reshape(k, m)
+        if m == 0:
+            return
+        n = yy[0].numel() if n is None else n
+        self._check(self.lib.itsolv_gemm_outer_f64(self.handle, _dbl(a), k, m, _ptr_array(xx), _ptr_array(yy), n,
+                                                   1 if beta_zero else 0))
+
+    def precondition(self, residuals: Sequence, diag, shift: Sequence[float]):
+        s = np.ascontiguousarray(shift, dtype=np.float64)
+        self._check(self.lib.itsolv_precondition_f64(self.handle, _ptr_array(residuals), len(residuals), _ptr(diag),
+                                                     _dbl(s), diag.numel()))
+
+    def select(self, x, nsel: int, max: bool = False, ignore_sign: bool = False, y=None, global_offset: int = 0):
+        idx = np.zeros(nsel, dtype=np.int64)
+        val = np.zeros(nsel)
+        found = C.c_int()
+        self._check(self.lib.itsolv_select_f64(self.handle, _ptr(x), _ptr(y) if y is not None else None, x.numel(),
+                                               global_offset, nsel, int(max), int(ignore_sign),
+                                               idx.ctypes.data_as(N.c_int64_p), _dbl(val), C.byref(found)))
+        return idx[:found.value].copy(), val[:found.value].copy()
+
+    def banded_apply(self, x, y, n_global: int, row_offset: int, b: int, eps: float, x_lo=None, x_hi=None):
+        self._check(self.lib.itsolv_banded_apply_f64(self.handle, n_global, row_offset, x.numel(), b, eps, _ptr(x),
+                                                     _ptr(x_lo) if x_lo is not None else None,
+                                                     _ptr(x_hi) if x_hi is not None else None, _ptr(y)))
+
+
+def distribution(n: int, nranks: int) -> np.ndarray:
+    """chunk borders of the reference's make_distribution_spread_remainder (array/util/Distribution.h:99-110)"""
+    b = np.zeros(nranks + 1, dtype=np.int64)
+    N.kernels().itsolv_distribution(n, nranks, b.ctypes.data_as(N.c_int64_p))
+    return b
+
+
+def select_merge(idx: np.ndarray, val: np.ndarray, nsel: int, max: bool = False, ignore_sign: bool = False):
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    oi = np.zeros(nsel, dtype=np.int64)
+    ov = np.zeros(nsel)
+    c = N.kernels().itsolv_select_merge(idx.ctypes.data_as(N.c_int64_p), _dbl(val), idx.size, nsel, int(max),
+                                        int(ignore_sign), oi.ctypes.data_as(N.c_int64_p), _dbl(ov))
+    return oi[:c], ov[:c]

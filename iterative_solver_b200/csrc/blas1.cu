@@ -1,0 +1,218 @@
+// Streaming (BLAS-1) kernels of the handler contract and the Davidson diagonal preconditioner.
+// All are HBM-bound with no reuse: 128-bit coalesced accesses, 4 independent row pairs per thread per trip so that
+// each SM keeps >= 64 KB of loads in flight, grid = a whole number of CTAs per SM (no tail wave).
+// Arithmetic mirrors the reference's CPU loops operation for operation (no FMA contraction) so results are bit-identical
+// to ArrayHandlerIterable (reference src/molpro/linalg/array/ArrayHandlerIterable.h:46-74) and to
+// precondition_default (reference src/molpro/linalg/itsolv/IterativeSolver.h:46-55).
+#include "common.cuh"
+
+namespace itsolv {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+struct PrecondParams {
+  double* r[ITSOLV_MAX_PANEL];
+  double shift[ITSOLV_MAX_PANEL];
+  const double* diag;
+  size_t n;
+  int w;
+};
+
+// ---- generic driver: VEC = all pointers 16-byte aligned -> double2 path for the even prefix, scalar for the last odd row
+template <bool VEC, class OpPair, class OpOne>
+__device__ __forceinline__ void stream_rows(size_t n, OpPair op2, OpOne op1) {
+  const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = size_t(gridDim.x) * blockDim.x;
+  if (VEC) {
+    const size_t npairs = n / 2;
+    size_t p = tid;
+    for (; p + (kUnroll - 1) * nthreads < npairs; p += kUnroll * nthreads) {
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        op2(p + u * nthreads);
+    }
+    for (; p < npairs; p += nthreads)
+      op2(p);
+    if ((n & 1) && tid == 0)
+      op1(n - 1);
+  } else {
+    for (size_t i = tid; i < n; i += nthreads)
+      op1(i);
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 4) fill_kernel(double alpha, double* __restrict__ x, size_t n) {
+  stream_rows<VEC>(
+      n, [&](size_t p) { reinterpret_cast<double2*>(x)[p] = make_double2(alpha, alpha); },
+      [&](size_t i) { x[i] = alpha; });
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 4) scal_kernel(double alpha, double* __restrict__ x, size_t n) {
+  stream_rows<VEC>(
+      n,
+      [&](size_t p) {
+        double2 v = reinterpret_cast<double2*>(x)[p];
+        v.x = __dmul_rn(v.x, alpha);
+        v.y = __dmul_rn(v.y, alpha);
+        reinterpret_cast<double2*>(x)[p] = v;
+      },
+      [&](size_t i) { x[i] = __dmul_rn(x[i], alpha); });
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 4) copy_kernel(double* __restrict__ dst, const double* __restrict__ src, size_t n) {
+  stream_rows<VEC>(
+      n, [&](size_t p) { reinterpret_cast<double2*>(dst)[p] = reinterpret_cast<const double2*>(src)[p]; },
+      [&](size_t i) { dst[i] = src[i]; });
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 4)
+    axpy_kernel(double alpha, const double* __restrict__ x, double* __restrict__ y, size_t n) {
+  // y + alpha*x with the product rounded before the sum (reference ArrayHandlerIterable.h:71-72)
+  stream_rows<VEC>(
+      n,
+      [&](size_t p) {
+        const double2 xv = reinterpret_cast<const double2*>(x)[p];
+        double2 yv = reinterpret_cast<double2*>(y)[p];
+        yv.x = __dadd_rn(yv.x, __dmul_rn(alpha, xv.x));
+        yv.y = __dadd_rn(yv.y, __dmul_rn(alpha, xv.y));
+        reinterpret_cast<double2*>(y)[p] = yv;
+      },
+      [&](size_t i) { y[i] = __dadd_rn(y[i], __dmul_rn(alpha, x[i])); });
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 4) shift_kernel(double c, const double* __restrict__ x, double* __restrict__ out, size_t n) {
+  stream_rows<VEC>(
+      n,
+      [&](size_t p) {
+        double2 v = reinterpret_cast<const double2*>(x)[p];
+        v.x = __dadd_rn(v.x, c);
+        v.y = __dadd_rn(v.y, c);
+        reinterpret_cast<double2*>(out)[p] = v;
+      },
+      [&](size_t i) { out[i] = __dadd_rn(x[i], c); });
+}
+
+// r_k[i] = r_k[i] / ((diag[i] - shift_k) + 1e-15): the diagonal is read once for all w residuals
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 4) precondition_kernel(const __grid_constant__ PrecondParams prm) {
+  const double* __restrict__ diag = prm.diag;
+  const int w = prm.w;
+  stream_rows<VEC>(
+      prm.n,
+      [&](size_t p) {
+        const double2 d = reinterpret_cast<const double2*>(diag)[p];
+        for (int k = 0; k < w; ++k) {
+          double2* rk = reinterpret_cast<double2*>(prm.r[k]);
+          double2 v = rk[p];
+          const double s = prm.shift[k];
+          v.x = __ddiv_rn(v.x, __dadd_rn(__dsub_rn(d.x, s), 1e-15));
+          v.y = __ddiv_rn(v.y, __dadd_rn(__dsub_rn(d.y, s), 1e-15));
+          rk[p] = v;
+        }
+      },
+      [&](size_t i) {
+        const double d = diag[i];
+        for (int k = 0; k < w; ++k)
+          prm.r[k][i] = __ddiv_rn(prm.r[k][i], __dadd_rn(__dsub_rn(d, prm.shift[k]), 1e-15));
+      });
+}
+
+static int stream_grid(itsolv_ctx* ctx, size_t n) {
+  const int per_sm = ctx->opt_blas1_ctas > 0 ? ctx->opt_blas1_ctas : 4; // 4 x 256 threads, 4 row pairs in flight each
+  const size_t want = (n / 2 + size_t(kThreads) * kUnroll - 1) / (size_t(kThreads) * kUnroll);
+  size_t grid = size_t(ctx->num_sms) * per_sm;
+  if (want < grid)
+    grid = want ? want : 1;
+  return int(grid);
+}
+
+} // namespace itsolv
+
+using namespace itsolv;
+
+#define LAUNCH_STREAM(kernel, vec, ...)                                                                                \
+  do {                                                                                                                 \
+    const int grid__ = stream_grid(ctx, n);                                                                            \
+    if (vec)                                                                                                           \
+      kernel<true><<<grid__, kThreads, 0, ctx->stream>>>(__VA_ARGS__);                                                 \
+    else                                                                                                               \
+      kernel<false><<<grid__, kThreads, 0, ctx->stream>>>(__VA_ARGS__);                                                \
+    ctx->counters.launches += 1;                                                                                       \
+    ITSOLV_CUDA(cudaGetLastError());                                                                                   \
+  } while (0)
+
+extern "C" {
+
+int itsolv_fill_f64(itsolv_ctx* ctx, double alpha, double* x, size_t n) {
+  ctx->counters.n_fill++;
+  if (n == 0)
+    return 0;
+  CallScope scope(ctx, OP_BLAS1, 8.0 * n);
+  LAUNCH_STREAM(fill_kernel, aligned16(x), alpha, x, n);
+  return 0;
+}
+
+int itsolv_scal_f64(itsolv_ctx* ctx, double alpha, double* x, size_t n) {
+  ctx->counters.n_scal++;
+  if (n == 0)
+    return 0;
+  CallScope scope(ctx, OP_BLAS1, 16.0 * n);
+  LAUNCH_STREAM(scal_kernel, aligned16(x), alpha, x, n);
+  return 0;
+}
+
+int itsolv_copy_f64(itsolv_ctx* ctx, double* dst, const double* src, size_t n) {
+  ctx->counters.n_copy++;
+  if (n == 0 || dst == src)
+    return 0;
+  CallScope scope(ctx, OP_BLAS1, 16.0 * n);
+  LAUNCH_STREAM(copy_kernel, aligned16(dst) && aligned16(src), dst, src, n);
+  return 0;
+}
+
+int itsolv_axpy_f64(itsolv_ctx* ctx, double alpha, const double* x, double* y, size_t n) {
+  ctx->counters.n_axpy++;
+  if (n == 0)
+    return 0;
+  CallScope scope(ctx, OP_BLAS1, 24.0 * n);
+  LAUNCH_STREAM(axpy_kernel, aligned16(x) && aligned16(y), alpha, x, y, n);
+  return 0;
+}
+
+int itsolv_shift_f64(itsolv_ctx* ctx, double c, const double* x, double* out, size_t n) {
+  if (n == 0)
+    return 0;
+  LAUNCH_STREAM(shift_kernel, aligned16(x) && aligned16(out), c, x, out, n);
+  return 0;
+}
+
+int itsolv_precondition_f64(itsolv_ctx* ctx, double* const* r, int w, const double* diag, const double* shift, size_t n) {
+  ctx->counters.n_precondition++;
+  if (n == 0 || w == 0)
+    return 0;
+  ITSOLV_REQUIRE(w > 0, "itsolv_precondition_f64: w < 0");
+  for (int start = 0; start < w; start += ITSOLV_MAX_PANEL) {
+    const int cnt = (w - start) < ITSOLV_MAX_PANEL ? (w - start) : ITSOLV_MAX_PANEL;
+    PrecondParams prm;
+    bool vec = aligned16(diag);
+    for (int k = 0; k < cnt; ++k) {
+      prm.r[k] = r[start + k];
+      prm.shift[k] = shift[start + k];
+      vec = vec && aligned16(prm.r[k]);
+    }
+    prm.diag = diag;
+    prm.n = n;
+    prm.w = cnt;
+    CallScope scope(ctx, OP_BLAS1, 8.0 * n * (2.0 * cnt + 1));
+    LAUNCH_STREAM(precondition_kernel, vec, prm);
+  }
+  return 0;
+}
+
+} // extern "C"

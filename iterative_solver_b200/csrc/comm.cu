@@ -1,0 +1,197 @@
+// Communicator: NCCL over NVLink/NVSwitch, one rank per GPU. Replaces the reference's MPI calls on the vector path
+// (MPI_Allreduce of k*m doubles, reference array/util/gemm.h:179-182; of one double, array/DistrArray.cpp:134-136;
+// the gather/broadcast of select candidates, array/DistrArray.cpp:191-224).
+//
+// libnccl is resolved at run time with dlopen so that the library loads on a box without NCCL and, inside a torch
+// process, binds to the NCCL that torch already loaded. There is no host fallback: without NCCL comm_init fails.
+#include <dlfcn.h>
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace itsolv {
+
+// minimal NCCL surface (ABI-stable since NCCL 2.x)
+typedef struct ncclComm* ncclComm_t;
+typedef struct {
+  char internal[128];
+} ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclInt8 = 0, ncclChar = 0, ncclUint8 = 1, ncclFloat64 = 8, ncclDouble = 8 };
+enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 };
+
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried)
+    return api.handle ? &api : nullptr;
+  tried = true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle)
+      break;
+  }
+  if (!api.handle) {
+    if (const char* extra = std::getenv("ITSOLV_NCCL_LIBRARY"))
+      api.handle = dlopen(extra, RTLD_NOW | RTLD_GLOBAL);
+  }
+  if (!api.handle)
+    return nullptr;
+#define LOAD(sym) api.sym = reinterpret_cast<decltype(api.sym)>(dlsym(api.handle, "nccl" #sym))
+  LOAD(GetUniqueId);
+  LOAD(CommInitRank);
+  LOAD(CommDestroy);
+  LOAD(AllReduce);
+  LOAD(AllGather);
+  LOAD(Send);
+  LOAD(Recv);
+  LOAD(GroupStart);
+  LOAD(GroupEnd);
+  LOAD(GetErrorString);
+#undef LOAD
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.AllGather || !api.Send || !api.Recv ||
+      !api.GroupStart || !api.GroupEnd) {
+    api.handle = nullptr;
+    return nullptr;
+  }
+  return &api;
+}
+
+struct Comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, size = 1;
+  double* d_small = nullptr; // staging for host all-reduces and halos
+};
+
+#define ITSOLV_NCCL(call)                                                                                              \
+  do {                                                                                                                 \
+    int r__ = (call);                                                                                                  \
+    if (r__ != ncclSuccess) {                                                                                          \
+      NcclApi* a__ = nccl_api();                                                                                       \
+      set_error(std::string(#call) + ": " + (a__ && a__->GetErrorString ? a__->GetErrorString(r__) : "nccl error"));  \
+      return 1;                                                                                                        \
+    }                                                                                                                  \
+  } while (0)
+
+void comm_destroy(itsolv_ctx* ctx) {
+  if (!ctx->comm)
+    return;
+  NcclApi* api = nccl_api();
+  if (api && ctx->comm->comm && api->CommDestroy)
+    api->CommDestroy(ctx->comm->comm);
+  cudaFree(ctx->comm->d_small);
+  delete ctx->comm;
+  ctx->comm = nullptr;
+}
+
+int comm_allreduce_device(itsolv_ctx* ctx, double* d, size_t count, bool op_max) {
+  if (!ctx->comm || ctx->comm->size == 1 || count == 0)
+    return 0;
+  NcclApi* api = nccl_api();
+  ITSOLV_NCCL(api->AllReduce(d, d, count, ncclDouble, op_max ? ncclMax : ncclSum, ctx->comm->comm, ctx->stream));
+  return 0;
+}
+
+int comm_allgather_device(itsolv_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank) {
+  if (!ctx->comm || ctx->comm->size == 1) {
+    if (send != recv)
+      ITSOLV_CUDA(cudaMemcpyAsync(recv, send, bytes_per_rank, cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+  }
+  NcclApi* api = nccl_api();
+  ITSOLV_NCCL(api->AllGather(send, recv, bytes_per_rank, ncclUint8, ctx->comm->comm, ctx->stream));
+  return 0;
+}
+
+} // namespace itsolv
+
+using namespace itsolv;
+
+extern "C" {
+
+int itsolv_comm_unique_id(void* id) {
+  NcclApi* api = nccl_api();
+  ITSOLV_REQUIRE(api, "itsolv_comm_unique_id: libnccl.so.2 could not be loaded");
+  static_assert(sizeof(ncclUniqueId) == ITSOLV_UNIQUE_ID_BYTES, "unique id size");
+  ncclUniqueId uid;
+  ITSOLV_NCCL(api->GetUniqueId(&uid));
+  std::memcpy(id, &uid, sizeof(uid));
+  return 0;
+}
+
+int itsolv_comm_init(itsolv_ctx* ctx, int rank, int nranks, const void* id) {
+  ITSOLV_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "itsolv_comm_init: bad rank/size");
+  comm_destroy(ctx);
+  auto* c = new Comm();
+  c->rank = rank;
+  c->size = nranks;
+  ctx->comm = c;
+  ITSOLV_CUDA(cudaSetDevice(ctx->device));
+  ITSOLV_CUDA(cudaMalloc(&c->d_small, size_t(ITSOLV_MAX_PANEL) * ITSOLV_MAX_PANEL * sizeof(double)));
+  if (nranks == 1)
+    return 0;
+  NcclApi* api = nccl_api();
+  ITSOLV_REQUIRE(api, "itsolv_comm_init: libnccl.so.2 could not be loaded");
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof(uid));
+  ITSOLV_NCCL(api->CommInitRank(&c->comm, nranks, uid, rank));
+  return 0;
+}
+
+int itsolv_comm_rank(itsolv_ctx* ctx) { return ctx->comm ? ctx->comm->rank : 0; }
+int itsolv_comm_size(itsolv_ctx* ctx) { return ctx->comm ? ctx->comm->size : 1; }
+
+int itsolv_comm_allreduce_host(itsolv_ctx* ctx, double* values, size_t count, int op_max) {
+  if (!ctx->comm || ctx->comm->size == 1 || count == 0)
+    return 0;
+  ITSOLV_REQUIRE(count <= size_t(ITSOLV_MAX_PANEL) * ITSOLV_MAX_PANEL, "itsolv_comm_allreduce_host: too many values");
+  double* d = ctx->comm->d_small;
+  ITSOLV_CUDA(cudaMemcpyAsync(d, values, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (comm_allreduce_device(ctx, d, count, op_max != 0))
+    return 1;
+  ITSOLV_CUDA(cudaMemcpyAsync(values, d, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  ITSOLV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int itsolv_comm_barrier(itsolv_ctx* ctx) {
+  double one = 1;
+  return itsolv_comm_allreduce_host(ctx, &one, 1, 0);
+}
+
+int itsolv_comm_halo_exchange(itsolv_ctx* ctx, const double* send_lo, const double* send_hi, double* recv_lo,
+                              double* recv_hi, size_t count) {
+  if (!ctx->comm || ctx->comm->size == 1 || count == 0)
+    return 0;
+  NcclApi* api = nccl_api();
+  const int r = ctx->comm->rank, p = ctx->comm->size;
+  ITSOLV_NCCL(api->GroupStart());
+  if (r > 0) {
+    ITSOLV_NCCL(api->Send(send_lo, count, ncclDouble, r - 1, ctx->comm->comm, ctx->stream));
+    ITSOLV_NCCL(api->Recv(recv_lo, count, ncclDouble, r - 1, ctx->comm->comm, ctx->stream));
+  }
+  if (r < p - 1) {
+    ITSOLV_NCCL(api->Send(send_hi, count, ncclDouble, r + 1, ctx->comm->comm, ctx->stream));
+    ITSOLV_NCCL(api->Recv(recv_hi, count, ncclDouble, r + 1, ctx->comm->comm, ctx->stream));
+  }
+  ITSOLV_NCCL(api->GroupEnd());
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,113 @@
+// Shared internals of libitsolv_b200: context, error handling, accounting, small device helpers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include <itsolv_b200.h>
+
+namespace itsolv {
+
+void set_error(const std::string& msg);
+
+#define ITSOLV_CUDA(call)                                                                                              \
+  do {                                                                                                                 \
+    cudaError_t err__ = (call);                                                                                        \
+    if (err__ != cudaSuccess) {                                                                                        \
+      ::itsolv::set_error(std::string(#call) + ": " + cudaGetErrorString(err__) + " (" + __FILE__ + ":" +             \
+                          std::to_string(__LINE__) + ")");                                                             \
+      return 1;                                                                                                        \
+    }                                                                                                                  \
+  } while (0)
+
+#define ITSOLV_REQUIRE(cond, msg)                                                                                      \
+  do {                                                                                                                 \
+    if (!(cond)) {                                                                                                     \
+      ::itsolv::set_error(std::string(msg));                                                                           \
+      return 2;                                                                                                        \
+    }                                                                                                                  \
+  } while (0)
+
+struct Comm; // NCCL communicator wrapper (comm.cu)
+
+enum OpClass { OP_BLAS1 = 0, OP_GEMM_INNER = 1, OP_GEMM_OUTER = 2, OP_OTHER = 3 };
+
+struct PendingEvent {
+  cudaEvent_t start, stop;
+  int cls;
+};
+
+} // namespace itsolv
+
+struct itsolv_ctx {
+  int device = 0;
+  int num_sms = 148;
+  int max_smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaMemPool_t pool = nullptr;
+
+  // workspace for per-CTA partial Gram matrices and reduced results (device), pinned host mirror for results
+  double* d_partials = nullptr;
+  size_t partials_capacity = 0; // doubles
+  double* d_result = nullptr;   // ITSOLV_MAX_PANEL^2 doubles
+  double* h_result = nullptr;   // pinned, ITSOLV_MAX_PANEL^2 doubles
+  // staging for small host->device payloads (alphas, sparse maps, pointer tables): pinned ring + device ring
+  char* h_stage = nullptr;
+  char* d_stage = nullptr;
+  size_t stage_slot_bytes = 0;
+  int stage_slots = 0;
+  int stage_next = 0;
+  std::vector<cudaEvent_t> stage_events;
+  // select scratch
+  unsigned long long* d_select = nullptr;
+
+  itsolv::Comm* comm = nullptr;
+
+  // options
+  int opt_gi_rows = 0;    // rows per smem tile of gemm_inner (0 = auto)
+  int opt_gi_stages = 0;  // pipeline stages (0 = auto)
+  int opt_gi_threads = 0; // max threads per CTA (0 = auto)
+  int opt_gi_tile = 0;    // thread tile TI*16+TJ (0 = auto)
+  int opt_gi_ctas = 0;    // CTAs per SM (0 = auto)
+  int opt_go_cols = 0;    // gemm_outer columns per thread (0 = auto)
+  int opt_go_ctas = 0;    // gemm_outer CTAs per SM
+  int opt_blas1_ctas = 0; // CTAs per SM for streaming kernels
+
+  itsolv_counters counters{};
+  bool profiling = false;
+  std::vector<itsolv::PendingEvent> pending;
+  std::vector<cudaEvent_t> event_pool;
+  cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
+};
+
+namespace itsolv {
+
+//! RAII accounting of one C-ABI call: algorithmic bytes, call class and (when profiling) a CUDA-event pair.
+struct CallScope {
+  itsolv_ctx* ctx;
+  int cls;
+  cudaEvent_t start = nullptr;
+  CallScope(itsolv_ctx* c, int cls, double bytes);
+  ~CallScope();
+};
+void drain_pending(itsolv_ctx* ctx);
+
+//! Reserve a staging slot (pinned host + matching device region) of at least `bytes`; caller fills host, then commit copies.
+int stage_acquire(itsolv_ctx* ctx, size_t bytes, char** host, char** dev, int* slot);
+int stage_commit(itsolv_ctx* ctx, int slot, size_t bytes);
+//! call after launching the kernel that reads the device side of the slot
+int stage_done(itsolv_ctx* ctx, int slot);
+
+int ensure_partials(itsolv_ctx* ctx, size_t doubles);
+
+//! sum in place over ranks (device buffer); no-op without a communicator
+int comm_allreduce_device(itsolv_ctx* ctx, double* d, size_t count, bool op_max);
+int comm_allgather_device(itsolv_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank);
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+} // namespace itsolv

@@ -1,0 +1,469 @@
+// gemm_inner: the tall-skinny FP64 contraction  M(i,j) = sum_r x_i[r] * y_j[r]   (k x m, k,m <= 128)
+// that builds the overlap / action / rhs blocks of the subspace problem
+// (contract: reference src/molpro/linalg/array/ArrayHandler.h:200; CPU path: array/util/gemm.h:157-184, 268-279, which
+// runs k*m separate std::inner_product sweeps, i.e. 2km vector passes; here every HBM byte is read once and feeds all
+// k*m dot products).
+//
+// Kernel structure (sm_100a):
+//   * the k+m vectors are separate allocations (reference itsolv/subspace/QSpace.h:157), so a "tile" is T rows of each
+//     distinct vector; one producer warp moves a tile into shared memory with one 1-D TMA bulk copy per vector
+//     (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP), S stages deep, signalled through full/empty mbarriers;
+//   * consumer threads own a TI x TJ register tile of the k x m accumulators (strided assignment i = ib + a*KB,
+//     j = jb + b*MB so that neighbouring lanes read neighbouring vectors -> conflict-free, broadcast LDS.128) and,
+//     when the output needs fewer than all threads, split the rows of the tile between G row groups;
+//   * persistent grid, tile t -> CTA t mod grid (static, so the summation order is fixed for a given shape and n);
+//   * per-CTA partial k x m sums go to a workspace, a second small kernel adds them in CTA order: run-to-run
+//     reproducible, no FP64 atomics.
+// Vectors that appear on both sides (overlap(x,x), dot(x,x)) are loaded once.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace itsolv {
+
+constexpr int kMaxStages = 8;
+constexpr int kMaxConsumers = 256;
+
+struct GiParams {
+  const double* vec[2 * ITSOLV_MAX_PANEL]; // distinct vectors of the call
+  unsigned char xslot[ITSOLV_MAX_PANEL];   // xx[i] -> index into vec
+  unsigned char yslot[ITSOLV_MAX_PANEL];   // yy[j] -> index into vec
+  double* partials;                        // [gridDim.x][k*m]
+  size_t n;
+  long long nfull; // number of full tiles of `rows` rows
+  int nvec, k, m;
+  int rows;   // T: rows per tile (multiple of 2)
+  int stride; // doubles between consecutive vectors inside a stage (T + 2: shifts each vector by one 16-byte bank group)
+  int stages;
+  int KB, MB, G; // thread-tile grid (KB x MB tiles) and number of row groups
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile("{\n"
+               ".reg .pred P1;\n"
+               "LAB_WAIT:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+               "@P1 bra DONE;\n"
+               "bra LAB_WAIT;\n"
+               "DONE:\n"
+               "}" ::"r"(smem_u32(bar)),
+               "r"(parity)
+               : "memory");
+}
+//! 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int TI, int TJ>
+__device__ __forceinline__ void consume_tile(const double* __restrict__ st, int npairs, int g, int G, const int (&xoff)[TI],
+                                             const int (&yoff)[TJ], double (&acc)[TI][TJ]) {
+#pragma unroll 2
+  for (int rp = g; rp < npairs; rp += G) {
+    double2 xv[TI], yv[TJ];
+#pragma unroll
+    for (int a = 0; a < TI; ++a)
+      xv[a] = *reinterpret_cast<const double2*>(st + xoff[a] + 2 * rp);
+#pragma unroll
+    for (int b = 0; b < TJ; ++b)
+      yv[b] = *reinterpret_cast<const double2*>(st + yoff[b] + 2 * rp);
+#pragma unroll
+    for (int a = 0; a < TI; ++a)
+#pragma unroll
+      for (int b = 0; b < TJ; ++b) {
+        acc[a][b] = fma(xv[a].x, yv[b].x, acc[a][b]);
+        acc[a][b] = fma(xv[a].y, yv[b].y, acc[a][b]);
+      }
+  }
+}
+
+//! all threads of the CTA copy rows [row0, row0+nrows) of every vector into stage 0, zero-filling up to `rows`
+__device__ __forceinline__ void cooperative_fill(const GiParams& p, double* st, size_t row0, int nrows) {
+  for (int v = 0; v < p.nvec; ++v) {
+    const double* __restrict__ src = p.vec[v] + row0;
+    double* dst = st + size_t(v) * p.stride;
+    for (int r = threadIdx.x; r < p.rows; r += blockDim.x)
+      dst[r] = r < nrows ? src[r] : 0.0;
+  }
+}
+
+template <int TI, int TJ, bool ASYNC>
+__global__ void __launch_bounds__(kMaxConsumers + 32, (TI * TJ >= 32 ? 1 : 2)) gemm_inner_kernel(const __grid_constant__ GiParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* tiles = reinterpret_cast<double*>(smem_raw);
+  __shared__ uint64_t full_bar[kMaxStages];
+  __shared__ uint64_t empty_bar[kMaxStages];
+
+  const int tid = threadIdx.x;
+  const int nconsumers = blockDim.x - 32; // last warp is the producer
+  const int nconsumer_warps = nconsumers / 32;
+  const bool is_producer = tid >= nconsumers;
+  const int NT = p.KB * p.MB;
+  const bool active = !is_producer && tid < NT * p.G;
+  const int tile = tid % NT, g = tid / NT;
+  const int ib = tile / p.MB, jb = tile % p.MB;
+
+  int xoff[TI], yoff[TJ];
+#pragma unroll
+  for (int a = 0; a < TI; ++a) {
+    const int i = ib + a * p.KB;
+    xoff[a] = int(p.xslot[i < p.k ? i : 0]) * p.stride;
+  }
+#pragma unroll
+  for (int b = 0; b < TJ; ++b) {
+    const int j = jb + b * p.MB;
+    yoff[b] = int(p.yslot[j < p.m ? j : 0]) * p.stride;
+  }
+  double acc[TI][TJ];
+#pragma unroll
+  for (int a = 0; a < TI; ++a)
+#pragma unroll
+    for (int b = 0; b < TJ; ++b)
+      acc[a][b] = 0.0;
+
+  const long long my_tiles =
+      p.nfull > (long long)blockIdx.x ? (p.nfull - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const size_t stage_doubles = size_t(p.nvec) * p.stride;
+  const int npairs = p.rows / 2;
+
+  if (ASYNC) {
+    if (tid == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], nconsumer_warps);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (is_producer) {
+      // UBLKCP takes its addresses from uniform registers: one elected lane issues every copy of the tile
+      if ((tid & 31) == 0) {
+        const uint32_t vec_bytes = uint32_t(p.rows) * 8u;
+        for (long long s = 0; s < my_tiles; ++s) {
+          const int stage = int(s % p.stages);
+          const long long use = s / p.stages;
+          if (use > 0)
+            mbar_wait(&empty_bar[stage], uint32_t((use - 1) & 1));
+          mbar_expect_tx(&full_bar[stage], vec_bytes * uint32_t(p.nvec));
+          const size_t row0 = size_t(blockIdx.x + s * gridDim.x) * size_t(p.rows);
+          double* st = tiles + size_t(stage) * stage_doubles;
+#pragma unroll 4
+          for (int v = 0; v < p.nvec; ++v)
+            bulk_load(st + size_t(v) * p.stride, p.vec[v] + row0, vec_bytes, &full_bar[stage]);
+        }
+      }
+    } else {
+      const int lane = tid & 31;
+      for (long long s = 0; s < my_tiles; ++s) {
+        const int stage = int(s % p.stages);
+        mbar_wait(&full_bar[stage], uint32_t((s / p.stages) & 1));
+        if (active)
+          consume_tile<TI, TJ>(tiles + size_t(stage) * stage_doubles, npairs, g, p.G, xoff, yoff, acc);
+        __syncwarp();
+        if (lane == 0)
+          mbar_arrive(&empty_bar[stage]);
+      }
+    }
+    __syncthreads();
+  } else {
+    // pointers not 16-byte aligned: plain loads by all threads, one stage
+    for (long long s = 0; s < my_tiles; ++s) {
+      const size_t row0 = size_t(blockIdx.x + s * gridDim.x) * size_t(p.rows);
+      cooperative_fill(p, tiles, row0, p.rows);
+      __syncthreads();
+      if (active)
+        consume_tile<TI, TJ>(tiles, npairs, g, p.G, xoff, yoff, acc);
+      __syncthreads();
+    }
+  }
+
+  // the last, partial tile belongs to the CTA that would own tile number nfull
+  const size_t tail0 = size_t(p.nfull) * size_t(p.rows);
+  if (tail0 < p.n && int(p.nfull % gridDim.x) == int(blockIdx.x)) {
+    cooperative_fill(p, tiles, tail0, int(p.n - tail0));
+    __syncthreads();
+    if (active)
+      consume_tile<TI, TJ>(tiles, npairs, g, p.G, xoff, yoff, acc);
+    __syncthreads();
+  }
+
+  // reduce the G row groups in group order; red[(a*TJ+b)][g][tile]
+  double* red = tiles;
+  const int nact = NT * p.G;
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < TI; ++a)
+#pragma unroll
+      for (int b = 0; b < TJ; ++b)
+        red[size_t(a * TJ + b) * nact + tid] = acc[a][b];
+  }
+  __syncthreads();
+  const int km = p.k * p.m;
+  double* out = p.partials + size_t(blockIdx.x) * km;
+  for (int e = tid; e < km; e += blockDim.x) {
+    const int i = e / p.m, j = e % p.m;
+    const int a = i / p.KB, tb_i = i % p.KB;
+    const int b = j / p.MB, tb_j = j % p.MB;
+    const double* src = red + size_t(a * TJ + b) * nact + (tb_i * p.MB + tb_j);
+    double sum = 0.0;
+    for (int gg = 0; gg < p.G; ++gg)
+      sum += src[size_t(gg) * NT];
+    out[e] = sum;
+  }
+}
+
+//! out[e] = sum over CTAs (in CTA order within each lane, then a fixed shuffle tree) of partials[c][e]; one warp per element
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int nparts, int km,
+                                                              double* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= km)
+    return;
+  double sum = 0.0;
+  for (int c = lane; c < nparts; c += 32)
+    sum += partials[size_t(c) * km + warp];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+    sum += __shfl_down_sync(0xffffffffu, sum, off);
+  if (lane == 0)
+    out[warp] = sum;
+}
+
+using GiKernel = void (*)(const GiParams);
+
+template <int TI, int TJ>
+static GiKernel pick_async(bool async) {
+  return async ? gemm_inner_kernel<TI, TJ, true> : gemm_inner_kernel<TI, TJ, false>;
+}
+
+static GiKernel pick_kernel(int ti, int tj, bool async) {
+#define CASE(I, J)                                                                                                     \
+  if (ti == I && tj == J)                                                                                              \
+  return pick_async<I, J>(async)
+  CASE(1, 1);
+  CASE(1, 2);
+  CASE(2, 1);
+  CASE(2, 2);
+  CASE(1, 4);
+  CASE(4, 1);
+  CASE(2, 4);
+  CASE(4, 2);
+  CASE(4, 4);
+  CASE(4, 8);
+  CASE(8, 4);
+  CASE(8, 8);
+#undef CASE
+  return nullptr;
+}
+
+static int pow2_at_most(int v, int cap) {
+  int r = 1;
+  while (r * 2 <= v && r * 2 <= cap)
+    r *= 2;
+  return r;
+}
+
+//! Launch the contraction into ctx->d_result (device, k*m doubles); no synchronisation.
+int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const double* const* yy, int m, size_t n) {
+  ITSOLV_REQUIRE(k >= 1 && m >= 1 && k <= ITSOLV_MAX_PANEL && m <= ITSOLV_MAX_PANEL, "gemm_inner: panel size out of range");
+  const int km = k * m;
+  if (n == 0) {
+    ITSOLV_CUDA(cudaMemsetAsync(ctx->d_result, 0, size_t(km) * sizeof(double), ctx->stream));
+    return 0;
+  }
+  GiParams p;
+  p.nvec = 0;
+  bool async = true;
+  auto slot_of = [&](const double* ptr) {
+    for (int v = 0; v < p.nvec; ++v)
+      if (p.vec[v] == ptr)
+        return v;
+    p.vec[p.nvec] = ptr;
+    return p.nvec++;
+  };
+  for (int i = 0; i < k; ++i) {
+    ITSOLV_REQUIRE(xx[i] != nullptr, "gemm_inner: null vector");
+    p.xslot[i] = (unsigned char)slot_of(xx[i]);
+    async = async && aligned16(xx[i]);
+  }
+  for (int j = 0; j < m; ++j) {
+    ITSOLV_REQUIRE(yy[j] != nullptr, "gemm_inner: null vector");
+    p.yslot[j] = (unsigned char)slot_of(yy[j]);
+    async = async && aligned16(yy[j]);
+  }
+  for (int i = k; i < ITSOLV_MAX_PANEL; ++i)
+    p.xslot[i] = 0;
+  for (int j = m; j < ITSOLV_MAX_PANEL; ++j)
+    p.yslot[j] = 0;
+  p.k = k;
+  p.m = m;
+  p.n = n;
+
+  // thread tile
+  int ti = pow2_at_most(k, 4), tj = pow2_at_most(m, 4);
+  if (ctx->opt_gi_tile > 0) {
+    ti = ctx->opt_gi_tile / 16;
+    tj = ctx->opt_gi_tile % 16;
+  }
+  int max_consumers = ctx->opt_gi_threads > 0 ? ctx->opt_gi_threads : 256;
+  max_consumers = std::min(kMaxConsumers, std::max(32, (max_consumers / 32) * 32));
+  auto ntiles = [&](int a, int b) { return ((k + a - 1) / a) * ((m + b - 1) / b); };
+  while (ntiles(ti, tj) > max_consumers) {
+    if (tj <= ti && tj < 8)
+      tj *= 2;
+    else if (ti < 8)
+      ti *= 2;
+    else if (tj < 8)
+      tj *= 2;
+    else
+      break;
+  }
+  ITSOLV_REQUIRE(ntiles(ti, tj) <= max_consumers, "gemm_inner: no thread tile fits this panel");
+  p.KB = (k + ti - 1) / ti;
+  p.MB = (m + tj - 1) / tj;
+  const int NT = p.KB * p.MB;
+  p.G = std::max(1, max_consumers / NT);
+  const int nconsumers = ((NT * p.G + 31) / 32) * 32;
+
+  // shared-memory tile: rows per stage and stages
+  int ctas_per_sm = ctx->opt_gi_ctas > 0 ? ctx->opt_gi_ctas : 2;
+  const size_t reduce_bytes = size_t(ti) * tj * NT * p.G * sizeof(double);
+  const size_t smem_cap = size_t(ctx->max_smem_optin) - 1024;
+  if (reduce_bytes > smem_cap / 2 - 1024 || ti * tj >= 32)
+    ctas_per_sm = 1; // register budget of the 4x8 / 8x8 tiles allows one CTA per SM
+  const size_t budget = (ctas_per_sm == 1 ? smem_cap : (smem_cap - 1024) / ctas_per_sm) & ~size_t(127);
+  int stages = async ? (ctx->opt_gi_stages > 0 ? ctx->opt_gi_stages : 3) : 1;
+  stages = std::min(stages, kMaxStages);
+  int rows;
+  if (ctx->opt_gi_rows > 0) {
+    rows = ctx->opt_gi_rows;
+  } else {
+    rows = int(budget / (size_t(stages) * p.nvec * sizeof(double)));
+    rows = std::min(rows, 2048);
+  }
+  rows = std::max(16, (rows / 16) * 16);
+  while (stages > 1 && size_t(stages) * p.nvec * (rows + 2) * sizeof(double) > budget) {
+    if (rows > 16)
+      rows -= 16;
+    else
+      --stages;
+  }
+  while (size_t(stages) * p.nvec * (rows + 2) * sizeof(double) > smem_cap && rows > 16)
+    rows -= 16;
+  // do not make tiles so large that the grid cannot be filled
+  {
+    const size_t want_tiles = size_t(ctx->num_sms) * ctas_per_sm * 2;
+    while (rows > 64 && n / size_t(rows) < want_tiles)
+      rows = std::max(64, ((rows / 2) / 16) * 16);
+  }
+  p.rows = rows;
+  p.stride = rows + 2;
+  p.stages = stages;
+  p.nfull = (long long)(n / size_t(rows));
+  const size_t smem_bytes = std::max(size_t(stages) * p.nvec * p.stride * sizeof(double), reduce_bytes);
+  ITSOLV_REQUIRE(smem_bytes <= smem_cap, "gemm_inner: shared-memory tile does not fit");
+
+  const long long total_tiles = p.nfull + ((n % size_t(rows)) ? 1 : 0);
+  const int grid = int(std::min<long long>(total_tiles, (long long)ctx->num_sms * ctas_per_sm));
+  if (ensure_partials(ctx, size_t(grid) * km))
+    return 1;
+  p.partials = ctx->d_partials;
+
+  GiKernel kernel = pick_kernel(ti, tj, async);
+  ITSOLV_REQUIRE(kernel != nullptr, "gemm_inner: thread tile not instantiated");
+  ITSOLV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
+  kernel<<<grid, nconsumers + 32, smem_bytes, ctx->stream>>>(p);
+  ITSOLV_CUDA(cudaGetLastError());
+  const int rblocks = (km * 32 + 255) / 256;
+  reduce_partials_kernel<<<rblocks, 256, 0, ctx->stream>>>(ctx->d_partials, grid, km, ctx->d_result);
+  ITSOLV_CUDA(cudaGetLastError());
+  ctx->counters.launches += 2;
+  return 0;
+}
+
+//! all-reduce over ranks, copy to the pinned buffer, synchronise, hand to the caller
+int finish_result(itsolv_ctx* ctx, int count, double* out) {
+  if (comm_allreduce_device(ctx, ctx->d_result, size_t(count), false))
+    return 1;
+  ITSOLV_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, size_t(count) * sizeof(double), cudaMemcpyDeviceToHost,
+                              ctx->stream));
+  ITSOLV_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int e = 0; e < count; ++e)
+    out[e] = ctx->h_result[e];
+  return 0;
+}
+
+static double distinct_bytes(const double* const* xx, int k, const double* const* yy, int m, size_t n) {
+  int nd = 0;
+  const double* seen[2 * ITSOLV_MAX_PANEL];
+  auto add = [&](const double* ptr) {
+    for (int v = 0; v < nd; ++v)
+      if (seen[v] == ptr)
+        return;
+    seen[nd++] = ptr;
+  };
+  for (int i = 0; i < k; ++i)
+    add(xx[i]);
+  for (int j = 0; j < m; ++j)
+    add(yy[j]);
+  return 8.0 * double(n) * nd;
+}
+
+} // namespace itsolv
+
+using namespace itsolv;
+
+extern "C" {
+
+int itsolv_gemm_inner_f64(itsolv_ctx* ctx, const double* const* xx, int k, const double* const* yy, int m, size_t n,
+                          double* out) {
+  ctx->counters.n_gemm_inner++;
+  if (k <= 0 || m <= 0)
+    return 0;
+  // panels wider than ITSOLV_MAX_PANEL are processed block by block
+  for (int i0 = 0; i0 < k; i0 += ITSOLV_MAX_PANEL) {
+    const int kb = std::min(ITSOLV_MAX_PANEL, k - i0);
+    for (int j0 = 0; j0 < m; j0 += ITSOLV_MAX_PANEL) {
+      const int mb = std::min(ITSOLV_MAX_PANEL, m - j0);
+      CallScope scope(ctx, OP_GEMM_INNER, distinct_bytes(xx + i0, kb, yy + j0, mb, n));
+      if (gemm_inner_device(ctx, xx + i0, kb, yy + j0, mb, n))
+        return 1;
+      if (kb == k && mb == m) {
+        if (finish_result(ctx, kb * mb, out))
+          return 1;
+      } else {
+        std::vector<double> block(size_t(kb) * mb);
+        if (finish_result(ctx, kb * mb, block.data()))
+          return 1;
+        for (int i = 0; i < kb; ++i)
+          for (int j = 0; j < mb; ++j)
+            out[size_t(i0 + i) * m + (j0 + j)] = block[size_t(i) * mb + j];
+      }
+    }
+  }
+  return 0;
+}
+
+int itsolv_dot_f64(itsolv_ctx* ctx, const double* x, const double* y, size_t n, double* result) {
+  ctx->counters.n_dot++;
+  CallScope scope(ctx, OP_BLAS1, (x == y ? 8.0 : 16.0) * double(n));
+  if (gemm_inner_device(ctx, &x, 1, &y, 1, n))
+    return 1;
+  return finish_result(ctx, 1, result);
+}
+
+} // extern "C"

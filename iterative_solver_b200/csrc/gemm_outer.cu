@@ -1,0 +1,251 @@
+// gemm_outer: subspace -> full-space expansion  y_j += sum_i alpha(i,j) * x_i   (k x m coefficients)
+// (contract: reference src/molpro/linalg/array/ArrayHandler.h:195; CPU path array/util/gemm.h:186-203, 258-265, which
+// performs k*m separate axpy sweeps = 3km vector passes; here x is read once per 16 output columns and every y is read
+// and written once: 8n(k+2m) bytes, or 8n(k+m) with beta_zero when the caller has just zeroed y,
+// reference itsolv/IterativeSolverTemplate.h:45-47).
+//
+// Rows are independent, so lanes map to consecutive row pairs (128-bit coalesced loads of every x_i and y_j); a
+// thread keeps the m (<= 16 per pass) running sums of its two rows in registers, streams the k x-vectors through
+// them with 4 independent 128-bit loads in flight, and reads alpha (staged once per CTA into shared memory) with
+// warp-uniform broadcast loads. The sum over i runs in ascending i as the reference's loop does; each term is one FMA.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace itsolv {
+
+constexpr int kGoThreads = 256;
+constexpr int kGoUnroll = 4;
+
+struct GoParams {
+  const double* x[ITSOLV_MAX_PANEL];
+  double* y[ITSOLV_MAX_PANEL];
+  const double* alpha; // device, k x m row-major
+  size_t n;
+  int k, m;
+  int ld; // leading dimension of alpha in shared memory (m rounded up to a multiple of MJ)
+  int beta_zero;
+};
+
+template <class RV>
+struct RowOps;
+template <>
+struct RowOps<double2> {
+  static constexpr int width = 2;
+  static __device__ __forceinline__ double2 zero() { return make_double2(0.0, 0.0); }
+  static __device__ __forceinline__ void fma_to(double2& acc, double a, const double2& x) {
+    acc.x = fma(a, x.x, acc.x);
+    acc.y = fma(a, x.y, acc.y);
+  }
+};
+template <>
+struct RowOps<double> {
+  static constexpr int width = 1;
+  static __device__ __forceinline__ double zero() { return 0.0; }
+  static __device__ __forceinline__ void fma_to(double& acc, double a, const double& x) { acc = fma(a, x, acc); }
+};
+
+//! MJ consecutive coefficients of one alpha row; the address is warp-uniform (broadcast) and 16-byte aligned for MJ >= 2
+template <int MJ>
+__device__ __forceinline__ void load_alpha_row(const double* __restrict__ arow, double (&av)[MJ]) {
+  if constexpr (MJ >= 2) {
+#pragma unroll
+    for (int b = 0; b < MJ / 2; ++b) {
+      const double2 t = reinterpret_cast<const double2*>(arow)[b];
+      av[2 * b] = t.x;
+      av[2 * b + 1] = t.y;
+    }
+  } else {
+    av[0] = arow[0];
+  }
+}
+
+//! one thread, one row group `r` (index in units of RV), all column chunks
+template <int MJ, class RV>
+__device__ __forceinline__ void expand_rows(const GoParams& p, const double* __restrict__ sa, size_t r) {
+  using Ops = RowOps<RV>;
+  for (int jc = 0; jc < p.m; jc += MJ) {
+    RV acc[MJ];
+#pragma unroll
+    for (int b = 0; b < MJ; ++b) {
+      if (!p.beta_zero && jc + b < p.m)
+        acc[b] = reinterpret_cast<const RV*>(p.y[jc + b])[r];
+      else
+        acc[b] = Ops::zero();
+    }
+    int i = 0;
+    for (; i + kGoUnroll <= p.k; i += kGoUnroll) {
+      RV xv[kGoUnroll];
+#pragma unroll
+      for (int u = 0; u < kGoUnroll; ++u)
+        xv[u] = reinterpret_cast<const RV*>(p.x[i + u])[r];
+#pragma unroll
+      for (int u = 0; u < kGoUnroll; ++u) {
+        double av[MJ];
+        load_alpha_row<MJ>(sa + size_t(i + u) * p.ld + jc, av);
+#pragma unroll
+        for (int b = 0; b < MJ; ++b)
+          Ops::fma_to(acc[b], av[b], xv[u]);
+      }
+    }
+    for (; i < p.k; ++i) {
+      const RV xv = reinterpret_cast<const RV*>(p.x[i])[r];
+      double av[MJ];
+      load_alpha_row<MJ>(sa + size_t(i) * p.ld + jc, av);
+#pragma unroll
+      for (int b = 0; b < MJ; ++b)
+        Ops::fma_to(acc[b], av[b], xv);
+    }
+#pragma unroll
+    for (int b = 0; b < MJ; ++b)
+      if (jc + b < p.m)
+        reinterpret_cast<RV*>(p.y[jc + b])[r] = acc[b];
+  }
+}
+
+template <int MJ, bool VEC>
+__global__ void __launch_bounds__(kGoThreads, 2) gemm_outer_kernel(const __grid_constant__ GoParams p) {
+  extern __shared__ __align__(16) double sa[]; // k x ld, zero padded columns
+  for (int e = threadIdx.x; e < p.k * p.ld; e += blockDim.x) {
+    const int i = e / p.ld, j = e % p.ld;
+    sa[e] = j < p.m ? p.alpha[size_t(i) * p.m + j] : 0.0;
+  }
+  __syncthreads();
+  const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = size_t(gridDim.x) * blockDim.x;
+  if (VEC) {
+    const size_t npairs = p.n / 2;
+    for (size_t r = tid; r < npairs; r += nthreads)
+      expand_rows<MJ, double2>(p, sa, r);
+    if ((p.n & 1) && tid == 0)
+      expand_rows<MJ, double>(p, sa, p.n - 1);
+  } else {
+    for (size_t r = tid; r < p.n; r += nthreads)
+      expand_rows<MJ, double>(p, sa, r);
+  }
+}
+
+using GoKernel = void (*)(const GoParams);
+template <int MJ>
+static GoKernel go_pick_vec(bool vec) {
+  return vec ? gemm_outer_kernel<MJ, true> : gemm_outer_kernel<MJ, false>;
+}
+static GoKernel go_pick(int mj, bool vec) {
+  switch (mj) {
+  case 1:
+    return go_pick_vec<1>(vec);
+  case 2:
+    return go_pick_vec<2>(vec);
+  case 4:
+    return go_pick_vec<4>(vec);
+  case 8:
+    return go_pick_vec<8>(vec);
+  case 16:
+    return go_pick_vec<16>(vec);
+  }
+  return nullptr;
+}
+
+} // namespace itsolv
+
+using namespace itsolv;
+
+extern "C" {
+
+int itsolv_gemm_outer_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* xx,
+                          double* const* yy, size_t n, int beta_zero) {
+  ctx->counters.n_gemm_outer++;
+  if (m <= 0)
+    return 0;
+  if (k <= 0) {
+    if (beta_zero)
+      for (int j = 0; j < m; ++j)
+        if (itsolv_fill_f64(ctx, 0.0, yy[j], n))
+          return 1;
+    return 0;
+  }
+  if (n == 0)
+    return 0;
+  // Aliased operands (a y that is also an x, or the same y twice) have sequential meaning in the reference's loop of
+  // axpys; keep that meaning by issuing the axpys one by one.
+  bool aliased = false;
+  for (int j = 0; j < m && !aliased; ++j) {
+    for (int i = 0; i < k; ++i)
+      if (xx[i] == yy[j])
+        aliased = true;
+    for (int j2 = 0; j2 < j; ++j2)
+      if (yy[j2] == yy[j])
+        aliased = true;
+  }
+  if (aliased) {
+    if (beta_zero)
+      for (int j = 0; j < m; ++j)
+        if (itsolv_fill_f64(ctx, 0.0, yy[j], n))
+          return 1;
+    for (int i = 0; i < k; ++i)
+      for (int j = 0; j < m; ++j)
+        if (itsolv_axpy_f64(ctx, alpha[size_t(i) * m + j], xx[i], yy[j], n))
+          return 1;
+    return 0;
+  }
+  // blocks of at most ITSOLV_MAX_PANEL x ITSOLV_MAX_PANEL coefficients per launch
+  for (int j0 = 0; j0 < m; j0 += ITSOLV_MAX_PANEL) {
+    const int mb = std::min(ITSOLV_MAX_PANEL, m - j0);
+    for (int i0 = 0; i0 < k; i0 += ITSOLV_MAX_PANEL) {
+      const int kb = std::min(ITSOLV_MAX_PANEL, k - i0);
+      const bool bz = beta_zero && i0 == 0;
+      CallScope scope(ctx, OP_GEMM_OUTER, 8.0 * double(n) * (kb + (bz ? 1.0 : 2.0) * mb));
+      GoParams p;
+      bool vec = true;
+      for (int i = 0; i < kb; ++i) {
+        p.x[i] = xx[i0 + i];
+        vec = vec && aligned16(p.x[i]);
+      }
+      for (int j = 0; j < mb; ++j) {
+        p.y[j] = yy[j0 + j];
+        vec = vec && aligned16(p.y[j]);
+      }
+      char *h = nullptr, *d = nullptr;
+      int slot = 0;
+      const size_t abytes = size_t(kb) * mb * sizeof(double);
+      if (stage_acquire(ctx, abytes, &h, &d, &slot))
+        return 1;
+      double* ha = reinterpret_cast<double*>(h);
+      for (int i = 0; i < kb; ++i)
+        for (int j = 0; j < mb; ++j)
+          ha[size_t(i) * mb + j] = alpha[size_t(i0 + i) * m + (j0 + j)];
+      if (stage_commit(ctx, slot, abytes))
+        return 1;
+      p.alpha = reinterpret_cast<const double*>(d);
+      p.n = n;
+      p.k = kb;
+      p.m = mb;
+      p.beta_zero = bz ? 1 : 0;
+      int mj = 1;
+      while (mj < mb && mj < 16)
+        mj *= 2;
+      if (ctx->opt_go_cols > 0)
+        mj = ctx->opt_go_cols;
+      p.ld = ((mb + mj - 1) / mj) * mj;
+      GoKernel kernel = go_pick(mj, vec);
+      ITSOLV_REQUIRE(kernel != nullptr, "gemm_outer: column tile not instantiated");
+      const size_t smem = size_t(kb) * p.ld * sizeof(double);
+      ITSOLV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<size_t>(smem, 1024))));
+      int per_sm = ctx->opt_go_ctas > 0 ? ctx->opt_go_ctas : (mj <= 2 ? 6 : mj == 4 ? 4 : mj == 8 ? 3 : 2);
+      if (smem * per_sm > size_t(ctx->max_smem_optin))
+        per_sm = std::max<int>(1, int(size_t(ctx->max_smem_optin) / smem));
+      const size_t units = vec ? n / 2 : n;
+      size_t grid = std::min<size_t>((units + kGoThreads - 1) / kGoThreads, size_t(ctx->num_sms) * per_sm);
+      if (grid == 0)
+        grid = 1;
+      kernel<<<int(grid), kGoThreads, smem, ctx->stream>>>(p);
+      ITSOLV_CUDA(cudaGetLastError());
+      ctx->counters.launches += 1;
+      if (stage_done(ctx, slot))
+        return 1;
+    }
+  }
+  return 0;
+}
+
+} // extern "C"

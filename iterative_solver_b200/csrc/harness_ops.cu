@@ -1,0 +1,222 @@
+// Harness operator kernels: the user's side of the solver (Problem::action / diagonals / p_action, reference
+// src/molpro/linalg/itsolv/IterativeSolver.h:90-172) for the synthetic benchmark operator of SURVEY.md section 8(d):
+//   A(i,i) = i+1,  A(i,j) = eps*(1 + ((i+j) mod 7))  for 0 < |i-j| <= b      (symmetric, diagonally dominant, banded)
+// either generated on the fly or read from CSR arrays. Row sums run over ascending column with the product rounded before
+// the sum, the same order as the CPU twin used by the oracle (oracle/ref_driver.cpp BandedProblemHost::apply), so both
+// sides of a parity test see bit-identical operator actions. Not part of the measured subspace path.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace itsolv {
+
+__device__ __forceinline__ double band_entry(long long i, long long j, double eps) {
+  return i == j ? double(i + 1) : __dmul_rn(eps, double(1 + ((i + j) % 7)));
+}
+
+//! x value at global column c given the local shard [off, off+n) and the two halos of b rows
+__device__ __forceinline__ double x_at(long long c, long long off, long long n, int b, const double* __restrict__ x,
+                                       const double* __restrict__ x_lo, const double* __restrict__ x_hi) {
+  const long long l = c - off;
+  if (l < 0)
+    return x_lo[b + l];
+  if (l >= n)
+    return x_hi[l - n];
+  return x[l];
+}
+
+__global__ void __launch_bounds__(256)
+    banded_apply_kernel(long long n_global, long long off, long long n, int b, double eps, const double* __restrict__ x,
+                        const double* __restrict__ x_lo, const double* __restrict__ x_hi, double* __restrict__ y) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const long long i = off + r;
+    const long long lo = i - b > 0 ? i - b : 0;
+    const long long hi = i + b < n_global - 1 ? i + b : n_global - 1;
+    double acc = 0.0;
+    for (long long j = lo; j <= hi; ++j)
+      acc = __dadd_rn(acc, __dmul_rn(band_entry(i, j, eps), x_at(j, off, n, b, x, x_lo, x_hi)));
+    y[r] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    csr_apply_kernel(long long off, long long n, int b, const long long* __restrict__ row_ptr, const int* __restrict__ col,
+                     const double* __restrict__ val, const double* __restrict__ x, const double* __restrict__ x_lo,
+                     const double* __restrict__ x_hi, double* __restrict__ y) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (long long e = row_ptr[r]; e < row_ptr[r + 1]; ++e)
+      acc = __dadd_rn(acc, __dmul_rn(val[e], x_at(col[e], off, n, b, x, x_lo, x_hi)));
+    y[r] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) banded_fill_kernel(int kind, int k, long long off, long long n, double* __restrict__ out) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const long long i = off + r;
+    out[r] = kind == 0 ? double(i + 1) : 1.0 + double((i + k) % (k + 3)) / double(k + 3);
+  }
+}
+
+__global__ void __launch_bounds__(128) example_apply_kernel(long long n, const double* __restrict__ x, double* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  double acc = 0.0;
+  for (long long j = 0; j < n; ++j) {
+    const double mij = i == j ? double(i + 1) : __dmul_rn(0.001, double((i + j) % n));
+    acc = __dadd_rn(acc, __dmul_rn(mij, x[j]));
+  }
+  y[i] = acc;
+}
+
+struct PActionParams {
+  double* actions[ITSOLV_MAX_PANEL];
+  const long long* rows; // candidate global rows (sorted, unique)
+  const int* map_ptr;
+  const long long* idx;
+  const double* val;
+  const double* pcoef; // nact x nP
+  long long off, n;
+  int nrows, nact, nP, b;
+  double eps;
+};
+
+//! actions[k][i] += sum over P vectors p (ascending) and their entries (c,v): A(i,c) * (v * pcoef[k][p])
+__global__ void p_action_kernel(const __grid_constant__ PActionParams p) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.nrows * p.nact)
+    return;
+  const int k = t / p.nrows;
+  const long long i = p.rows[t % p.nrows];
+  if (i < p.off || i >= p.off + p.n)
+    return;
+  double a = p.actions[k][i - p.off];
+  for (int q = 0; q < p.nP; ++q) {
+    const double ck = p.pcoef[size_t(k) * p.nP + q];
+    for (int e = p.map_ptr[q]; e < p.map_ptr[q + 1]; ++e) {
+      const long long c = p.idx[e];
+      const long long d = i > c ? i - c : c - i;
+      if (d <= p.b)
+        a = __dadd_rn(a, __dmul_rn(band_entry(i, c, p.eps), __dmul_rn(p.val[e], ck)));
+    }
+  }
+  p.actions[k][i - p.off] = a;
+}
+
+static int rows_grid(itsolv_ctx* ctx, size_t n) {
+  return int(std::max<size_t>(1, std::min<size_t>((n + 255) / 256, size_t(ctx->num_sms) * 8)));
+}
+
+} // namespace itsolv
+
+using namespace itsolv;
+
+extern "C" {
+
+int itsolv_banded_apply_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offset, size_t n, int b, double eps,
+                            const double* x, const double* x_lo, const double* x_hi, double* y) {
+  if (n == 0)
+    return 0;
+  ITSOLV_REQUIRE(x != y, "itsolv_banded_apply_f64: in-place application is not supported");
+  ITSOLV_REQUIRE((row_offset == 0 || x_lo) && (row_offset + int64_t(n) == n_global || x_hi),
+                 "itsolv_banded_apply_f64: interior shard needs halo rows");
+  banded_apply_kernel<<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(n_global, row_offset, (long long)n, b, eps, x, x_lo,
+                                                                  x_hi, y);
+  ITSOLV_CUDA(cudaGetLastError());
+  ctx->counters.launches += 1;
+  return 0;
+}
+
+int itsolv_csr_apply_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offset, size_t n, int b, const int64_t* row_ptr,
+                         const int32_t* col, const double* val, const double* x, const double* x_lo, const double* x_hi,
+                         double* y) {
+  if (n == 0)
+    return 0;
+  ITSOLV_REQUIRE(x != y, "itsolv_csr_apply_f64: in-place application is not supported");
+  ITSOLV_REQUIRE((row_offset == 0 || x_lo) && (row_offset + int64_t(n) == n_global || x_hi),
+                 "itsolv_csr_apply_f64: interior shard needs halo rows");
+  csr_apply_kernel<<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(row_offset, (long long)n, b,
+                                                               reinterpret_cast<const long long*>(row_ptr), col, val, x,
+                                                               x_lo, x_hi, y);
+  ITSOLV_CUDA(cudaGetLastError());
+  ctx->counters.launches += 1;
+  return 0;
+}
+
+int itsolv_banded_fill_f64(itsolv_ctx* ctx, int kind, int k, int64_t row_offset, size_t n, double* out) {
+  if (n == 0)
+    return 0;
+  banded_fill_kernel<<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(kind, k, row_offset, (long long)n, out);
+  ITSOLV_CUDA(cudaGetLastError());
+  ctx->counters.launches += 1;
+  return 0;
+}
+
+int itsolv_example_apply_f64(itsolv_ctx* ctx, size_t n, const double* x, double* y) {
+  if (n == 0)
+    return 0;
+  ITSOLV_REQUIRE(x != y, "itsolv_example_apply_f64: in-place application is not supported");
+  example_apply_kernel<<<int((n + 127) / 128), 128, 0, ctx->stream>>>((long long)n, x, y);
+  ITSOLV_CUDA(cudaGetLastError());
+  ctx->counters.launches += 1;
+  return 0;
+}
+
+int itsolv_banded_p_action_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offset, size_t n, int b, double eps,
+                               int nact, double* const* actions, int nP, const int32_t* map_ptr, const int64_t* idx,
+                               const double* val, const double* pcoef) {
+  if (nact <= 0 || nP <= 0 || n == 0)
+    return 0;
+  ITSOLV_REQUIRE(nact <= ITSOLV_MAX_PANEL, "itsolv_banded_p_action_f64: too many action vectors");
+  const int nnz = map_ptr[nP];
+  std::vector<long long> rows;
+  rows.reserve(size_t(nnz) * (2 * b + 1));
+  for (int e = 0; e < nnz; ++e)
+    for (long long i = std::max<long long>(0, idx[e] - b); i <= std::min<long long>(n_global - 1, idx[e] + b); ++i)
+      if (i >= row_offset && i < row_offset + (long long)n)
+        rows.push_back(i);
+  std::sort(rows.begin(), rows.end());
+  rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+  if (rows.empty())
+    return 0;
+  auto a16 = [](size_t v) { return (v + 15) & ~size_t(15); };
+  const size_t off_rows = 0, off_ptr = a16(rows.size() * 8), off_idx = a16(off_ptr + size_t(nP + 1) * 4),
+               off_val = a16(off_idx + size_t(nnz) * 8), off_coef = a16(off_val + size_t(nnz) * 8),
+               bytes = a16(off_coef + size_t(nact) * nP * 8);
+  char *h = nullptr, *d = nullptr;
+  int slot = 0;
+  if (stage_acquire(ctx, bytes, &h, &d, &slot))
+    return 1;
+  std::memcpy(h + off_rows, rows.data(), rows.size() * 8);
+  std::memcpy(h + off_ptr, map_ptr, size_t(nP + 1) * 4);
+  std::memcpy(h + off_idx, idx, size_t(nnz) * 8);
+  std::memcpy(h + off_val, val, size_t(nnz) * 8);
+  std::memcpy(h + off_coef, pcoef, size_t(nact) * nP * 8);
+  if (stage_commit(ctx, slot, bytes))
+    return 1;
+  PActionParams p;
+  for (int k = 0; k < nact; ++k)
+    p.actions[k] = actions[k];
+  p.rows = reinterpret_cast<const long long*>(d + off_rows);
+  p.map_ptr = reinterpret_cast<const int*>(d + off_ptr);
+  p.idx = reinterpret_cast<const long long*>(d + off_idx);
+  p.val = reinterpret_cast<const double*>(d + off_val);
+  p.pcoef = reinterpret_cast<const double*>(d + off_coef);
+  p.off = row_offset;
+  p.n = (long long)n;
+  p.nrows = int(rows.size());
+  p.nact = nact;
+  p.nP = nP;
+  p.b = b;
+  p.eps = eps;
+  const int total = p.nrows * nact;
+  p_action_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(p);
+  ITSOLV_CUDA(cudaGetLastError());
+  ctx->counters.launches += 1;
+  return stage_done(ctx, slot);
+}
+
+} // extern "C"

@@ -1,0 +1,206 @@
+// select / select_max_dot: the n entries of a device vector that the reference's heap selection keeps
+// (reference src/molpro/linalg/array/util/select.h:28-55, util/select_max_dot.h:22-46; distributed merge
+// array/DistrArray.cpp:191-224). The reference keeps the n largest (key, index) PAIRS under lexicographic order,
+// key = v or |v| (max) / -v or -|v| (min), so among equal keys the higher index wins. That rule is reproduced exactly
+// by a most-significant-digit radix select over the 128-bit composite (order-preserving image of key, global index):
+// 8 histogram passes over the key bytes + the index bytes that can be non-zero, all on the device with no host round
+// trip, then one compaction pass. Runs once or twice per solve (initial guess, P-space choice), HBM-bound, 8n bytes/pass.
+#include <algorithm>
+#include <cstring>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+
+namespace itsolv {
+
+// layout of ctx->d_select (unsigned long long words)
+enum { SEL_KEY = 0, SEL_IDX = 1, SEL_REMAINING = 2, SEL_COUNT = 3, SEL_HIST = 16 };
+
+struct SelParams {
+  const double* x;
+  const double* y; // nullptr unless select_max_dot
+  size_t n;
+  unsigned long long offset; // global index of x[0]
+  int max, ignore_sign;
+};
+
+__device__ __forceinline__ double sel_value(const SelParams& p, size_t i) {
+  double v = p.x[i];
+  if (p.y)
+    return fabs(__dmul_rn(v, p.y[i]));
+  return p.ignore_sign ? fabs(v) : v;
+}
+//! order-preserving map of the reference's heap key onto unsigned integers; -0.0 and +0.0 compare equal there, so both map to +0.0
+__device__ __forceinline__ unsigned long long sel_key(const SelParams& p, double value) {
+  double key = (p.max || p.y) ? value : -value;
+  key = key + 0.0;
+  const long long b = __double_as_longlong(key);
+  return static_cast<unsigned long long>(b) ^ (static_cast<unsigned long long>(b >> 63) | 0x8000000000000000ull);
+}
+
+//! does the element agree with the digits fixed so far, and what is its digit `d` (0..7 key bytes, 8..15 index bytes)
+__device__ __forceinline__ bool sel_digit(unsigned long long u, unsigned long long gi, int d, unsigned long long kpre,
+                                          unsigned long long ipre, unsigned& digit) {
+  if (d < 8) {
+    if (d > 0 && (u >> (64 - 8 * d)) != (kpre >> (64 - 8 * d)))
+      return false;
+    digit = unsigned(u >> (56 - 8 * d)) & 0xFFu;
+    return true;
+  }
+  if (u != kpre)
+    return false;
+  const int dd = d - 8;
+  if (dd > 0 && (gi >> (64 - 8 * dd)) != (ipre >> (64 - 8 * dd)))
+    return false;
+  digit = unsigned(gi >> (56 - 8 * dd)) & 0xFFu;
+  return true;
+}
+
+__global__ void __launch_bounds__(256) select_hist_kernel(const __grid_constant__ SelParams p, int d,
+                                                          unsigned long long* __restrict__ state) {
+  __shared__ unsigned int hist[256];
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+  const unsigned long long kpre = state[SEL_KEY], ipre = state[SEL_IDX];
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n; i += size_t(gridDim.x) * blockDim.x) {
+    const unsigned long long u = sel_key(p, sel_value(p, i));
+    unsigned digit;
+    if (sel_digit(u, p.offset + i, d, kpre, ipre, digit))
+      atomicAdd(&hist[digit], 1u);
+  }
+  __syncthreads();
+  if (hist[threadIdx.x])
+    atomicAdd(&state[SEL_HIST + threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+}
+
+//! choose the bin that holds the boundary element: walk bins from the top until `remaining` elements are covered
+__global__ void select_pick_kernel(int d, unsigned long long* __restrict__ state) {
+  if (threadIdx.x != 0 || blockIdx.x != 0)
+    return;
+  unsigned long long remaining = state[SEL_REMAINING];
+  int chosen = 0;
+  for (int bin = 255; bin >= 0; --bin) {
+    const unsigned long long c = state[SEL_HIST + bin];
+    if (c >= remaining) {
+      chosen = bin;
+      break;
+    }
+    remaining -= c;
+  }
+  state[SEL_REMAINING] = remaining;
+  if (d < 8)
+    state[SEL_KEY] |= (unsigned long long)chosen << (56 - 8 * d);
+  else
+    state[SEL_IDX] |= (unsigned long long)chosen << (56 - 8 * (d - 8));
+  for (int bin = 0; bin < 256; ++bin)
+    state[SEL_HIST + bin] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+    select_compact_kernel(const __grid_constant__ SelParams p, unsigned long long* __restrict__ state,
+                          long long* __restrict__ out_idx, double* __restrict__ out_val, unsigned long long capacity) {
+  const unsigned long long kthr = state[SEL_KEY], ithr = state[SEL_IDX];
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n; i += size_t(gridDim.x) * blockDim.x) {
+    const double value = sel_value(p, i);
+    const unsigned long long u = sel_key(p, value);
+    const unsigned long long gi = p.offset + i;
+    if (u > kthr || (u == kthr && gi >= ithr)) {
+      const unsigned long long pos = atomicAdd(&state[SEL_COUNT], 1ull);
+      if (pos < capacity) {
+        out_idx[pos] = (long long)gi;
+        out_val[pos] = value;
+      }
+    }
+  }
+}
+
+static double host_key(double value, bool max) {
+  double key = max ? value : -value;
+  return key + 0.0;
+}
+
+} // namespace itsolv
+
+using namespace itsolv;
+
+extern "C" {
+
+int itsolv_select_merge(const int64_t* idx, const double* val, size_t ncand, size_t nsel, int max, int /*ignore_sign*/,
+                        int64_t* out_idx, double* out_val) {
+  // values arrive already as |v| when ignore_sign was requested; order by the reference's (key, index) pairs
+  std::vector<std::pair<std::pair<double, int64_t>, double>> c;
+  c.reserve(ncand);
+  for (size_t i = 0; i < ncand; ++i)
+    if (idx[i] >= 0)
+      c.push_back({{host_key(val[i], max != 0), idx[i]}, val[i]});
+  std::sort(c.begin(), c.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+  if (c.size() > nsel)
+    c.resize(nsel);
+  std::sort(c.begin(), c.end(), [](const auto& a, const auto& b) { return a.first.second < b.first.second; });
+  for (size_t i = 0; i < c.size(); ++i) {
+    out_idx[i] = c[i].first.second;
+    out_val[i] = c[i].second;
+  }
+  return int(c.size());
+}
+
+int itsolv_select_f64(itsolv_ctx* ctx, const double* x, const double* y, size_t n, size_t global_offset, size_t nsel,
+                      int max, int ignore_sign, int64_t* indices, double* values, int* nfound) {
+  ctx->counters.n_select++;
+  const int nranks = itsolv_comm_size(ctx);
+  ITSOLV_REQUIRE(nsel * 16 * size_t(nranks) <= ctx->stage_slot_bytes, "itsolv_select_f64: too many entries requested");
+  *nfound = 0;
+  if (nsel == 0)
+    return 0;
+  const size_t nloc = std::min(nsel, n);
+  CallScope scope(ctx, OP_OTHER, 8.0 * double(n) * (y ? 2 : 1));
+  // candidate buffer on the device: [idx(nsel) | val(nsel)] per rank, gathered rank after rank
+  char *h = nullptr, *d = nullptr;
+  int slot = 0;
+  if (stage_acquire(ctx, nsel * 16 * size_t(nranks), &h, &d, &slot))
+    return 1;
+  const int myrank = itsolv_comm_rank(ctx);
+  char* dmine = d + size_t(myrank) * nsel * 16;
+  long long* d_idx = reinterpret_cast<long long*>(dmine);
+  double* d_val = reinterpret_cast<double*>(dmine + nsel * 8);
+  ITSOLV_CUDA(cudaMemsetAsync(dmine, 0xFF, nsel * 8, ctx->stream)); // idx = -1: empty candidate
+  if (nloc > 0) {
+    SelParams p{x, y, n, (unsigned long long)global_offset, (max || y) ? 1 : 0, ignore_sign};
+    unsigned long long init[SEL_HIST + 256];
+    std::memset(init, 0, sizeof(init));
+    init[SEL_REMAINING] = nloc;
+    ITSOLV_CUDA(cudaMemcpyAsync(ctx->d_select, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    const int grid = int(std::min<size_t>((n + 255) / 256, size_t(ctx->num_sms) * 8));
+    // index bytes above the largest global index are zero for every element: skip those passes
+    int idx_bytes = 1;
+    while (idx_bytes < 8 && ((global_offset + n - 1) >> (8 * idx_bytes)) != 0)
+      ++idx_bytes;
+    for (int dgt = 0; dgt < 16; ++dgt) {
+      if (dgt >= 8 && dgt - 8 < 8 - idx_bytes)
+        continue;
+      select_hist_kernel<<<grid, 256, 0, ctx->stream>>>(p, dgt, ctx->d_select);
+      select_pick_kernel<<<1, 32, 0, ctx->stream>>>(dgt, ctx->d_select);
+      ctx->counters.launches += 2;
+    }
+    select_compact_kernel<<<grid, 256, 0, ctx->stream>>>(p, ctx->d_select, d_idx, d_val, nloc);
+    ctx->counters.launches += 1;
+    ITSOLV_CUDA(cudaGetLastError());
+  }
+  if (comm_allgather_device(ctx, dmine, d, nsel * 16))
+    return 1;
+  ITSOLV_CUDA(cudaMemcpyAsync(h, d, nsel * 16 * size_t(nranks), cudaMemcpyDeviceToHost, ctx->stream));
+  ITSOLV_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (stage_done(ctx, slot))
+    return 1;
+  std::vector<int64_t> cidx(nsel * nranks);
+  std::vector<double> cval(nsel * nranks);
+  for (int r = 0; r < nranks; ++r) {
+    std::memcpy(cidx.data() + size_t(r) * nsel, h + size_t(r) * nsel * 16, nsel * 8);
+    std::memcpy(cval.data() + size_t(r) * nsel, h + size_t(r) * nsel * 16 + nsel * 8, nsel * 8);
+  }
+  *nfound = itsolv_select_merge(cidx.data(), cval.data(), cidx.size(), nsel, (max || y) ? 1 : 0, ignore_sign, indices, values);
+  return 0;
+}
+
+} // extern "C"

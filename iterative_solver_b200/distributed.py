@@ -1,0 +1,37 @@
+"""One process per GPU: torch.distributed carries the NCCL unique id from rank 0 to the other ranks (plumbing); the
+communicator itself lives in libitsolv_b200.so and is what the kernels' all-reduces run on."""
+from __future__ import annotations
+
+import os
+
+from .api import Context
+
+
+def env_rank_world() -> tuple[int, int, int]:
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def broadcast_bytes(payload: bytes | None, nbytes: int, src: int = 0) -> bytes:
+    """broadcast a byte string over the default torch.distributed group (works on gloo and nccl)"""
+    import torch
+    import torch.distributed as dist
+
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    if dist.get_rank() == src:
+        t.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+    dist.broadcast(t, src=src)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def attach_communicator(ctx: Context) -> None:
+    """Give the context a communicator spanning the torch.distributed world (no-op for a single process)."""
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        ctx.init_comm(0, 1, b"\0" * 128)
+        return
+    uid = ctx.unique_id() if dist.get_rank() == 0 else None
+    uid = broadcast_bytes(uid, 128, 0)
+    ctx.init_comm(dist.get_rank(), dist.get_world_size(), uid)

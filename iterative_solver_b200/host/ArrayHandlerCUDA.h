@@ -1,0 +1,279 @@
+// ArrayHandlerCUDA / ArrayHandlerCUDASparse: the reference's vector-operation contract
+// (molpro::linalg::array::ArrayHandler<AL,AR>, reference src/molpro/linalg/array/ArrayHandler.h:161-437) implemented
+// on DistrArrayCUDA through the C ABI of include/itsolv_b200.h. They take the place that ArrayHandlerDistr /
+// ArrayHandlerDistrSparse (reference array/ArrayHandlerDistr.h:14-73, ArrayHandlerDistrSparse.h:18-80) have for the
+// MPI containers: inject them through the 7-argument ArrayHandlers constructor
+// (reference itsolv/ArrayHandlers.h:30-34) or use make_handlers() below. No arithmetic is done on the host.
+#ifndef ITSOLV_B200_HOST_ARRAYHANDLERCUDA_H
+#define ITSOLV_B200_HOST_ARRAYHANDLERCUDA_H
+#include <functional>
+#include <map>
+#include <memory>
+#include <vector>
+
+#include <molpro/linalg/array/ArrayHandler.h>
+#include <molpro/linalg/array/ArrayHandlerSparse.h>
+#include <molpro/linalg/itsolv/ArrayHandlers.h>
+
+#include "DistrArrayCUDA.h"
+
+namespace itsolv_b200 {
+
+using molpro::linalg::array::ArrayHandler;
+using molpro::linalg::itsolv::CVecRef;
+using molpro::linalg::itsolv::VecRef;
+using molpro::linalg::itsolv::subspace::Matrix;
+
+//! Optional observer of every number a handler returns to the solver ('d' dot, 'g' gemm_inner); used by parity tests
+using ResultObserver = std::function<void(char op, size_t rows, size_t cols, const double* values)>;
+
+class ArrayHandlerCUDA : public ArrayHandler<DistrArrayCUDA, DistrArrayCUDA> {
+public:
+  using Base = ArrayHandler<DistrArrayCUDA, DistrArrayCUDA>;
+  using AL = DistrArrayCUDA;
+  using AR = DistrArrayCUDA;
+  using typename Base::ProxyHandle;
+  using typename Base::value_type;
+  using typename Base::value_type_abs;
+
+  ArrayHandlerCUDA() = default;
+  explicit ArrayHandlerCUDA(ResultObserver observer) : m_observer(std::move(observer)) {}
+
+  AL copy(const AR& source) override {
+    this->m_counter->copy++;
+    return AL{source};
+  }
+  void copy(AL& x, const AR& y) override {
+    this->m_counter->copy++;
+    x.copy(y);
+  }
+  void scal(value_type alpha, AL& x) override {
+    this->m_counter->scal++;
+    x.scal(alpha);
+  }
+  void fill(value_type alpha, AL& x) override { x.fill(alpha); }
+  void axpy(value_type alpha, const AR& x, AL& y) override {
+    this->m_counter->axpy++;
+    y.axpy(alpha, x);
+  }
+  value_type dot(const AL& x, const AR& y) override {
+    this->m_counter->dot++;
+    const double d = x.dot(y);
+    if (m_observer)
+      m_observer('d', 1, 1, &d);
+    return d;
+  }
+
+  void gemm_outer(const Matrix<value_type> alphas, const CVecRef<AR>& xx, const VecRef<AL>& yy) override {
+    this->m_counter->gemm_outer++;
+    // shape rules of the reference's distributed implementation (array/util/gemm.h:66-71)
+    if (alphas.rows() != xx.size())
+      throw std::out_of_range("gemm_outer: dimensions of xx and alphas are different.");
+    if (alphas.cols() != yy.size())
+      throw std::out_of_range("gemm_outer: dimensions of yy and alphas are different.");
+    if (xx.empty() || yy.empty())
+      return;
+    std::vector<const double*> px(xx.size());
+    std::vector<double*> py(yy.size());
+    const AL& first = yy[0].get();
+    for (size_t i = 0; i < xx.size(); ++i) {
+      first.require_compatible(xx[i].get(), "gemm_outer");
+      px[i] = xx[i].get().data();
+    }
+    for (size_t j = 0; j < yy.size(); ++j) {
+      first.require_compatible(yy[j].get(), "gemm_outer");
+      py[j] = yy[j].get().data();
+    }
+    check(itsolv_gemm_outer_f64(first.context(), alphas.data().data(), int(xx.size()), int(yy.size()), px.data(),
+                                py.data(), first.local_size(), 0),
+          "ArrayHandlerCUDA::gemm_outer");
+  }
+
+  Matrix<value_type> gemm_inner(const CVecRef<AL>& xx, const CVecRef<AR>& yy) override {
+    this->m_counter->gemm_inner++;
+    auto mat = Matrix<value_type>({xx.size(), yy.size()});
+    if (xx.empty() || yy.empty())
+      return mat;
+    std::vector<const double*> px(xx.size()), py(yy.size());
+    const AL& first = xx[0].get();
+    for (size_t i = 0; i < xx.size(); ++i) {
+      first.require_compatible(xx[i].get(), "gemm_inner");
+      px[i] = xx[i].get().data();
+    }
+    for (size_t j = 0; j < yy.size(); ++j) {
+      first.require_compatible(yy[j].get(), "gemm_inner");
+      py[j] = yy[j].get().data();
+    }
+    std::vector<double> out(xx.size() * yy.size());
+    check(itsolv_gemm_inner_f64(first.context(), px.data(), int(xx.size()), py.data(), int(yy.size()),
+                                first.local_size(), out.data()),
+          "ArrayHandlerCUDA::gemm_inner");
+    for (size_t i = 0; i < mat.rows(); ++i)
+      for (size_t j = 0; j < mat.cols(); ++j)
+        mat(i, j) = out[i * mat.cols() + j];
+    if (m_observer)
+      m_observer('g', mat.rows(), mat.cols(), out.data());
+    return mat;
+  }
+
+  std::map<size_t, value_type_abs> select_max_dot(size_t n, const AL& x, const AR& y) override {
+    if (n > x.size() || n > y.size())
+      error("ArrayHandlerCUDA::select_max_dot() n is too large");
+    return x.select_max_dot(n, y);
+  }
+
+  std::map<size_t, value_type> select(size_t n, const AL& x, bool max = false, bool ignore_sign = false) override {
+    if (n > x.size())
+      error("ArrayHandlerCUDA::select() n is too large");
+    return x.select(n, max, ignore_sign);
+  }
+
+  ProxyHandle lazy_handle() override { return this->lazy_handle(*this); }
+
+protected:
+  using Base::error;
+  using Base::lazy_handle;
+  ResultObserver m_observer;
+};
+
+//! dense (device) x sparse (std::map on the host): the rp / qp handlers of the P-space
+class ArrayHandlerCUDASparse : public ArrayHandler<DistrArrayCUDA, std::map<size_t, double>> {
+public:
+  using AL = DistrArrayCUDA;
+  using AR = std::map<size_t, double>;
+  using Base = ArrayHandler<AL, AR>;
+  using typename Base::ProxyHandle;
+  using typename Base::value_type;
+  using typename Base::value_type_abs;
+
+  ArrayHandlerCUDASparse() = default;
+  explicit ArrayHandlerCUDASparse(ResultObserver observer) : m_observer(std::move(observer)) {}
+
+  AL copy(const AR&) override { throw std::logic_error("General construction of dense from sparse is ill-defined"); }
+
+  //! x = 0, then x[index] = value for the entries this rank owns (reference ArrayHandlerDistrSparse.h:30-38)
+  void copy(AL& x, const AR& y) override {
+    Packed p({std::cref(y)});
+    check(itsolv_sparse_copy_f64(x.context(), x.data(), x.local_size(), x.local_start(), int(p.idx.size()), p.idx.data(),
+                                 p.val.data()),
+          "ArrayHandlerCUDASparse::copy");
+  }
+  void scal(value_type, AL&) override {} // unary operations belong to the dense handler, as in the reference
+  void fill(value_type, AL&) override {}
+
+  void axpy(value_type alpha, const AR& x, AL& y) override {
+    this->m_counter->axpy++;
+    Packed p({std::cref(x)});
+    double* py = y.data();
+    check(itsolv_sparse_gemm_outer_f64(y.context(), &alpha, 1, 1, p.ptr.data(), p.idx.data(), p.val.data(), &py,
+                                       y.local_size(), y.local_start()),
+          "ArrayHandlerCUDASparse::axpy");
+  }
+
+  value_type dot(const AL& x, const AR& y) override {
+    this->m_counter->dot++;
+    Packed p({std::cref(y)});
+    const double* px = x.data();
+    double d = 0;
+    check(itsolv_sparse_gemm_inner_f64(x.context(), &px, 1, x.local_size(), x.local_start(), 1, p.ptr.data(),
+                                       p.idx.data(), p.val.data(), &d),
+          "ArrayHandlerCUDASparse::dot");
+    if (m_observer)
+      m_observer('d', 1, 1, &d);
+    return d;
+  }
+
+  //! alphas: rows <-> sparse xx, columns <-> dense yy (reference array/util/gemm.h:207-224)
+  void gemm_outer(const Matrix<value_type> alphas, const CVecRef<AR>& xx, const VecRef<AL>& yy) override {
+    this->m_counter->gemm_outer++;
+    if (alphas.rows() != xx.size() || alphas.cols() != yy.size())
+      throw std::out_of_range("gemm_outer: dimensions of alphas do not match xx, yy");
+    if (xx.empty() || yy.empty())
+      return;
+    Packed p(xx);
+    std::vector<double*> py(yy.size());
+    const AL& first = yy[0].get();
+    for (size_t j = 0; j < yy.size(); ++j) {
+      first.require_compatible(yy[j].get(), "gemm_outer");
+      py[j] = yy[j].get().data();
+    }
+    check(itsolv_sparse_gemm_outer_f64(first.context(), alphas.data().data(), int(xx.size()), int(yy.size()),
+                                       p.ptr.data(), p.idx.data(), p.val.data(), py.data(), first.local_size(),
+                                       first.local_start()),
+          "ArrayHandlerCUDASparse::gemm_outer");
+  }
+
+  Matrix<value_type> gemm_inner(const CVecRef<AL>& xx, const CVecRef<AR>& yy) override {
+    this->m_counter->gemm_inner++;
+    auto mat = Matrix<value_type>({xx.size(), yy.size()});
+    if (xx.empty() || yy.empty())
+      return mat;
+    Packed p(yy);
+    std::vector<const double*> px(xx.size());
+    const AL& first = xx[0].get();
+    for (size_t i = 0; i < xx.size(); ++i) {
+      first.require_compatible(xx[i].get(), "gemm_inner");
+      px[i] = xx[i].get().data();
+    }
+    std::vector<double> out(xx.size() * yy.size());
+    check(itsolv_sparse_gemm_inner_f64(first.context(), px.data(), int(xx.size()), first.local_size(),
+                                       first.local_start(), int(yy.size()), p.ptr.data(), p.idx.data(), p.val.data(),
+                                       out.data()),
+          "ArrayHandlerCUDASparse::gemm_inner");
+    for (size_t i = 0; i < mat.rows(); ++i)
+      for (size_t j = 0; j < mat.cols(); ++j)
+        mat(i, j) = out[i * mat.cols() + j];
+    if (m_observer)
+      m_observer('g', mat.rows(), mat.cols(), out.data());
+    return mat;
+  }
+
+  std::map<size_t, value_type_abs> select_max_dot(size_t, const AL&, const AR&) override {
+    error("ArrayHandlerCUDASparse::select_max_dot() is not provided (used by perturbation theory only)");
+    return {};
+  }
+
+  std::map<size_t, value_type> select(size_t n, const AL& x, bool max = false, bool ignore_sign = false) override {
+    if (n > x.size())
+      error("ArrayHandlerCUDASparse::select() n is too large");
+    return x.select(n, max, ignore_sign);
+  }
+
+  ProxyHandle lazy_handle() override { return this->lazy_handle(*this); }
+
+protected:
+  using Base::error;
+  using Base::lazy_handle;
+  ResultObserver m_observer;
+
+  //! std::map vectors packed CSR-like for the C ABI
+  struct Packed {
+    std::vector<int32_t> ptr;
+    std::vector<int64_t> idx;
+    std::vector<double> val;
+    explicit Packed(const CVecRef<AR>& maps) {
+      ptr.push_back(0);
+      for (const auto& m : maps) {
+        for (const auto& e : m.get()) {
+          idx.push_back(int64_t(e.first));
+          val.push_back(e.second);
+        }
+        ptr.push_back(int32_t(idx.size()));
+      }
+    }
+  };
+};
+
+using HandlersCUDA = molpro::linalg::itsolv::ArrayHandlers<DistrArrayCUDA, DistrArrayCUDA, std::map<size_t, double>>;
+
+//! The seven handlers of a solver whose R and Q containers are DistrArrayCUDA and whose P container is std::map
+inline std::shared_ptr<HandlersCUDA> make_handlers(ResultObserver observer = nullptr) {
+  using P = std::map<size_t, double>;
+  auto dense = std::make_shared<ArrayHandlerCUDA>(observer);
+  auto sparse = std::make_shared<ArrayHandlerCUDASparse>(observer);
+  auto pp = std::make_shared<molpro::linalg::array::ArrayHandlerSparse<P, P>>();
+  return std::make_shared<HandlersCUDA>(dense, dense, pp, dense, sparse, dense, sparse);
+}
+
+} // namespace itsolv_b200
+#endif

@@ -1,0 +1,172 @@
+// DistrArrayCUDA: row-sharded FP64 vector resident in the HBM of the calling rank's B200.
+//
+// It is the R/Q container handed to the reference's solver templates
+// (LinearEigensystemDavidson<DistrArrayCUDA, DistrArrayCUDA, std::map<size_t,double>>, ...). The solvers never touch
+// elements; they need value_type, copy/move construction and move assignment only
+// (reference src/molpro/linalg/itsolv/IterativeSolverTemplate.h:431-442, subspace/DSpace.h:41-45),
+// and every O(n) operation goes through ArrayHandlerCUDA. The sharding follows the reference's DistrArray:
+// contiguous chunks from util::make_distribution_spread_remainder (reference array/util/Distribution.h:99-110), one
+// chunk per rank of the context's communicator. The member functions mirror the names of the reference's DistrArray
+// (reference array/DistrArray.h:90-300) where the operation makes sense for device memory.
+#ifndef ITSOLV_B200_HOST_DISTRARRAYCUDA_H
+#define ITSOLV_B200_HOST_DISTRARRAYCUDA_H
+#include <cstddef>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include <itsolv_b200.h>
+
+namespace itsolv_b200 {
+
+//! Error raised by the CUDA backend; message comes from itsolv_last_error()
+struct CudaBackendError : public std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+inline void check(int rc, const char* where) {
+  if (rc != 0)
+    throw CudaBackendError(std::string(where) + ": " + itsolv_last_error());
+}
+
+class DistrArrayCUDA {
+public:
+  using value_type = double;
+  using index_type = size_t;
+
+  DistrArrayCUDA() = default;
+
+  //! Allocates this rank's shard of a vector of global length `dimension`; contents are unspecified
+  DistrArrayCUDA(size_t dimension, itsolv_ctx* ctx) : m_ctx(ctx), m_dimension(dimension) {
+    const int nranks = itsolv_comm_size(ctx), rank = itsolv_comm_rank(ctx);
+    std::vector<int64_t> borders(size_t(nranks) + 1);
+    itsolv_distribution(dimension, nranks, borders.data());
+    m_start = size_t(borders[rank]);
+    m_local = size_t(borders[rank + 1] - borders[rank]);
+    check(itsolv_alloc(m_ctx, m_local, &m_data), "DistrArrayCUDA: allocation");
+  }
+
+  DistrArrayCUDA(const DistrArrayCUDA& source)
+      : m_ctx(source.m_ctx), m_dimension(source.m_dimension), m_start(source.m_start), m_local(source.m_local) {
+    if (source.m_data) {
+      check(itsolv_alloc(m_ctx, m_local, &m_data), "DistrArrayCUDA: allocation");
+      check(itsolv_copy_f64(m_ctx, m_data, source.m_data, m_local), "DistrArrayCUDA: copy");
+    }
+  }
+
+  DistrArrayCUDA(DistrArrayCUDA&& source) noexcept { swap(source); }
+
+  DistrArrayCUDA& operator=(DistrArrayCUDA&& source) noexcept {
+    if (this != &source) {
+      release();
+      swap(source);
+    }
+    return *this;
+  }
+
+  DistrArrayCUDA& operator=(const DistrArrayCUDA& source) {
+    if (this == &source)
+      return *this;
+    if (!m_data || !compatible(source)) {
+      DistrArrayCUDA t(source);
+      release();
+      swap(t);
+    } else {
+      check(itsolv_copy_f64(m_ctx, m_data, source.m_data, m_local), "DistrArrayCUDA: copy");
+    }
+    return *this;
+  }
+
+  ~DistrArrayCUDA() { release(); }
+
+  //! global length, as DistrArray::size() (reference array/DistrArray.h:112)
+  size_t size() const { return m_dimension; }
+  bool empty() const { return m_data == nullptr; }
+  //! this rank's rows [start, start + local_size)
+  size_t local_size() const { return m_local; }
+  size_t local_start() const { return m_start; }
+  std::pair<size_t, size_t> local_range() const { return {m_start, m_start + m_local}; }
+  double* data() { return m_data; }
+  const double* data() const { return m_data; }
+  itsolv_ctx* context() const { return m_ctx; }
+
+  //! same global length and same sharding (reference DistrArray::compatible, array/DistrArray.h:117-120)
+  bool compatible(const DistrArrayCUDA& other) const {
+    return m_ctx == other.m_ctx && m_dimension == other.m_dimension && m_local == other.m_local && m_start == other.m_start;
+  }
+
+  // ---- device operations named after the reference's DistrArray members (array/DistrArray.cpp:43-138) ----
+  void fill(double a) { check(itsolv_fill_f64(m_ctx, a, m_data, m_local), "DistrArrayCUDA::fill"); }
+  void scal(double a) { check(itsolv_scal_f64(m_ctx, a, m_data, m_local), "DistrArrayCUDA::scal"); }
+  void copy(const DistrArrayCUDA& y) {
+    require_compatible(y, "copy");
+    check(itsolv_copy_f64(m_ctx, m_data, y.m_data, m_local), "DistrArrayCUDA::copy");
+  }
+  void axpy(double a, const DistrArrayCUDA& x) {
+    require_compatible(x, "axpy");
+    check(itsolv_axpy_f64(m_ctx, a, x.m_data, m_data, m_local), "DistrArrayCUDA::axpy");
+  }
+  double dot(const DistrArrayCUDA& y) const {
+    require_compatible(y, "dot");
+    double r = 0;
+    check(itsolv_dot_f64(m_ctx, m_data, y.m_data, m_local, &r), "DistrArrayCUDA::dot");
+    return r;
+  }
+  std::map<size_t, double> select(size_t n, bool max = false, bool ignore_sign = false) const {
+    return select_impl(n, nullptr, max, ignore_sign);
+  }
+  std::map<size_t, double> select_max_dot(size_t n, const DistrArrayCUDA& y) const {
+    require_compatible(y, "select_max_dot");
+    return select_impl(n, y.m_data, true, false);
+  }
+
+  // ---- host transfers of the local shard (tests, harness) ----
+  void upload(const double* host) { check(itsolv_upload(m_ctx, m_data, host, m_local), "DistrArrayCUDA::upload"); }
+  void download(double* host) const { check(itsolv_download(m_ctx, host, m_data, m_local), "DistrArrayCUDA::download"); }
+
+  void swap(DistrArrayCUDA& o) noexcept {
+    std::swap(m_ctx, o.m_ctx);
+    std::swap(m_dimension, o.m_dimension);
+    std::swap(m_start, o.m_start);
+    std::swap(m_local, o.m_local);
+    std::swap(m_data, o.m_data);
+  }
+
+  void require_compatible(const DistrArrayCUDA& o, const char* op) const {
+    if (!m_data || !o.m_data || !compatible(o))
+      throw std::runtime_error(std::string("DistrArrayCUDA::") + op + ": incompatible arrays");
+  }
+
+private:
+  std::map<size_t, double> select_impl(size_t n, const double* y, bool max, bool ignore_sign) const {
+    if (n > m_dimension)
+      throw std::runtime_error("DistrArrayCUDA::select: n is too large");
+    std::vector<int64_t> idx(n);
+    std::vector<double> val(n);
+    int found = 0;
+    check(itsolv_select_f64(m_ctx, m_data, y, m_local, m_start, n, max ? 1 : 0, ignore_sign ? 1 : 0, idx.data(),
+                            val.data(), &found),
+          "DistrArrayCUDA::select");
+    std::map<size_t, double> result;
+    for (int i = 0; i < found; ++i)
+      result.emplace(size_t(idx[i]), val[i]);
+    return result;
+  }
+
+  void release() noexcept {
+    if (m_data && m_ctx)
+      itsolv_free(m_ctx, m_data);
+    m_data = nullptr;
+  }
+
+  itsolv_ctx* m_ctx = nullptr;
+  size_t m_dimension = 0;
+  size_t m_start = 0;
+  size_t m_local = 0;
+  double* m_data = nullptr;
+};
+
+} // namespace itsolv_b200
+#endif
