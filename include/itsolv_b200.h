@@ -51,9 +51,9 @@ typedef struct itsolv_counters {
   int64_t n_dot, n_axpy, n_scal, n_copy, n_fill, n_gemm_inner, n_gemm_outer, n_precondition, n_select, n_sparse;
   double bytes;          /* algorithmic bytes of all calls */
   double device_seconds; /* only while profiling */
-  double bytes_gemm_inner, seconds_gemm_inner;
-  double bytes_gemm_outer, seconds_gemm_outer;
-  double bytes_blas1, seconds_blas1;
+  double bytes_gemm_inner, seconds_gemm_inner; /* gemm_inner_kernel launches: gemm_inner and dot (its 1 x 1 case) */
+  double bytes_gemm_outer, seconds_gemm_outer; /* gemm_outer_kernel launches */
+  double bytes_blas1, seconds_blas1;           /* streaming kernels: axpy, scal, copy, fill, preconditioner */
 } itsolv_counters;
 void itsolv_ctx_counters(itsolv_ctx* ctx, itsolv_counters* out);
 void itsolv_ctx_reset_counters(itsolv_ctx* ctx);

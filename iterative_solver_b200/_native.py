@@ -43,7 +43,10 @@ class SolveResult(C.Structure):
                 ("r_creations", C.c_int64), ("q_creations", C.c_int64), ("p_creations", C.c_int64),
                 ("d_creations", C.c_int64), ("n_dot", C.c_int64), ("n_axpy", C.c_int64), ("n_scal", C.c_int64),
                 ("n_copy", C.c_int64), ("n_fill", C.c_int64), ("n_gemm_inner", C.c_int64), ("n_gemm_outer", C.c_int64),
-                ("handler_bytes", C.c_double), ("handler_device_seconds", C.c_double), ("kernel_launches", C.c_int64)]
+                ("handler_bytes", C.c_double), ("handler_device_seconds", C.c_double), ("kernel_launches", C.c_int64),
+                ("device_ms_solve", C.c_double), ("bytes_gemm_inner", C.c_double), ("seconds_gemm_inner", C.c_double),
+                ("bytes_gemm_outer", C.c_double), ("seconds_gemm_outer", C.c_double), ("bytes_blas1", C.c_double),
+                ("seconds_blas1", C.c_double)]
 
 
 class TraceEntry(C.Structure):

@@ -92,6 +92,8 @@ struct CallScope {
   int cls;
   cudaEvent_t start = nullptr;
   CallScope(itsolv_ctx* c, int cls, double bytes);
+  //! record the closing event now (after the last kernel launch, before any host synchronisation)
+  void stop();
   ~CallScope();
 };
 void drain_pending(itsolv_ctx* ctx);

@@ -43,7 +43,9 @@ CallScope::CallScope(itsolv_ctx* c, int cls_, double bytes) : ctx(c), cls(cls_) 
   }
 }
 
-CallScope::~CallScope() {
+CallScope::~CallScope() { stop(); }
+
+void CallScope::stop() {
   if (!start)
     return;
   cudaEvent_t stop;
@@ -56,6 +58,7 @@ CallScope::~CallScope() {
   }
   cudaEventRecord(stop, ctx->stream);
   ctx->pending.push_back({start, stop, cls});
+  start = nullptr;
   if (ctx->pending.size() > 4096)
     drain_pending(ctx);
 }

@@ -442,6 +442,7 @@ int itsolv_gemm_inner_f64(itsolv_ctx* ctx, const double* const* xx, int k, const
       CallScope scope(ctx, OP_GEMM_INNER, distinct_bytes(xx + i0, kb, yy + j0, mb, n));
       if (gemm_inner_device(ctx, xx + i0, kb, yy + j0, mb, n))
         return 1;
+      scope.stop();
       if (kb == k && mb == m) {
         if (finish_result(ctx, kb * mb, out))
           return 1;
@@ -460,9 +461,11 @@ int itsolv_gemm_inner_f64(itsolv_ctx* ctx, const double* const* xx, int k, const
 
 int itsolv_dot_f64(itsolv_ctx* ctx, const double* x, const double* y, size_t n, double* result) {
   ctx->counters.n_dot++;
-  CallScope scope(ctx, OP_BLAS1, (x == y ? 8.0 : 16.0) * double(n));
+  // a dot is the 1 x 1 case of the panel kernel and is accounted with it
+  CallScope scope(ctx, OP_GEMM_INNER, (x == y ? 8.0 : 16.0) * double(n));
   if (gemm_inner_device(ctx, &x, 1, &y, 1, n))
     return 1;
+  scope.stop();
   return finish_result(ctx, 1, result);
 }
 

@@ -57,6 +57,7 @@ inline double now_seconds() {
  *   size_t n_local();
  *   ProblemT& problem();                              Problem<R> with make_rhs(k, R&), seconds_action, seconds_precond
  *   void synchronize();                               wait for outstanding device work (no-op on the host)
+ *   void timer_start(); double timer_stop_ms();       device stopwatch around solve() (0 on the host)
  */
 template <class Backend>
 int run_solve(const itsolv_solve_spec& spec, Backend& backend, itsolv_solve_result& res, double* solutions) {
@@ -90,6 +91,7 @@ int run_solve(const itsolv_solve_spec& spec, Backend& backend, itsolv_solve_resu
       solver.set_max_size_qspace(spec.max_size_qspace);
   };
   auto finish = [&](auto& solver, bool converged, double t0) {
+    res.device_ms_solve = backend.timer_stop_ms();
     backend.synchronize();
     res.seconds_solve = now_seconds() - t0;
     res.converged = converged ? 1 : 0;
@@ -134,6 +136,7 @@ int run_solve(const itsolv_solve_spec& spec, Backend& backend, itsolv_solve_resu
       solver.set_max_p(spec.max_p);
     backend.synchronize();
     const double t0 = now_seconds();
+    backend.timer_start();
     const bool ok = solver.solve(parameters, actions, problem, true);
     finish(solver, ok, t0);
     const auto ev = solver.eigenvalues();
@@ -161,6 +164,7 @@ int run_solve(const itsolv_solve_spec& spec, Backend& backend, itsolv_solve_resu
     }
     backend.synchronize();
     const double t0 = now_seconds();
+    backend.timer_start();
     const bool ok = solver.solve(parameters, actions, problem, false);
     finish(solver, ok, t0);
     export_solutions(solver);
@@ -169,6 +173,7 @@ int run_solve(const itsolv_solve_spec& spec, Backend& backend, itsolv_solve_resu
     configure(solver);
     backend.synchronize();
     const double t0 = now_seconds();
+    backend.timer_start();
     const bool ok = solver.solve(parameters[0], actions[0], problem, false);
     finish(solver, ok, t0);
     if (solutions) {

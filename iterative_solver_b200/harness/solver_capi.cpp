@@ -238,6 +238,12 @@ struct DeviceBackend {
   size_t n_local() { return prob.nloc; }
   DeviceProblem& problem() { return prob; }
   void synchronize() { check(itsolv_ctx_synchronize(ctx), "synchronize"); }
+  void timer_start() { check(itsolv_ctx_timer_start(ctx), "timer"); }
+  double timer_stop_ms() {
+    double ms = 0;
+    check(itsolv_ctx_timer_stop(ctx, &ms), "timer");
+    return ms;
+  }
 };
 
 void fill_counters(itsolv_ctx* ctx, itsolv_solve_result* result) {
@@ -253,6 +259,12 @@ void fill_counters(itsolv_ctx* ctx, itsolv_solve_result* result) {
   result->handler_bytes = c.bytes;
   result->handler_device_seconds = c.device_seconds;
   result->kernel_launches = c.launches;
+  result->bytes_gemm_inner = c.bytes_gemm_inner;
+  result->seconds_gemm_inner = c.seconds_gemm_inner;
+  result->bytes_gemm_outer = c.bytes_gemm_outer;
+  result->seconds_gemm_outer = c.seconds_gemm_outer;
+  result->bytes_blas1 = c.bytes_blas1;
+  result->seconds_blas1 = c.seconds_blas1;
 }
 
 template <class F>

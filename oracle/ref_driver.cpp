@@ -200,6 +200,8 @@ struct HostBackend {
   size_t n_local() { return n; }
   ProblemT& problem() { return prob; }
   void synchronize() {}
+  void timer_start() {}
+  double timer_stop_ms() { return 0; }
 };
 
 Vec to_vec(const double* p, size_t n) { return Vec(p, p + n); }

@@ -23,8 +23,11 @@ def oracle():
 @pytest.fixture(scope="session")
 def ctx():
     """One context on cuda:0 for the whole session. Fails (does not skip) when the CUDA path is unavailable."""
+    import torch
+
     import iterative_solver_b200 as pkg
-    c = pkg.Context(0)
+    # issue the kernels on torch's current stream so that they are ordered with the test's tensor copies
+    c = pkg.Context(0, stream=torch.cuda.current_stream().cuda_stream)
     c.init_comm(0, 1, b"\0" * 128)
     yield c
     c.close()

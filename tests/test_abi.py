@@ -1,0 +1,48 @@
+"""The drop-in boundary: both shared libraries load without a GPU and export every symbol the public headers declare;
+compute calls fail loudly (no CPU fallback) when there is no device."""
+import os
+import re
+
+import pytest
+
+from iterative_solver_b200 import _native as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(itsolv_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_kernel_library_exports_every_declared_symbol():
+    lib = N.kernels()
+    names = declared("itsolv_b200.h")
+    assert len(names) >= 40
+    for name in names:
+        assert hasattr(lib, name), f"{name} is declared in include/itsolv_b200.h but not exported"
+    assert sorted(N.KERNEL_API) == names, "the ctypes table must cover exactly the header"
+
+
+def test_host_library_exports_every_declared_symbol():
+    lib = N.host()
+    names = declared("itsolv_b200_harness.h")
+    for name in names:
+        assert hasattr(lib, name), f"{name} is declared in include/itsolv_b200_harness.h but not exported"
+    assert sorted(N.HARNESS_API) == names
+
+
+def test_struct_layouts_match_the_header():
+    import ctypes as C
+    assert C.sizeof(N.SolveSpec) == 80
+    assert C.sizeof(N.SolveResult) == 16 + 2 * 64 * 8 + 3 * 8 + 4 * 8 + 7 * 8 + 2 * 8 + 8 + 7 * 8
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from iterative_solver_b200 import BackendError, Context
+    with pytest.raises(BackendError):
+        Context(0)

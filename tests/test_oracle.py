@@ -1,0 +1,148 @@
+"""Pins the CPU oracle (TEST INFRASTRUCTURE, oracle/): the plain-C restatement against (a) the golden vectors held by
+the reference's own tests, (b) fixtures generated from the reference's own templates (tests/golden/, made by
+tests/golden/make_golden.py) and (c) those templates themselves, bit for bit, when oracle/_ref/libitsolv_ref.so is
+built. Runs without a GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from iterative_solver_b200 import _native as N
+from iterative_solver_b200 import harness as H
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def inputs(seed=2024, n=4099):
+    rng = np.random.default_rng(seed)
+    X, Y = rng.standard_normal((4, n)), rng.standard_normal((6, n))
+    alpha = rng.standard_normal((4, 6))
+    return rng, X, Y, alpha
+
+
+def test_kat_modified_gram_schmidt(oracle):
+    """reference test/itsolv/subspace/test_util.cpp:154-173"""
+    V = np.array([[1., 1., 1., 1.], [1., 1. / 5., 1. / 10., 1. / 15.], [1. / 3., 1. / 6., 1. / 9., 1. / 12.],
+                  [1. / 2., 1. / 4., 1. / 6., 1. / 8.]])
+    ref = np.array([[0.5, 0.5, 0.5, 0.5],
+                    [0.858898629520365, -0.184826287365142, -0.3152919019758303, -0.3587804401793933],
+                    [-0.1096025454090415, 0.783967708523809, -0.06699956264207202, -0.6073656004726955]])
+    out, nulls = oracle.c.modified_gram_schmidt(V, 1e-14)
+    assert nulls == [3]
+    assert np.abs(out[:3] - ref).max() <= 1e-14
+
+
+def test_kat_select_max_dot(oracle):
+    """reference test/array/testArrayHandlerIterable.cpp:57-69"""
+    x = np.array([1., -2., 1., 0., 3., 0., -4., 1.])
+    idx, val = oracle.c.select(x, 3, y=np.ones(8))
+    assert dict(zip(idx.tolist(), val.tolist())) == {6: 4.0, 4: 3.0, 1: 2.0}
+
+
+def test_kat_sparse_axpy_dot(oracle):
+    """reference test/array/testArrayHandlers.cpp:27-60"""
+    m = {1: 1.0, 3: 2.0, 6: 3.0, 11: 4.0}
+    y = np.full(20, 0.5)
+    out = oracle.c.sparse_gemm_outer(np.array([[2.0]]), [m], y[None, :])[0]
+    want = y.copy()
+    for i, v in m.items():
+        want[i] += 2.0 * v
+    assert np.array_equal(out, want)
+    assert oracle.c.sparse_gemm_inner(np.full((1, 20), 0.5), [m])[0, 0] == 0.5 + 0.5 * 2. + 0.5 * 3. + 0.5 * 4.
+
+
+def test_gemm_equals_loops_of_dot_and_axpy(oracle):
+    """the property the reference asserts for every handler family (test/array/testGemm.cpp:58-88, 290-326)"""
+    _, X, Y, alpha = inputs()
+    G = oracle.c.gemm_inner(X, Y)
+    for i in range(4):
+        for j in range(6):
+            assert G[i, j] == oracle.c.dot(X[i].copy(), Y[j].copy())
+    out = oracle.c.gemm_outer(alpha, X, Y)
+    want = Y.copy()
+    for i in range(4):
+        for j in range(6):
+            want[j] = oracle.c.axpy(alpha[i, j], X[i].copy(), want[j].copy())
+    assert np.array_equal(out, want)
+
+
+def test_c_oracle_against_reference_fixtures(oracle):
+    g = np.load(os.path.join(GOLD, "handler_golden.npz"))
+    rng, X, Y, alpha = inputs(int(g["seed"]), int(g["n"]))
+    n = X.shape[1]
+    shift = np.array([0.9, 1.9, 2.9, 3.9])
+    diag = np.arange(1, n + 1, dtype=np.float64)
+    c = oracle.c
+    assert np.array_equal(c.gemm_inner(X, Y), g["gemm_inner"])
+    assert np.array_equal(c.gemm_outer(alpha, X, Y), g["gemm_outer"])
+    assert np.array_equal(c.axpy(0.37, X[0].copy(), Y[0].copy()), g["axpy"])
+    assert np.array_equal(c.scal(-1.7, X[1].copy()), g["scal"])
+    assert c.dot(X[0].copy(), Y[0].copy()) == g["dot"][0]
+    assert np.array_equal(c.precondition(X, shift, diag), g["precondition"])
+    xr = np.round(X[2], 1)
+    for name, kw in (("select_min", {}), ("select_max", {"max": True}),
+                     ("select_absmax", {"max": True, "ignore_sign": True})):
+        i, v = c.select(xr.copy(), 25, **kw)
+        assert np.array_equal(i, g[name + "_idx"]) and np.array_equal(v, g[name + "_val"])
+    i, v = c.select(xr.copy(), 25, y=np.round(Y[2], 1).copy())
+    assert np.array_equal(i, g["select_maxdot_idx"]) and np.array_equal(v, g["select_maxdot_val"])
+    V, nulls = c.modified_gram_schmidt(np.vstack([X, X[0] + X[1]]), 1e-10)
+    assert np.array_equal(V, g["mgs"]) and nulls == g["mgs_nulls"].tolist()
+    maps = [{int(i): float(w) for i, w in zip(rng.choice(n, 3, replace=False), rng.standard_normal(3))} for _ in range(5)]
+    assert np.array_equal(c.sparse_gemm_inner(X, maps), g["sparse_gemm_inner"])
+    assert np.array_equal(c.sparse_gemm_outer(rng.standard_normal((5, 4)), maps, X), g["sparse_gemm_outer"])
+    assert np.array_equal(c.banded_apply(X[3].copy(), 4, 1e-3), g["banded_apply"])
+    assert np.array_equal(c.distribution(10, 3), g["distribution_10_3"])
+    assert np.array_equal(c.distribution(2_000_000_001, 8), g["distribution_2e9_8"])
+
+
+def test_c_oracle_against_reference_build(oracle):
+    """bit-for-bit against the reference's own ArrayHandlerIterable on fresh random inputs of ragged sizes"""
+    if oracle.ref is None:
+        pytest.skip("oracle/_ref/libitsolv_ref.so needs /root/reference; covered by the committed fixtures")
+    c, r = oracle.c, oracle.ref
+    for n in (1, 2, 7, 64, 1001):
+        rng = np.random.default_rng(n)
+        X, Y = rng.standard_normal((3, n)), rng.standard_normal((5, n))
+        alpha = rng.standard_normal((3, 5))
+        assert np.array_equal(c.gemm_inner(X, Y), r.gemm_inner(X, Y))
+        assert np.array_equal(c.gemm_outer(alpha, X, Y), r.gemm_outer(alpha, X, Y))
+        assert np.array_equal(c.precondition(X, [0.1, 0.2, 0.3], np.arange(1., n + 1)),
+                              r.precondition(X, [0.1, 0.2, 0.3], np.arange(1., n + 1)))
+        xr = np.round(X[0], 1)
+        for kw in ({}, {"max": True}, {"max": True, "ignore_sign": True}, {"ignore_sign": True}):
+            a, b = c.select(xr.copy(), min(n, 4), **kw), r.select(xr.copy(), min(n, 4), **kw)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        assert np.array_equal(c.banded_apply(X[1].copy(), 4, 1e-3), r.banded_apply(X[1].copy(), 4, 1e-3))
+    for n, p in ((0, 1), (7, 8), (10, 3), (1000, 7)):
+        assert np.array_equal(c.distribution(n, p), r.distribution(n, p))
+
+
+def test_reference_build_reproduces_its_fixtures(oracle):
+    """the solve fixtures are stable outputs of the reference build (and of the LAPACK restatement of its helper)"""
+    if oracle.ref is None:
+        pytest.skip("oracle/_ref/libitsolv_ref.so needs /root/reference")
+    with open(os.path.join(GOLD, "solve_golden.json")) as f:
+        golden = json.load(f)
+    for name in ("example_davidson_n20_r1", "example_davidson_n20_r2", "example_lineq_n20_r1", "example_diis_n20",
+                 "banded_davidson_n30000_r6_qcap8"):
+        want = golden[name]
+        res, _ = oracle.ref.solve(H.make_spec(**want["spec"]))
+        assert res.iterations == want["iterations"]
+        assert [res.errors[i] for i in range(res.nroots)] == want["errors"]
+
+
+def test_config0_example_problem_against_numpy(oracle):
+    """BASELINE.json configs[0] (examples/LinearEigensystemExample.cpp): eigenvalues of the ExampleProblem matrix
+    from an independent dense solver"""
+    with open(os.path.join(GOLD, "solve_golden.json")) as f:
+        golden = json.load(f)
+    for name, n in (("example_davidson_n20_r2", 20), ("example_davidson_n200_r4_herm", 200)):
+        i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+        M = np.where(i == j, i + 1.0, 0.001 * ((i + j) % n))
+        ev = np.linalg.eigvalsh(M)
+        got = np.array(golden[name]["eigenvalues"])
+        assert np.abs(got - ev[:got.size]).max() <= 1e-12
+    assert golden["example_davidson_n20_r1"]["iterations"] == 5  # BASELINE.md probe: 5 iterations, 0.999813133574363
+    assert abs(golden["example_davidson_n20_r1"]["eigenvalues"][0] - 0.999813133574363) < 1e-14
