@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json: Davidson iterations/s and subspace-update HBM GB/s.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    (the reference's own CPU path on the host cores)
+
+Workload at N=1 = BASELINE.json configs[1]: synthetic diagonally dominant banded symmetric CSR matrix, n = 1e7, 4 roots,
+LinearEigensystemDavidson FP64, hermitian, R/Q containers DistrArrayCUDA, handlers ArrayHandlerCUDA. At N>1 every GPU
+keeps a 1e7-row shard (weak scaling; vectors row-sharded, partial Gram matrices all-reduced over NCCL).
+A step is one complete solve() (operator resident in HBM). Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+N_PER_GPU = 10_000_000
+NROOTS = 4
+HALF_BANDWIDTH = 4
+EPS = 1e-3
+METRIC = "davidson_iterations_per_s"
+UNIT = "iterations/s"
+
+
+def workload_name(n_per_gpu, nroots):
+    return (f"BASELINE.json configs[1]: banded symmetric CSR operator (half bandwidth {HALF_BANDWIDTH}, eps {EPS}), "
+            f"n={n_per_gpu:.0e} rows per GPU, {nroots} roots, LinearEigensystemDavidson FP64, hermitian")
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled during the timed region"""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.thread = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def reference_arm(args):
+    """The reference's own CPU path (std::vector + ArrayHandlerIterable driven by its LinearEigensystemDavidson
+    template, compiled in place into oracle/_ref) on the host cores. The path is single-threaded by construction
+    (no OpenMP / threads anywhere in it), so cores = 1."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import itsolv_oracle_lib
+    from iterative_solver_b200 import _native as N
+    from iterative_solver_b200 import harness as H
+    o = itsolv_oracle_lib.load()
+    if o.ref is None:
+        raise SystemExit("oracle/_ref/libitsolv_ref.so is missing: run __graft_entry__.build() where /root/reference exists")
+    # bounded sample: the same solve at the largest n (<= the full 1e7) for which steps+warmup solves end in ~4 minutes;
+    # the path streams vectors (time is linear in n), so the sample's rate is scaled by n_sample / n_full
+    per_row_seconds = 2.4e-6  # measured ~2.2 us per row per solve on this class of host
+    budget = 220.0
+    n_sample = args.n
+    for cand in (args.n, args.n // 2, args.n // 5, args.n // 10, args.n // 20, args.n // 50):
+        n_sample = cand
+        if (args.steps + args.warmup) * cand * per_row_seconds <= budget:
+            break
+    spec = H.make_spec(n_sample, kind=N.KIND_DAVIDSON, nroots=args.roots, hermitian=1, half_bandwidth=HALF_BANDWIDTH,
+                       eps=EPS)
+    for _ in range(args.warmup):
+        o.ref.solve(spec)
+    iterations, seconds = 0, 0.0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        res, _ = o.ref.solve(spec)
+        seconds += time.perf_counter() - t0
+        iterations += res.iterations
+    scale = n_sample / args.n
+    value = iterations / seconds * scale
+    sample = (f"{args.steps} solve(s) of the same operator at n={n_sample} "
+              f"({'the full workload' if n_sample == args.n else 'rate scaled by n_sample/n, the path is linear in n'})")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": seconds / args.steps * 1e3 / scale, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.n, args.roots), "n_per_gpu": args.n, "nroots": args.roots},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "iterations_per_solve": iterations / args.steps,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=N_PER_GPU, help="rows per GPU")
+    ap.add_argument("--roots", type=int, default=NROOTS)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--min-warmup", type=int, default=3, help="profiling runs only: allow fewer than 3 warm-up steps")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import iterative_solver_b200 as pkg
+    from iterative_solver_b200 import _native as N
+    from iterative_solver_b200 import distributed as D
+    from iterative_solver_b200 import harness as H
+
+    rank, world, local_rank = D.env_rank_world()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = pkg.Context(local_rank)
+    D.attach_communicator(ctx)
+
+    n_global = args.n * world
+    spec = H.make_spec(n_global, kind=N.KIND_DAVIDSON, nroots=args.roots, hermitian=1, half_bandwidth=HALF_BANDWIDTH,
+                       eps=EPS, explicit_csr=1)
+    borders = pkg.distribution(n_global, world)
+    lo, hi = int(borders[rank]), int(borders[rank + 1])
+
+    # ---- device-resident leg: operator (stored CSR) in HBM before the timed region starts
+    problem = H.Problem(ctx, spec)
+    for _ in range(max(args.warmup, args.min_warmup)):
+        problem.solve(spec)
+    ctx.set_profiling(True)
+    lib = N.kernels()
+    lib.itsolv_comm_barrier(ctx.handle)
+    torch.cuda.synchronize()
+    iterations, launches = 0, 0
+    agg = dict(bytes=0.0, secs=0.0, bgi=0.0, sgi=0.0, bgo=0.0, sgo=0.0, bb1=0.0, sb1=0.0, action=0.0)
+    with ClockSampler(local_rank) as clocks:
+        ctx.timer_start()
+        for _ in range(args.steps):
+            res = problem.solve(spec)
+            iterations += res.iterations
+            launches += res.kernel_launches
+            agg["bytes"] += res.handler_bytes
+            agg["secs"] += res.handler_device_seconds
+            agg["bgi"] += res.bytes_gemm_inner
+            agg["sgi"] += res.seconds_gemm_inner
+            agg["bgo"] += res.bytes_gemm_outer
+            agg["sgo"] += res.seconds_gemm_outer
+            agg["bb1"] += res.bytes_blas1
+            agg["sb1"] += res.seconds_blas1
+        ms = ctx.timer_stop()
+        lib.itsolv_comm_barrier(ctx.handle)
+        torch.cuda.synchronize()
+    ctx.set_profiling(False)
+    converged, eig = res.converged, [res.eigenvalues[i] for i in range(args.roots)]
+    ms_max = float(ctx.allreduce_host(np.array([ms]), op_max=True)[0])
+    sums = ctx.allreduce_host(np.array([agg["bytes"], agg["bgi"], agg["bgo"], agg["bb1"], float(launches)]))
+    maxs = ctx.allreduce_host(np.array([agg["secs"], agg["sgi"], agg["sgo"], agg["sb1"]]), op_max=True)
+    value = world * iterations / (ms_max * 1e-3)  # shard-iterations per second: every rank iterates over its 1e7-row shard
+    problem.close()
+
+    # ---- end-to-end leg: the caller owns the operator as host CSR (pinned); every step uploads it, solves, and downloads
+    # eigenvalues and the solution vectors
+    e2e = None
+    if not args.no_e2e:
+        row_ptr, col, val, diag = H.banded_csr_host(n_global, HALF_BANDWIDTH, EPS, lo, hi)
+        pinned = [torch.from_numpy(a).pin_memory() for a in (row_ptr, col, val, diag)]
+        row_ptr, col, val, diag = [t.numpy() for t in pinned]
+        spec_e = H.make_spec(n_global, kind=N.KIND_DAVIDSON, nroots=args.roots, hermitian=1,
+                             half_bandwidth=HALF_BANDWIDTH, eps=EPS)
+        sol = torch.empty((args.roots, hi - lo), dtype=torch.float64).pin_memory()
+        sol_np = sol.numpy()
+        e_steps = max(1, min(args.steps, 3))
+
+        def one_e2e():
+            p = H.Problem(ctx, spec_e, csr=(row_ptr, col, val, diag))
+            r = p.solve(spec_e, solutions=sol_np)
+            p.close()
+            return r
+
+        one_e2e()
+        lib.itsolv_comm_barrier(ctx.handle)
+        torch.cuda.synchronize()
+        e_iter = 0
+        ctx.timer_start()
+        for _ in range(e_steps):
+            e_iter += one_e2e().iterations
+        e_ms = ctx.timer_stop()
+        lib.itsolv_comm_barrier(ctx.handle)
+        e_ms = float(ctx.allreduce_host(np.array([e_ms]), op_max=True)[0])
+        h2d = row_ptr.nbytes + col.nbytes + val.nbytes + diag.nbytes
+        d2h = sol_np.nbytes + 8 * args.roots * 2
+        e2e = {"value": world * e_iter / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": e_steps, "ms_per_step": e_ms / e_steps,
+               "api": "itsolv_harness_problem_create(host CSR) + itsolv_harness_problem_solve(host solutions)"}
+        del pinned, sol
+
+    # ---- CPU baseline beside it (rank 0, single GPU runs only): the reference's own std::vector path, full workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import itsolv_oracle_lib
+        o = itsolv_oracle_lib.load()
+        if o.ref is not None:
+            spec_c = H.make_spec(args.n, kind=N.KIND_DAVIDSON, nroots=args.roots, hermitian=1,
+                                 half_bandwidth=HALF_BANDWIDTH, eps=EPS)
+            t0 = time.perf_counter()
+            rres, _ = o.ref.solve(spec_c)
+            dt = time.perf_counter() - t0
+            same = (rres.iterations * args.steps == iterations and
+                    max(abs(rres.eigenvalues[i] / eig[i] - 1) for i in range(args.roots)) <= 1e-10)
+            cpu = {"value": rres.iterations / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+                   "sample": f"1 solve of the full workload (n={args.n}, {args.roots} roots) by the reference's "
+                             f"std::vector/ArrayHandlerIterable path, {dt:.1f} s; host has {os.cpu_count()} logical cores, "
+                             f"the path is single-threaded", "parity_with_gpu_run": bool(same)}
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        gi_gbs = agg_gbs(sums[1] / world, maxs[1])
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, args.min_warmup),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.n, args.roots), "n_per_gpu": args.n, "n_global": n_global,
+                       "nroots": args.roots, "sharding": f"rows/{world}" if world > 1 else "none",
+                       "l2": "inputs larger than L2 (each vector 80 MB, ~40 live vectors)",
+                       "value_unit_note": "iterations/s x number of 1e7-row shards (weak scaling)"},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(sums[4]),
+            "roofline": {"bound": "hbm", "kernel": "gemm_inner_kernel (gemm_inner and its 1x1 case dot)",
+                         "achieved": gi_gbs, "peak": peak, "unit": "GB/s", "frac": gi_gbs / peak if peak else None,
+                         "peak_source": peak_src, "traffic": None,
+                         "launch_share_of_handler_time": maxs[1] / maxs[0] if maxs[0] else None},
+            "cpu_baseline": cpu,
+            "subspace_update": {"gbs_per_gpu": agg_gbs(sums[0] / world, maxs[0]),
+                                "frac_of_measured_hbm": agg_gbs(sums[0] / world, maxs[0]) / peak,
+                                "gemm_outer_gbs": agg_gbs(sums[2] / world, maxs[2]),
+                                "streaming_gbs": agg_gbs(sums[3] / world, maxs[3]),
+                                "device_seconds_per_step": maxs[0] / args.steps},
+            "iterations_per_solve": iterations / args.steps, "converged": int(converged), "eigenvalues": eig,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def agg_gbs(nbytes, seconds):
+    return float(nbytes / seconds / 1e9) if seconds else 0.0
+
+
+if __name__ == "__main__":
+    main()

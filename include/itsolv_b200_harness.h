@@ -94,6 +94,19 @@ int itsolv_harness_solve_host_csr(struct itsolv_ctx* ctx, const itsolv_solve_spe
                                   itsolv_solve_result* result, double* solutions);
 const char* itsolv_harness_last_error(void);
 
+/*
+ * The same two calls split so that the operator stays resident in HBM between solves: create uploads (or, with
+ * row_ptr == NULL, generates: stored CSR when spec->explicit_csr, else entries computed inside the SpMV kernel) the
+ * operator once; solve may then be called repeatedly. All ranks call collectively.
+ */
+typedef struct itsolv_harness_problem itsolv_harness_problem;
+int itsolv_harness_problem_create(struct itsolv_ctx* ctx, const itsolv_solve_spec* spec, const int64_t* row_ptr,
+                                  const int32_t* col, const double* val, const double* diag,
+                                  itsolv_harness_problem** problem);
+int itsolv_harness_problem_solve(itsolv_harness_problem* problem, const itsolv_solve_spec* spec,
+                                 itsolv_solve_result* result, double* solutions);
+void itsolv_harness_problem_destroy(itsolv_harness_problem* problem);
+
 size_t itsolv_harness_trace_entries(void);
 size_t itsolv_harness_trace_values(void);
 void itsolv_harness_trace_read(itsolv_trace_entry* entries, double* values);

@@ -76,6 +76,7 @@ KERNEL_API = {
     "itsolv_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "itsolv_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "itsolv_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "itsolv_upload_bytes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "itsolv_mem_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "itsolv_comm_unique_id": (C.c_int, [C.c_void_p]),
     "itsolv_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
@@ -121,6 +122,10 @@ HARNESS_API = {
     "itsolv_harness_solve_host_csr": (C.c_int, [C.c_void_p, C.POINTER(SolveSpec), c_int64_p, c_int32_p, c_double_p,
                                                 c_double_p, C.POINTER(SolveResult), c_double_p]),
     "itsolv_harness_last_error": (C.c_char_p, []),
+    "itsolv_harness_problem_create": (C.c_int, [C.c_void_p, C.POINTER(SolveSpec), c_int64_p, c_int32_p, c_double_p,
+                                                c_double_p, c_void_pp]),
+    "itsolv_harness_problem_solve": (C.c_int, [C.c_void_p, C.POINTER(SolveSpec), C.POINTER(SolveResult), c_double_p]),
+    "itsolv_harness_problem_destroy": (None, [C.c_void_p]),
     "itsolv_harness_trace_entries": (C.c_size_t, []),
     "itsolv_harness_trace_values": (C.c_size_t, []),
     "itsolv_harness_trace_read": (None, [C.POINTER(TraceEntry), c_double_p]),

@@ -289,6 +289,11 @@ int itsolv_upload(itsolv_ctx* ctx, double* dst, const double* src, size_t n) {
   ITSOLV_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
+int itsolv_upload_bytes(itsolv_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  ITSOLV_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ITSOLV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
 int itsolv_download(itsolv_ctx* ctx, double* dst, const double* src, size_t n) {
   ITSOLV_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   ITSOLV_CUDA(cudaStreamSynchronize(ctx->stream));

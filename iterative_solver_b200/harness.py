@@ -66,6 +66,33 @@ def solve_host_csr(ctx: Context, spec: N.SolveSpec, row_ptr, col, val, diag, wan
     return res, sol
 
 
+class Problem:
+    """The harness operator resident in HBM: create once, solve repeatedly (bench.py's device-resident leg)."""
+
+    def __init__(self, ctx: Context, spec: N.SolveSpec, csr=None):
+        self.ctx = ctx
+        h = C.c_void_p()
+        if csr is None:
+            _hcheck(N.host().itsolv_harness_problem_create(ctx.handle, C.byref(spec), None, None, None, None, C.byref(h)))
+        else:
+            row_ptr, col, val, diag = csr
+            _hcheck(N.host().itsolv_harness_problem_create(ctx.handle, C.byref(spec), row_ptr.ctypes.data_as(N.c_int64_p),
+                                                           col.ctypes.data_as(N.c_int32_p), _dbl(val), _dbl(diag),
+                                                           C.byref(h)))
+        self.handle = h
+
+    def solve(self, spec: N.SolveSpec, solutions: np.ndarray | None = None) -> N.SolveResult:
+        res = N.SolveResult()
+        _hcheck(N.host().itsolv_harness_problem_solve(self.handle, C.byref(spec), C.byref(res),
+                                                      _dbl(solutions) if solutions is not None else None))
+        return res
+
+    def close(self):
+        if self.handle:
+            N.host().itsolv_harness_problem_destroy(self.handle)
+            self.handle = None
+
+
 def read_trace():
     """Every dot / gemm_inner result the handlers returned during the last traced solve, in call order."""
     lib = N.host()

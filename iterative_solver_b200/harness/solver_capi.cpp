@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -110,9 +111,7 @@ public:
     d_row_ptr = reinterpret_cast<int64_t*>(p_rp);
     d_col = reinterpret_cast<int32_t*>(p_col);
     check(itsolv_upload(ctx, p_rp, reinterpret_cast<const double*>(row_ptr), nloc + 1), "csr upload");
-    std::vector<double> packed((nnz + 1) / 2 + 1, 0.0);
-    std::memcpy(packed.data(), col, nnz * sizeof(int32_t));
-    check(itsolv_upload(ctx, p_col, packed.data(), packed.size()), "csr upload");
+    check(itsolv_upload_bytes(ctx, p_col, col, nnz * sizeof(int32_t)), "csr upload");
     check(itsolv_upload(ctx, d_val, val, nnz), "csr upload");
     check(itsolv_upload(ctx, d_diag, diag, nloc), "csr upload");
   }
@@ -292,29 +291,58 @@ extern "C" {
 
 const char* itsolv_harness_last_error(void) { return g_error.c_str(); }
 
-int itsolv_harness_solve(itsolv_ctx* ctx, const itsolv_solve_spec* spec, itsolv_solve_result* result, double* solutions) {
+struct itsolv_harness_problem {
+  itsolv_ctx* ctx;
+  std::unique_ptr<DeviceProblem> problem;
+};
+
+int itsolv_harness_problem_create(itsolv_ctx* ctx, const itsolv_solve_spec* spec, const int64_t* row_ptr,
+                                  const int32_t* col, const double* val, const double* diag,
+                                  itsolv_harness_problem** out) {
   return guarded([&] {
-    DeviceProblem problem(ctx, *spec);
-    if (spec->explicit_csr && spec->problem == ITSOLV_PROBLEM_BANDED)
-      problem.build_csr();
-    DeviceBackend backend(ctx, problem, size_t(spec->n));
-    itsolv_ctx_reset_counters(ctx);
-    itsolv_b200::harness::run_solve(*spec, backend, *result, solutions);
-    fill_counters(ctx, result);
+    auto p = std::make_unique<itsolv_harness_problem>();
+    p->ctx = ctx;
+    p->problem = std::make_unique<DeviceProblem>(ctx, *spec);
+    if (row_ptr)
+      p->problem->upload_csr(row_ptr, col, val, diag);
+    else if (spec->explicit_csr && spec->problem == ITSOLV_PROBLEM_BANDED)
+      p->problem->build_csr();
+    *out = p.release();
   });
+}
+
+int itsolv_harness_problem_solve(itsolv_harness_problem* p, const itsolv_solve_spec* spec, itsolv_solve_result* result,
+                                 double* solutions) {
+  return guarded([&] {
+    if (spec->n != p->problem->n || spec->half_bandwidth != p->problem->b || spec->problem != p->problem->kind)
+      throw std::invalid_argument("itsolv_harness_problem_solve: spec does not describe this operator");
+    DeviceBackend backend(p->ctx, *p->problem, size_t(spec->n));
+    itsolv_ctx_reset_counters(p->ctx);
+    itsolv_b200::harness::run_solve(*spec, backend, *result, solutions);
+    fill_counters(p->ctx, result);
+  });
+}
+
+void itsolv_harness_problem_destroy(itsolv_harness_problem* p) { delete p; }
+
+int itsolv_harness_solve(itsolv_ctx* ctx, const itsolv_solve_spec* spec, itsolv_solve_result* result, double* solutions) {
+  itsolv_harness_problem* p = nullptr;
+  if (int rc = itsolv_harness_problem_create(ctx, spec, nullptr, nullptr, nullptr, nullptr, &p))
+    return rc;
+  const int rc = itsolv_harness_problem_solve(p, spec, result, solutions);
+  itsolv_harness_problem_destroy(p);
+  return rc;
 }
 
 int itsolv_harness_solve_host_csr(itsolv_ctx* ctx, const itsolv_solve_spec* spec, const int64_t* row_ptr,
                                   const int32_t* col, const double* val, const double* diag,
                                   itsolv_solve_result* result, double* solutions) {
-  return guarded([&] {
-    DeviceProblem problem(ctx, *spec);
-    problem.upload_csr(row_ptr, col, val, diag);
-    DeviceBackend backend(ctx, problem, size_t(spec->n));
-    itsolv_ctx_reset_counters(ctx);
-    itsolv_b200::harness::run_solve(*spec, backend, *result, solutions);
-    fill_counters(ctx, result);
-  });
+  itsolv_harness_problem* p = nullptr;
+  if (int rc = itsolv_harness_problem_create(ctx, spec, row_ptr, col, val, diag, &p))
+    return rc;
+  const int rc = itsolv_harness_problem_solve(p, spec, result, solutions);
+  itsolv_harness_problem_destroy(p);
+  return rc;
 }
 
 size_t itsolv_harness_trace_entries(void) { return trace().entries.size(); }

@@ -92,8 +92,11 @@ public:
   Matrix<value_type> gemm_inner(const CVecRef<AL>& xx, const CVecRef<AR>& yy) override {
     this->m_counter->gemm_inner++;
     auto mat = Matrix<value_type>({xx.size(), yy.size()});
-    if (xx.empty() || yy.empty())
+    if (xx.empty() || yy.empty()) {
+      if (m_observer)
+        m_observer('g', mat.rows(), mat.cols(), nullptr);
       return mat;
+    }
     std::vector<const double*> px(xx.size()), py(yy.size());
     const AL& first = xx[0].get();
     for (size_t i = 0; i < xx.size(); ++i) {
@@ -206,8 +209,11 @@ public:
   Matrix<value_type> gemm_inner(const CVecRef<AL>& xx, const CVecRef<AR>& yy) override {
     this->m_counter->gemm_inner++;
     auto mat = Matrix<value_type>({xx.size(), yy.size()});
-    if (xx.empty() || yy.empty())
+    if (xx.empty() || yy.empty()) {
+      if (m_observer)
+        m_observer('g', mat.rows(), mat.cols(), nullptr);
       return mat;
+    }
     Packed p(yy);
     std::vector<const double*> px(xx.size());
     const AL& first = xx[0].get();
