@@ -58,9 +58,10 @@ typedef struct itsolv_counters {
 void itsolv_ctx_counters(itsolv_ctx* ctx, itsolv_counters* out);
 void itsolv_ctx_reset_counters(itsolv_ctx* ctx);
 void itsolv_ctx_set_profiling(itsolv_ctx* ctx, int enabled);
-/* CUDA-event stopwatch on the context's stream */
-int itsolv_ctx_timer_start(itsolv_ctx* ctx);
-int itsolv_ctx_timer_stop(itsolv_ctx* ctx, double* milliseconds);
+/* CUDA-event stopwatches on the context's stream; id in [0, ITSOLV_TIMERS) (the solve harness uses id 0) */
+#define ITSOLV_TIMERS 4
+int itsolv_ctx_timer_start(itsolv_ctx* ctx, int id);
+int itsolv_ctx_timer_stop(itsolv_ctx* ctx, int id, double* milliseconds);
 
 /* ---- memory: stream-ordered pool (no cudaMalloc/cudaFree on the hot path; the reference churns 2w Q vectors per
  * iteration, itsolv/subspace/QSpace.h:80-84) ---- */

@@ -70,8 +70,8 @@ KERNEL_API = {
     "itsolv_ctx_counters": (None, [C.c_void_p, C.POINTER(Counters)]),
     "itsolv_ctx_reset_counters": (None, [C.c_void_p]),
     "itsolv_ctx_set_profiling": (None, [C.c_void_p, C.c_int]),
-    "itsolv_ctx_timer_start": (C.c_int, [C.c_void_p]),
-    "itsolv_ctx_timer_stop": (C.c_int, [C.c_void_p, c_double_p]),
+    "itsolv_ctx_timer_start": (C.c_int, [C.c_void_p, C.c_int]),
+    "itsolv_ctx_timer_stop": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "itsolv_alloc": (C.c_int, [C.c_void_p, C.c_size_t, c_void_pp]),
     "itsolv_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "itsolv_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),

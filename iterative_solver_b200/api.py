@@ -85,12 +85,13 @@ class Context:
     def set_profiling(self, on: bool):
         self.lib.itsolv_ctx_set_profiling(self.handle, 1 if on else 0)
 
-    def timer_start(self):
-        self._check(self.lib.itsolv_ctx_timer_start(self.handle))
+    def timer_start(self, timer: int = 1):
+        """CUDA-event stopwatch on the context's stream (timer 0 belongs to the solve harness)"""
+        self._check(self.lib.itsolv_ctx_timer_start(self.handle, timer))
 
-    def timer_stop(self) -> float:
+    def timer_stop(self, timer: int = 1) -> float:
         ms = C.c_double()
-        self._check(self.lib.itsolv_ctx_timer_stop(self.handle, C.byref(ms)))
+        self._check(self.lib.itsolv_ctx_timer_stop(self.handle, timer, C.byref(ms)))
         return ms.value
 
     def init_comm(self, rank: int, nranks: int, unique_id: bytes):

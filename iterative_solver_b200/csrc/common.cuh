@@ -81,7 +81,7 @@ struct itsolv_ctx {
   bool profiling = false;
   std::vector<itsolv::PendingEvent> pending;
   std::vector<cudaEvent_t> event_pool;
-  cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
+  cudaEvent_t timer_start[ITSOLV_TIMERS] = {}, timer_stop[ITSOLV_TIMERS] = {};
 };
 
 namespace itsolv {

@@ -153,8 +153,10 @@ static int ctx_init(itsolv_ctx* ctx, int device, cudaStream_t stream, bool own) 
     ITSOLV_CUDA(cudaEventRecord(e, ctx->stream));
   }
   ITSOLV_CUDA(cudaMalloc(&ctx->d_select, 4096 * sizeof(unsigned long long)));
-  ITSOLV_CUDA(cudaEventCreate(&ctx->timer_start));
-  ITSOLV_CUDA(cudaEventCreate(&ctx->timer_stop));
+  for (int t = 0; t < ITSOLV_TIMERS; ++t) {
+    ITSOLV_CUDA(cudaEventCreate(&ctx->timer_start[t]));
+    ITSOLV_CUDA(cudaEventCreate(&ctx->timer_stop[t]));
+  }
   if (ensure_partials(ctx, size_t(4) * ctx->num_sms * 4096))
     return 1;
   ctx->opt_gi_rows = env_int("ITSOLV_GI_ROWS", 0);
@@ -209,8 +211,10 @@ void itsolv_ctx_destroy(itsolv_ctx* ctx) {
     cudaEventDestroy(e);
   for (auto e : ctx->stage_events)
     cudaEventDestroy(e);
-  cudaEventDestroy(ctx->timer_start);
-  cudaEventDestroy(ctx->timer_stop);
+  for (int t = 0; t < ITSOLV_TIMERS; ++t) {
+    cudaEventDestroy(ctx->timer_start[t]);
+    cudaEventDestroy(ctx->timer_stop[t]);
+  }
   cudaFree(ctx->d_partials);
   cudaFree(ctx->d_result);
   cudaFreeHost(ctx->h_result);
@@ -260,15 +264,17 @@ void itsolv_ctx_set_profiling(itsolv_ctx* ctx, int enabled) {
   ctx->profiling = enabled != 0;
 }
 
-int itsolv_ctx_timer_start(itsolv_ctx* ctx) {
-  ITSOLV_CUDA(cudaEventRecord(ctx->timer_start, ctx->stream));
+int itsolv_ctx_timer_start(itsolv_ctx* ctx, int id) {
+  ITSOLV_REQUIRE(id >= 0 && id < ITSOLV_TIMERS, "itsolv_ctx_timer_start: bad timer id");
+  ITSOLV_CUDA(cudaEventRecord(ctx->timer_start[id], ctx->stream));
   return 0;
 }
-int itsolv_ctx_timer_stop(itsolv_ctx* ctx, double* milliseconds) {
-  ITSOLV_CUDA(cudaEventRecord(ctx->timer_stop, ctx->stream));
-  ITSOLV_CUDA(cudaEventSynchronize(ctx->timer_stop));
+int itsolv_ctx_timer_stop(itsolv_ctx* ctx, int id, double* milliseconds) {
+  ITSOLV_REQUIRE(id >= 0 && id < ITSOLV_TIMERS, "itsolv_ctx_timer_stop: bad timer id");
+  ITSOLV_CUDA(cudaEventRecord(ctx->timer_stop[id], ctx->stream));
+  ITSOLV_CUDA(cudaEventSynchronize(ctx->timer_stop[id]));
   float ms = 0;
-  ITSOLV_CUDA(cudaEventElapsedTime(&ms, ctx->timer_start, ctx->timer_stop));
+  ITSOLV_CUDA(cudaEventElapsedTime(&ms, ctx->timer_start[id], ctx->timer_stop[id]));
   *milliseconds = ms;
   return 0;
 }

@@ -237,10 +237,10 @@ struct DeviceBackend {
   size_t n_local() { return prob.nloc; }
   DeviceProblem& problem() { return prob; }
   void synchronize() { check(itsolv_ctx_synchronize(ctx), "synchronize"); }
-  void timer_start() { check(itsolv_ctx_timer_start(ctx), "timer"); }
+  void timer_start() { check(itsolv_ctx_timer_start(ctx, 0), "timer"); }
   double timer_stop_ms() {
     double ms = 0;
-    check(itsolv_ctx_timer_stop(ctx, &ms), "timer");
+    check(itsolv_ctx_timer_stop(ctx, 0, &ms), "timer");
     return ms;
   }
 };

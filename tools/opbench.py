@@ -1,0 +1,119 @@
+#!/usr/bin/env python
+"""Per-shape device timing of the contract's kernels through the C ABI (CUDA events on the context's stream, inputs
+larger than L2 rotated between repetitions). Prints one line per shape: algorithmic GB/s and fraction of the measured
+HBM copy rate. Tuning knobs: --opt NAME=VALUE (see itsolv_ctx_set_option)."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import iterative_solver_b200 as pkg  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--opt", action="append", default=[])
+    ap.add_argument("--only", default="")
+    ap.add_argument("--json", default="")
+    args = ap.parse_args()
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        peak = 6650.0
+    ctx = pkg.Context(0)
+    ctx.init_comm(0, 1, b"\0" * 128)
+    for o in args.opt:
+        k, v = o.split("=")
+        ctx.set_option(k, int(v))
+    n = args.n
+    g = torch.Generator(device="cuda").manual_seed(0)
+    nvec = 160 if n <= 10_000_000 else 40
+    pool = [torch.randn(n, dtype=torch.float64, device="cuda", generator=g) for _ in range(nvec)]
+    torch.cuda.synchronize()
+    cursor = [0]
+
+    def take(k):
+        out = []
+        for _ in range(k):
+            out.append(pool[cursor[0] % nvec])
+            cursor[0] += 1
+        return out
+
+    results = []
+
+    def run(name, bytes_per_call, fn):
+        if args.only and args.only not in name:
+            return
+        fn()  # warm-up (also sets function attributes)
+        fn()
+        fn()
+        ctx.synchronize()
+        ctx.timer_start()
+        for _ in range(args.reps):
+            fn()
+        ms = ctx.timer_stop() / args.reps
+        # the same calls again with an event pair around each call's kernels: kernel time without host gaps
+        ctx.reset_counters()
+        ctx.set_profiling(True)
+        for _ in range(args.reps):
+            fn()
+        ctx.synchronize()
+        kms = ctx.counters().device_seconds * 1e3 / args.reps
+        ctx.set_profiling(False)
+        gbs = bytes_per_call / ms / 1e6
+        kgbs = bytes_per_call / kms / 1e6 if kms else 0.0
+        results.append({"op": name, "us": ms * 1e3, "gbs": gbs, "frac": gbs / peak, "kernel_us": kms * 1e3,
+                        "kernel_gbs": kgbs, "kernel_frac": kgbs / peak})
+        print(f"{name:22s} call {ms*1e3:9.1f} us {gbs:7.0f} GB/s {gbs/peak:5.2f} | kernels {kms*1e3:9.1f} us "
+              f"{kgbs:7.0f} GB/s {kgbs/peak:5.2f} of measured HBM copy", flush=True)
+
+    lib = ctx.lib
+    from iterative_solver_b200.api import _ptr_array, _dbl
+    out = np.zeros(128 * 128)
+
+    def gi(k, m):
+        def f():
+            xs, ys = take(k), take(m)
+            # asynchronous variant: launch only (no host sync inside the timed loop would need a C entry; use full call)
+            ctx._check(lib.itsolv_gemm_inner_f64(ctx.handle, _ptr_array(xs), k, _ptr_array(ys), m, n, _dbl(out)))
+        return f
+
+    def go(k, m):
+        alpha = np.random.default_rng(0).standard_normal((k, m)) * 1e-3
+
+        def f():
+            ctx.gemm_outer(alpha, take(k), take(m))
+        return f
+
+    run("fill", 8 * n, lambda: ctx.fill(1.0, take(1)[0]))
+    run("scal", 16 * n, lambda: ctx.scal(1.0000001, take(1)[0]))
+    run("copy", 16 * n, lambda: ctx.copy(*take(2)))
+    run("axpy", 24 * n, lambda: ctx.axpy(1e-9, *take(2)))
+    run("dot", 16 * n, lambda: ctx.dot(*take(2)))
+    run("dot(x,x)", 8 * n, lambda: (lambda v: ctx.dot(v, v))(take(1)[0]))
+    diag = torch.arange(1, n + 1, dtype=torch.float64, device="cuda")
+    run("precondition[w=4]", 8 * n * 9, lambda: ctx.precondition(take(4), diag, [0.1, 0.2, 0.3, 0.4]))
+    for k, m in [(4, 1), (1, 4), (4, 4), (4, 8), (4, 12), (4, 16), (4, 20), (8, 8), (16, 16), (16, 24), (16, 40), (16, 64),
+                 (8, 100), (16, 128), (64, 64), (128, 128)]:
+        if (k + m) * 2 > nvec:
+            continue
+        run(f"gemm_inner[{k}x{m}]", 8 * n * (k + m), gi(k, m))
+    for k, m in [(1, 4), (4, 4), (8, 4), (12, 4), (20, 4), (24, 16), (40, 16), (100, 16), (16, 40)]:
+        if (k + m) * 2 > nvec:
+            continue
+        run(f"gemm_outer[{k}x{m}]", 8 * n * (k + 2 * m), go(k, m))
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump({"n": n, "options": args.opt, "peak_gbs": peak, "results": results}, f, indent=1)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
