@@ -54,7 +54,10 @@ struct itsolv_ctx {
   double* d_partials = nullptr;
   size_t partials_capacity = 0; // doubles
   double* d_result = nullptr;   // ITSOLV_MAX_PANEL^2 doubles
-  double* h_result = nullptr;   // pinned, ITSOLV_MAX_PANEL^2 doubles
+  double* h_result = nullptr;   // pinned + mapped, ITSOLV_MAX_PANEL^2 doubles
+  unsigned long long* h_flag = nullptr; // pinned + mapped: sequence number of the last result delivered by a kernel
+  unsigned long long flag_seq = 0;
+  unsigned int* d_counter = nullptr;    // CTA arrival counter of the fused final reduction (self-resetting)
   // staging for small host->device payloads (alphas, sparse maps, pointer tables): pinned ring + device ring
   char* h_stage = nullptr;
   char* d_stage = nullptr;

@@ -142,7 +142,11 @@ static int ctx_init(itsolv_ctx* ctx, int device, cudaStream_t stream, bool own) 
   ITSOLV_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
   const size_t panel2 = size_t(ITSOLV_MAX_PANEL) * ITSOLV_MAX_PANEL;
   ITSOLV_CUDA(cudaMalloc(&ctx->d_result, panel2 * sizeof(double)));
-  ITSOLV_CUDA(cudaHostAlloc(&ctx->h_result, panel2 * sizeof(double), cudaHostAllocDefault));
+  ITSOLV_CUDA(cudaHostAlloc(&ctx->h_result, panel2 * sizeof(double), cudaHostAllocMapped));
+  ITSOLV_CUDA(cudaHostAlloc(&ctx->h_flag, 64, cudaHostAllocMapped));
+  *ctx->h_flag = 0;
+  ITSOLV_CUDA(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
+  ITSOLV_CUDA(cudaMemset(ctx->d_counter, 0, sizeof(unsigned int)));
   ctx->stage_slot_bytes = panel2 * sizeof(double) + 8192;
   ctx->stage_slots = 8;
   ITSOLV_CUDA(cudaHostAlloc(&ctx->h_stage, ctx->stage_slot_bytes * ctx->stage_slots, cudaHostAllocDefault));
@@ -218,6 +222,8 @@ void itsolv_ctx_destroy(itsolv_ctx* ctx) {
   cudaFree(ctx->d_partials);
   cudaFree(ctx->d_result);
   cudaFreeHost(ctx->h_result);
+  cudaFreeHost(ctx->h_flag);
+  cudaFree(ctx->d_counter);
   cudaFreeHost(ctx->h_stage);
   cudaFree(ctx->d_stage);
   cudaFree(ctx->d_select);

@@ -22,13 +22,17 @@
 namespace itsolv {
 
 constexpr int kMaxStages = 8;
-constexpr int kMaxConsumers = 256;
+constexpr int kMaxProducerWarps = 4;
 
 struct GiParams {
   const double* vec[2 * ITSOLV_MAX_PANEL]; // distinct vectors of the call
   unsigned char xslot[ITSOLV_MAX_PANEL];   // xx[i] -> index into vec
   unsigned char yslot[ITSOLV_MAX_PANEL];   // yy[j] -> index into vec
   double* partials;                        // [gridDim.x][k*m]
+  double* out;                             // final k*m sums when the last CTA reduces (device or mapped host memory)
+  unsigned int* counter;                   // CTAs that have published their partial sums (reset by the last one)
+  unsigned long long* flag;                // mapped host word that receives `seq` once `out` is complete (or null)
+  unsigned long long seq;
   size_t n;
   long long nfull; // number of full tiles of `rows` rows
   int nvec, k, m;
@@ -36,6 +40,8 @@ struct GiParams {
   int stride; // doubles between consecutive vectors inside a stage (T + 2: shifts each vector by one 16-byte bank group)
   int stages;
   int KB, MB, G; // thread-tile grid (KB x MB tiles) and number of row groups
+  int nprod;     // producer warps (each issues the TMA copies of the vectors v == warp (mod nprod))
+  int fused;     // 1: the last CTA to finish adds the per-CTA partial sums in CTA order and writes `out`
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -62,11 +68,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                : "memory");
 }
 //! 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (16-byte aligned, size % 16 == 0)
-__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src_gmem), "r"(bytes), "r"(bar)
                : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n"
+               ".reg .pred P;\n"
+               "elect.sync _|P, 0xffffffff;\n"
+               "selp.u32 %0, 1, 0, P;\n"
+               "}"
+               : "=r"(pred));
+  return pred != 0;
 }
 
 template <int TI, int TJ>
@@ -101,15 +116,27 @@ __device__ __forceinline__ void cooperative_fill(const GiParams& p, double* st, 
   }
 }
 
-template <int TI, int TJ, bool ASYNC>
-__global__ void __launch_bounds__(kMaxConsumers + 32, (TI * TJ >= 32 ? 1 : 2)) gemm_inner_kernel(const __grid_constant__ GiParams p) {
+// Thread budget: BIG kernels run one CTA per SM (large tiles for panels of many vectors, up to 4 producer warps);
+// the others run two CTAs per SM.
+template <int TI, int TJ, bool BIG>
+struct GiShape {
+  static constexpr bool heavy = TI * TJ >= 32; // 32 or 64 accumulators per thread
+  static constexpr int max_consumers = BIG ? (heavy ? 256 : 512) : 256;
+  static constexpr int max_threads = max_consumers + 32 * (BIG ? kMaxProducerWarps : 2);
+  static constexpr int min_ctas = BIG ? 1 : 2;
+};
+
+template <int TI, int TJ, bool ASYNC, bool BIG>
+__global__ void __launch_bounds__(GiShape<TI, TJ, BIG>::max_threads, GiShape<TI, TJ, BIG>::min_ctas)
+    gemm_inner_kernel(const __grid_constant__ GiParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* tiles = reinterpret_cast<double*>(smem_raw);
   __shared__ uint64_t full_bar[kMaxStages];
   __shared__ uint64_t empty_bar[kMaxStages];
+  __shared__ int s_is_last;
 
   const int tid = threadIdx.x;
-  const int nconsumers = blockDim.x - 32; // last warp is the producer
+  const int nconsumers = blockDim.x - 32 * p.nprod; // the last nprod warps are producers
   const int nconsumer_warps = nconsumers / 32;
   const bool is_producer = tid >= nconsumers;
   const int NT = p.KB * p.MB;
@@ -143,27 +170,36 @@ __global__ void __launch_bounds__(kMaxConsumers + 32, (TI * TJ >= 32 ? 1 : 2)) g
   if (ASYNC) {
     if (tid == 0) {
       for (int s = 0; s < p.stages; ++s) {
-        mbar_init(&full_bar[s], 1);
+        mbar_init(&full_bar[s], p.nprod);
         mbar_init(&empty_bar[s], nconsumer_warps);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (is_producer) {
-      // UBLKCP takes its addresses from uniform registers: one elected lane issues every copy of the tile
-      if ((tid & 31) == 0) {
-        const uint32_t vec_bytes = uint32_t(p.rows) * 8u;
-        for (long long s = 0; s < my_tiles; ++s) {
-          const int stage = int(s % p.stages);
-          const long long use = s / p.stages;
-          if (use > 0)
-            mbar_wait(&empty_bar[stage], uint32_t((use - 1) & 1));
-          mbar_expect_tx(&full_bar[stage], vec_bytes * uint32_t(p.nvec));
-          const size_t row0 = size_t(blockIdx.x + s * gridDim.x) * size_t(p.rows);
-          double* st = tiles + size_t(stage) * stage_doubles;
+      // Warp-uniform control flow and addresses (everything derives from kernel parameters and the loop counters), so
+      // the copies are issued from the uniform datapath; one elected lane executes the arrive and the UBLKCPs.
+      const int pw = (tid - nconsumers) >> 5;
+      const bool leader = elect_one();
+      const uint32_t vec_bytes = uint32_t(p.rows) * 8u;
+      const int my_nvec = (p.nvec - pw + p.nprod - 1) / p.nprod;
+      const uint32_t tiles_u32 = smem_u32(tiles);
+      for (long long s = 0; s < my_tiles; ++s) {
+        const int stage = int(s % p.stages);
+        const long long use = s / p.stages;
+        if (use > 0)
+          mbar_wait(&empty_bar[stage], uint32_t((use - 1) & 1));
+        const uint32_t bar = smem_u32(&full_bar[stage]);
+        if (leader)
+          mbar_expect_tx(&full_bar[stage], vec_bytes * uint32_t(my_nvec));
+        const size_t row0 = size_t(blockIdx.x + s * gridDim.x) * size_t(p.rows);
+        const uint32_t st = tiles_u32 + uint32_t(size_t(stage) * stage_doubles * 8);
 #pragma unroll 4
-          for (int v = 0; v < p.nvec; ++v)
-            bulk_load(st + size_t(v) * p.stride, p.vec[v] + row0, vec_bytes, &full_bar[stage]);
+        for (int v = pw; v < p.nvec; v += p.nprod) {
+          const double* src = p.vec[v] + row0;
+          const uint32_t dst = st + uint32_t(v) * uint32_t(p.stride) * 8u;
+          if (leader)
+            bulk_load(dst, src, vec_bytes, bar);
         }
       }
     } else {
@@ -224,6 +260,38 @@ __global__ void __launch_bounds__(kMaxConsumers + 32, (TI * TJ >= 32 ? 1 : 2)) g
       sum += src[size_t(gg) * NT];
     out[e] = sum;
   }
+  if (!p.fused)
+    return;
+
+  // The last CTA to publish its partial sums adds all of them in CTA order (deterministic: the order does not depend on
+  // which CTA happens to be last) and hands the result to the host.
+  __threadfence();
+  __syncthreads();
+  if (tid == 0)
+    s_is_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_is_last)
+    return;
+  __threadfence();
+  const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  for (int e = warp; e < km; e += nwarps) {
+    double sum = 0.0;
+    for (int c = lane; c < int(gridDim.x); c += 32)
+      sum += __ldcg(p.partials + size_t(c) * km + e);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+      sum += __shfl_down_sync(0xffffffffu, sum, off);
+    if (lane == 0)
+      p.out[e] = sum;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    *p.counter = 0u;
+    if (p.flag) {
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long*>(p.flag) = p.seq;
+    }
+  }
 }
 
 //! out[e] = sum over CTAs (in CTA order within each lane, then a fixed shuffle tree) of partials[c][e]; one warp per element
@@ -246,14 +314,20 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
 using GiKernel = void (*)(const GiParams);
 
 template <int TI, int TJ>
-static GiKernel pick_async(bool async) {
-  return async ? gemm_inner_kernel<TI, TJ, true> : gemm_inner_kernel<TI, TJ, false>;
+static GiKernel pick_variant(bool async, bool big) {
+  constexpr bool heavy = TI * TJ >= 32;
+  if (!async)
+    return gemm_inner_kernel<TI, TJ, false, heavy>;
+  if constexpr (heavy)
+    return gemm_inner_kernel<TI, TJ, true, true>;
+  else
+    return big ? gemm_inner_kernel<TI, TJ, true, true> : gemm_inner_kernel<TI, TJ, true, false>;
 }
 
-static GiKernel pick_kernel(int ti, int tj, bool async) {
+static GiKernel pick_kernel(int ti, int tj, bool async, bool big) {
 #define CASE(I, J)                                                                                                     \
   if (ti == I && tj == J)                                                                                              \
-  return pick_async<I, J>(async)
+  return pick_variant<I, J>(async, big)
   CASE(1, 1);
   CASE(1, 2);
   CASE(2, 1);
@@ -277,10 +351,16 @@ static int pow2_at_most(int v, int cap) {
   return r;
 }
 
-//! Launch the contraction into ctx->d_result (device, k*m doubles); no synchronisation.
-int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const double* const* yy, int m, size_t n) {
+/*!
+ * Launch the contraction. Returns in *host_direct whether the result is delivered straight into ctx->h_result by the
+ * kernel itself (single rank, fused final reduction: the host then waits on ctx->h_flag == ctx->flag_seq), otherwise the
+ * result is left in ctx->d_result. No synchronisation here.
+ */
+int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const double* const* yy, int m, size_t n,
+                      bool* host_direct) {
   ITSOLV_REQUIRE(k >= 1 && m >= 1 && k <= ITSOLV_MAX_PANEL && m <= ITSOLV_MAX_PANEL, "gemm_inner: panel size out of range");
   const int km = k * m;
+  *host_direct = false;
   if (n == 0) {
     ITSOLV_CUDA(cudaMemsetAsync(ctx->d_result, 0, size_t(km) * sizeof(double), ctx->stream));
     return 0;
@@ -313,15 +393,20 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
   p.m = m;
   p.n = n;
 
-  // thread tile
+  // ---- thread tile: 4 x 4 accumulators per thread unless the panel is small or needs more than the CTA's threads
   int ti = pow2_at_most(k, 4), tj = pow2_at_most(m, 4);
   if (ctx->opt_gi_tile > 0) {
     ti = ctx->opt_gi_tile / 16;
     tj = ctx->opt_gi_tile % 16;
   }
-  int max_consumers = ctx->opt_gi_threads > 0 ? ctx->opt_gi_threads : 256;
-  max_consumers = std::min(kMaxConsumers, std::max(32, (max_consumers / 32) * 32));
   auto ntiles = [&](int a, int b) { return ((k + a - 1) / a) * ((m + b - 1) / b); };
+  // ---- CTA shape: panels of many vectors run one large CTA per SM (bigger tiles -> bigger TMA copies, more producers)
+  bool big = async && (p.nvec > 24 || ntiles(ti, tj) > 256);
+  if (ctx->opt_gi_ctas == 1)
+    big = async;
+  else if (ctx->opt_gi_ctas >= 2)
+    big = false;
+  int max_consumers = big ? 512 : 256;
   while (ntiles(ti, tj) > max_consumers) {
     if (tj <= ti && tj < 8)
       tj *= 2;
@@ -332,43 +417,47 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
     else
       break;
   }
+  const bool heavy = ti * tj >= 32;
+  if (heavy) {
+    big = true;
+    max_consumers = 256;
+  }
+  if (ctx->opt_gi_threads > 0)
+    max_consumers = std::min(max_consumers, std::max(32, (ctx->opt_gi_threads / 32) * 32));
   ITSOLV_REQUIRE(ntiles(ti, tj) <= max_consumers, "gemm_inner: no thread tile fits this panel");
   p.KB = (k + ti - 1) / ti;
   p.MB = (m + tj - 1) / tj;
   const int NT = p.KB * p.MB;
   p.G = std::max(1, max_consumers / NT);
   const int nconsumers = ((NT * p.G + 31) / 32) * 32;
+  const int ctas_per_sm = (big || !async) && heavy ? 1 : (big ? 1 : 2);
+  p.nprod = !async ? 1 : (big ? (p.nvec > 64 ? 4 : (p.nvec > 24 ? 2 : 1)) : (p.nvec > 12 ? 2 : 1));
 
-  // shared-memory tile: rows per stage and stages
-  int ctas_per_sm = ctx->opt_gi_ctas > 0 ? ctx->opt_gi_ctas : 2;
+  // ---- shared-memory tile: rows per stage and stages
   const size_t reduce_bytes = size_t(ti) * tj * NT * p.G * sizeof(double);
-  const size_t smem_cap = size_t(ctx->max_smem_optin) - 1024;
-  if (reduce_bytes > smem_cap / 2 - 1024 || ti * tj >= 32)
-    ctas_per_sm = 1; // register budget of the 4x8 / 8x8 tiles allows one CTA per SM
-  const size_t budget = (ctas_per_sm == 1 ? smem_cap : (smem_cap - 1024) / ctas_per_sm) & ~size_t(127);
-  int stages = async ? (ctx->opt_gi_stages > 0 ? ctx->opt_gi_stages : 3) : 1;
-  stages = std::min(stages, kMaxStages);
+  const size_t smem_cap = size_t(ctx->max_smem_optin) - 2048;
+  const size_t budget = (ctas_per_sm == 1 ? smem_cap : (smem_cap - 2048) / 2) & ~size_t(127);
+  ITSOLV_REQUIRE(reduce_bytes <= budget, "gemm_inner: reduction scratch does not fit");
+  int stages = async ? (ctx->opt_gi_stages > 0 ? ctx->opt_gi_stages : (p.nvec > 96 ? 2 : 3)) : 1;
+  stages = std::max(1, std::min(stages, kMaxStages));
   int rows;
   if (ctx->opt_gi_rows > 0) {
     rows = ctx->opt_gi_rows;
   } else {
-    rows = int(budget / (size_t(stages) * p.nvec * sizeof(double)));
-    rows = std::min(rows, 2048);
+    rows = int(std::min<size_t>(budget / (size_t(stages) * p.nvec * sizeof(double)), 2048));
+    // keep enough tiles per CTA for a balanced static schedule
+    const size_t want_tiles = size_t(ctx->num_sms) * ctas_per_sm * 16;
+    while (rows > 64 && n / size_t(rows) < want_tiles)
+      rows /= 2;
   }
   rows = std::max(16, (rows / 16) * 16);
-  while (stages > 1 && size_t(stages) * p.nvec * (rows + 2) * sizeof(double) > budget) {
+  while (size_t(stages) * p.nvec * (rows + 2) * sizeof(double) > budget) {
     if (rows > 16)
       rows -= 16;
-    else
+    else if (stages > 1)
       --stages;
-  }
-  while (size_t(stages) * p.nvec * (rows + 2) * sizeof(double) > smem_cap && rows > 16)
-    rows -= 16;
-  // do not make tiles so large that the grid cannot be filled
-  {
-    const size_t want_tiles = size_t(ctx->num_sms) * ctas_per_sm * 2;
-    while (rows > 64 && n / size_t(rows) < want_tiles)
-      rows = std::max(64, ((rows / 2) / 16) * 16);
+    else
+      break;
   }
   p.rows = rows;
   p.stride = rows + 2;
@@ -382,26 +471,72 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
   if (ensure_partials(ctx, size_t(grid) * km))
     return 1;
   p.partials = ctx->d_partials;
+  p.fused = (size_t(grid) * km <= size_t(128) * 1024) ? 1 : 0;
+  const bool single_rank = itsolv_comm_size(ctx) == 1;
+  p.counter = ctx->d_counter;
+  p.flag = nullptr;
+  p.seq = 0;
+  p.out = ctx->d_result;
+  if (p.fused && single_rank) {
+    p.out = ctx->h_result; // mapped pinned memory: the kernel delivers the result, no copy, no stream synchronisation
+    p.flag = ctx->h_flag;
+    p.seq = ++ctx->flag_seq;
+    *host_direct = true;
+  }
 
-  GiKernel kernel = pick_kernel(ti, tj, async);
+  GiKernel kernel = pick_kernel(ti, tj, async, big);
   ITSOLV_REQUIRE(kernel != nullptr, "gemm_inner: thread tile not instantiated");
   ITSOLV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
-  kernel<<<grid, nconsumers + 32, smem_bytes, ctx->stream>>>(p);
+  kernel<<<grid, nconsumers + 32 * p.nprod, smem_bytes, ctx->stream>>>(p);
   ITSOLV_CUDA(cudaGetLastError());
-  const int rblocks = (km * 32 + 255) / 256;
-  reduce_partials_kernel<<<rblocks, 256, 0, ctx->stream>>>(ctx->d_partials, grid, km, ctx->d_result);
-  ITSOLV_CUDA(cudaGetLastError());
-  ctx->counters.launches += 2;
+  ctx->counters.launches += 1;
+  if (!p.fused) {
+    const int rblocks = (km * 32 + 255) / 256;
+    reduce_partials_kernel<<<rblocks, 256, 0, ctx->stream>>>(ctx->d_partials, grid, km, ctx->d_result);
+    ITSOLV_CUDA(cudaGetLastError());
+    ctx->counters.launches += 1;
+  }
   return 0;
 }
 
+//! wait for a result that the kernel writes into mapped host memory: spin on the sequence word, watch the stream for errors
+static int wait_host_flag(itsolv_ctx* ctx) {
+  volatile unsigned long long* flag = ctx->h_flag;
+  const unsigned long long want = ctx->flag_seq;
+  for (unsigned long long spins = 0;; ++spins) {
+    if (*flag == want)
+      return 0;
+    if ((spins & 0x3FFF) == 0x3FFF) {
+      const cudaError_t q = cudaStreamQuery(ctx->stream);
+      if (q == cudaSuccess) {
+        if (*flag == want)
+          return 0;
+        set_error("gemm_inner: kernel finished without delivering its result");
+        return 1;
+      }
+      if (q != cudaErrorNotReady) {
+        set_error(std::string("gemm_inner: ") + cudaGetErrorString(q));
+        return 1;
+      }
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
+
 //! all-reduce over ranks, copy to the pinned buffer, synchronise, hand to the caller
-int finish_result(itsolv_ctx* ctx, int count, double* out) {
-  if (comm_allreduce_device(ctx, ctx->d_result, size_t(count), false))
-    return 1;
-  ITSOLV_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, size_t(count) * sizeof(double), cudaMemcpyDeviceToHost,
-                              ctx->stream));
-  ITSOLV_CUDA(cudaStreamSynchronize(ctx->stream));
+int finish_result(itsolv_ctx* ctx, int count, double* out, bool host_direct) {
+  if (host_direct) {
+    if (wait_host_flag(ctx))
+      return 1;
+  } else {
+    if (comm_allreduce_device(ctx, ctx->d_result, size_t(count), false))
+      return 1;
+    ITSOLV_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, size_t(count) * sizeof(double), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+    ITSOLV_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   for (int e = 0; e < count; ++e)
     out[e] = ctx->h_result[e];
   return 0;
@@ -440,15 +575,16 @@ int itsolv_gemm_inner_f64(itsolv_ctx* ctx, const double* const* xx, int k, const
     for (int j0 = 0; j0 < m; j0 += ITSOLV_MAX_PANEL) {
       const int mb = std::min(ITSOLV_MAX_PANEL, m - j0);
       CallScope scope(ctx, OP_GEMM_INNER, distinct_bytes(xx + i0, kb, yy + j0, mb, n));
-      if (gemm_inner_device(ctx, xx + i0, kb, yy + j0, mb, n))
+      bool direct = false;
+      if (gemm_inner_device(ctx, xx + i0, kb, yy + j0, mb, n, &direct))
         return 1;
       scope.stop();
       if (kb == k && mb == m) {
-        if (finish_result(ctx, kb * mb, out))
+        if (finish_result(ctx, kb * mb, out, direct))
           return 1;
       } else {
         std::vector<double> block(size_t(kb) * mb);
-        if (finish_result(ctx, kb * mb, block.data()))
+        if (finish_result(ctx, kb * mb, block.data(), direct))
           return 1;
         for (int i = 0; i < kb; ++i)
           for (int j = 0; j < mb; ++j)
@@ -463,10 +599,11 @@ int itsolv_dot_f64(itsolv_ctx* ctx, const double* x, const double* y, size_t n, 
   ctx->counters.n_dot++;
   // a dot is the 1 x 1 case of the panel kernel and is accounted with it
   CallScope scope(ctx, OP_GEMM_INNER, (x == y ? 8.0 : 16.0) * double(n));
-  if (gemm_inner_device(ctx, &x, 1, &y, 1, n))
+  bool direct = false;
+  if (gemm_inner_device(ctx, &x, 1, &y, 1, n, &direct))
     return 1;
   scope.stop();
-  return finish_result(ctx, 1, result);
+  return finish_result(ctx, 1, result, direct);
 }
 
 } // extern "C"

@@ -12,7 +12,7 @@
 
 namespace itsolv {
 
-int finish_result(itsolv_ctx* ctx, int count, double* out); // gemm_inner.cu
+int finish_result(itsolv_ctx* ctx, int count, double* out, bool host_direct); // gemm_inner.cu
 
 struct SparseInnerParams {
   const double* x[ITSOLV_MAX_PANEL];
@@ -183,7 +183,7 @@ int itsolv_sparse_gemm_inner_f64(itsolv_ctx* ctx, const double* const* xx, int k
       if (stage_done(ctx, pk.slot))
         return 1;
       std::vector<double> block(static_cast<size_t>(total), 0.0);
-      if (finish_result(ctx, total, block.data()))
+      if (finish_result(ctx, total, block.data(), false))
         return 1;
       for (int i = 0; i < kb; ++i)
         for (int j = 0; j < mb; ++j)
