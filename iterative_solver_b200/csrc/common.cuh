@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include <itsolv_b200.h>
@@ -80,6 +81,8 @@ struct itsolv_ctx {
   int opt_go_ctas = 0;    // gemm_outer CTAs per SM
   int opt_blas1_ctas = 0; // CTAs per SM for streaming kernels
 
+  std::vector<std::pair<const void*, size_t>> smem_optin; // kernel -> largest dynamic shared memory size opted in
+
   itsolv_counters counters{};
   bool profiling = false;
   std::vector<itsolv::PendingEvent> pending;
@@ -108,6 +111,8 @@ int stage_commit(itsolv_ctx* ctx, int slot, size_t bytes);
 int stage_done(itsolv_ctx* ctx, int slot);
 
 int ensure_partials(itsolv_ctx* ctx, size_t doubles);
+//! opt a kernel in to `bytes` of dynamic shared memory (cached per kernel: the attribute call is made only when it grows)
+int ensure_dynamic_smem(itsolv_ctx* ctx, const void* kernel, size_t bytes);
 
 //! sum in place over ranks (device buffer); no-op without a communicator
 int comm_allreduce_device(itsolv_ctx* ctx, double* d, size_t count, bool op_max);

@@ -123,6 +123,22 @@ int ensure_partials(itsolv_ctx* ctx, size_t doubles) {
   return 0;
 }
 
+int ensure_dynamic_smem(itsolv_ctx* ctx, const void* kernel, size_t bytes) {
+  if (bytes <= 48 * 1024)
+    return 0;
+  for (auto& e : ctx->smem_optin)
+    if (e.first == kernel) {
+      if (e.second >= bytes)
+        return 0;
+      ITSOLV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+      e.second = bytes;
+      return 0;
+    }
+  ITSOLV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+  ctx->smem_optin.emplace_back(kernel, bytes);
+  return 0;
+}
+
 static int ctx_init(itsolv_ctx* ctx, int device, cudaStream_t stream, bool own) {
   ITSOLV_CUDA(cudaSetDevice(device));
   ctx->device = device;

@@ -406,21 +406,25 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
     big = async;
   else if (ctx->opt_gi_ctas >= 2)
     big = false;
+  auto grow = [&](int cap) {
+    while (ntiles(ti, tj) > cap) {
+      if (tj <= ti && tj < 8)
+        tj *= 2;
+      else if (ti < 8)
+        ti *= 2;
+      else if (tj < 8)
+        tj *= 2;
+      else
+        break;
+    }
+  };
   int max_consumers = big ? 512 : 256;
-  while (ntiles(ti, tj) > max_consumers) {
-    if (tj <= ti && tj < 8)
-      tj *= 2;
-    else if (ti < 8)
-      ti *= 2;
-    else if (tj < 8)
-      tj *= 2;
-    else
-      break;
-  }
+  grow(max_consumers);
   const bool heavy = ti * tj >= 32;
-  if (heavy) {
+  if (heavy) { // 32 or 64 accumulators per thread: 256 consumers, one CTA per SM
     big = true;
     max_consumers = 256;
+    grow(max_consumers);
   }
   if (ctx->opt_gi_threads > 0)
     max_consumers = std::min(max_consumers, std::max(32, (ctx->opt_gi_threads / 32) * 32));
@@ -486,7 +490,8 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
 
   GiKernel kernel = pick_kernel(ti, tj, async, big);
   ITSOLV_REQUIRE(kernel != nullptr, "gemm_inner: thread tile not instantiated");
-  ITSOLV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
+  if (ensure_dynamic_smem(ctx, reinterpret_cast<const void*>(kernel), smem_bytes))
+    return 1;
   kernel<<<grid, nconsumers + 32 * p.nprod, smem_bytes, ctx->stream>>>(p);
   ITSOLV_CUDA(cudaGetLastError());
   ctx->counters.launches += 1;

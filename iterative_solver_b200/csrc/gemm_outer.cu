@@ -230,7 +230,8 @@ int itsolv_gemm_outer_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, co
       GoKernel kernel = go_pick(mj, vec);
       ITSOLV_REQUIRE(kernel != nullptr, "gemm_outer: column tile not instantiated");
       const size_t smem = size_t(kb) * p.ld * sizeof(double);
-      ITSOLV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<size_t>(smem, 1024))));
+      if (ensure_dynamic_smem(ctx, reinterpret_cast<const void*>(kernel), smem))
+        return 1;
       int per_sm = ctx->opt_go_ctas > 0 ? ctx->opt_go_ctas : (mj <= 2 ? 6 : mj == 4 ? 4 : mj == 8 ? 3 : 2);
       if (smem * per_sm > size_t(ctx->max_smem_optin))
         per_sm = std::max<int>(1, int(size_t(ctx->max_smem_optin) / smem));
