@@ -1,0 +1,102 @@
+"""Worker of tests/test_multi_gpu.py: one process per GPU (torchrun). Vectors are row-sharded with the reference's
+Distribution rule, partial Gram matrices are all-reduced over NCCL, select candidates are all-gathered. Every rank
+checks the sharded results against the single-process CPU oracle on the same global inputs."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import iterative_solver_b200 as pkg  # noqa: E402
+import itsolv_oracle_lib  # noqa: E402
+from iterative_solver_b200 import _native as N  # noqa: E402
+from iterative_solver_b200 import distributed as D  # noqa: E402
+from iterative_solver_b200 import harness as H  # noqa: E402
+
+
+def main():
+    rank, world, local = D.env_rank_world()
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = pkg.Context(local)
+    D.attach_communicator(ctx)
+    assert ctx.rank == rank and ctx.nranks == world
+    o = itsolv_oracle_lib.load()
+    cpu = o.c
+    rng = np.random.default_rng(42)  # same inputs on every rank
+    n = 100003
+    X, Y = rng.standard_normal((4, n)), rng.standard_normal((7, n))
+    alpha = rng.standard_normal((4, 7))
+    b = pkg.distribution(n, world)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+
+    # Gram block: per-rank partial sums + NCCL all-reduce
+    G = H.handler_gemm_inner(ctx, X, Y)
+    want = cpu.gemm_inner(X, Y)
+    scale = np.linalg.norm(X, axis=1)[:, None] * np.linalg.norm(Y, axis=1)[None, :]
+    assert (np.abs(G - want) <= 1e-12 * scale).all()
+    d = H.handler_dot(ctx, X[0].copy(), Y[0].copy())
+    assert abs(d - cpu.dot(X[0].copy(), Y[0].copy())) <= 1e-12 * scale[0, 0]
+    # every rank holds the identical result (the host subspace problem is solved redundantly per rank)
+    allG = [torch.zeros(4, 7, dtype=torch.float64, device="cuda") for _ in range(world)]
+    dist.all_gather(allG, torch.from_numpy(G).cuda())
+    assert all(torch.equal(allG[0], g) for g in allG)
+
+    # expansion: no communication, each rank updates its rows (only those rows come back)
+    out = H.handler_gemm_outer(ctx, alpha, X, Y)
+    ref = cpu.gemm_outer(alpha, X, Y, fma=True)
+    assert np.array_equal(out[:, lo:hi], ref[:, lo:hi])
+
+    # select: local candidates all-gathered and merged by the reference's (key, index) order
+    xr = np.round(X[1], 1)
+    for kw in ({}, {"max": True}, {"max": True, "ignore_sign": True}):
+        gi, gv = H.handler_select(ctx, xr, 11, **kw)
+        wi, wv = cpu.select(xr, 11, **kw)
+        assert np.array_equal(gi, wi) and np.array_equal(gv, wv)
+
+    # sparse (P-space) ops with entries scattered over the shards
+    maps = [{5: 1.0, n - 2: 2.0}, {lo: -1.0}, {hi - 1: 0.5, 17: 3.0}]
+    assert np.array_equal(H.handler_sparse_gemm_inner(ctx, X, maps), cpu.sparse_gemm_inner(X, maps))
+    a2 = rng.standard_normal((3, 4))
+    assert np.array_equal(H.handler_sparse_gemm_outer(ctx, a2, maps, X)[:, lo:hi], cpu.sparse_gemm_outer(a2, maps, X)[:, lo:hi])
+
+    # operator with halo exchange between neighbouring shards
+    y = H.harness_banded_apply(ctx, X[2].copy(), 4, 1e-3)
+    assert np.array_equal(y[lo:hi], cpu.banded_apply(X[2].copy(), 4, 1e-3)[lo:hi])
+    y = H.harness_banded_apply(ctx, X[2].copy(), 4, 1e-3, explicit_csr=True)
+    assert np.array_equal(y[lo:hi], cpu.banded_apply(X[2].copy(), 4, 1e-3)[lo:hi])
+
+    # complete solves on sharded vectors against the reference's golden results
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "solve_golden.json")))
+    report = {}
+    for name in ("banded_davidson_n100000_r4", "banded_davidson_n30000_r6_qcap8", "banded_davidson_n30000_r4_p20",
+                 "banded_lineq_n50000_r1", "banded_diis_n50000", "banded_davidson_n30000_r16"):
+        want = golden[name]
+        spec = H.make_spec(trace=1, **want["spec"])
+        res, sol = H.solve(ctx, spec, want_solutions=True)
+        assert res.iterations == want["iterations"] and res.converged == want["converged"], name
+        assert [[op, r, c] for op, r, c, _ in H.read_trace()] == want["trace_shapes"], name
+        if want["eigenvalues"]:
+            ev = np.array([res.eigenvalues[i] for i in range(res.nroots)])
+            assert np.abs(ev / np.array(want["eigenvalues"]) - 1).max() <= 1e-10, name
+        bb = pkg.distribution(want["spec"]["n"], world)
+        if rank == 0:
+            for s, head in zip(sol, want["solution_head"]):
+                assert np.abs(s[:8] - np.array(head)).max() <= 1e-7 * max(1.0, np.abs(np.array(head)).max())
+        chk = ctx.allreduce_host(np.array([np.sum(s) for s in sol]))
+        for c, w in zip(chk, want["solution_checksums"]):
+            assert abs(c - w) <= 1e-6 * max(1.0, abs(w)), name
+        report[name] = res.iterations
+    dist.barrier()
+    print(f"rank {rank}/{world} ok {report}", flush=True)
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
