@@ -60,7 +60,7 @@ def main():
         assert np.array_equal(gi, wi) and np.array_equal(gv, wv)
 
     # sparse (P-space) ops with entries scattered over the shards
-    maps = [{5: 1.0, n - 2: 2.0}, {lo: -1.0}, {hi - 1: 0.5, 17: 3.0}]
+    maps = [{5: 1.0, n - 2: 2.0}, {int(b[1]): -1.0}, {int(b[1]) - 1: 0.5, 17: 3.0}]  # same maps on every rank
     assert np.array_equal(H.handler_sparse_gemm_inner(ctx, X, maps), cpu.sparse_gemm_inner(X, maps))
     a2 = rng.standard_normal((3, 4))
     assert np.array_equal(H.handler_sparse_gemm_outer(ctx, a2, maps, X)[:, lo:hi], cpu.sparse_gemm_outer(a2, maps, X)[:, lo:hi])
