@@ -40,6 +40,8 @@ struct GiParams {
   int stride; // doubles between consecutive vectors inside a stage (T + 2: shifts each vector by one 16-byte bank group)
   int stages;
   int KB, MB, G; // thread-tile grid (KB x MB tiles) and number of row groups
+  int chunk_rows; // rows per TMA copy: a vector's tile travels as ceil(rows / chunk_rows) copies (many small copies in
+                  // flight stream faster than a few large ones)
   int nprod;     // producer warps (each issues the TMA copies of the vectors v == warp (mod nprod))
   int fused;     // 1: the last CTA to finish adds the per-CTA partial sums in CTA order and writes `out`
 };
@@ -194,12 +196,15 @@ __global__ void __launch_bounds__(GiShape<TI, TJ, BIG>::max_threads, GiShape<TI,
           mbar_expect_tx(&full_bar[stage], vec_bytes * uint32_t(my_nvec));
         const size_t row0 = size_t(blockIdx.x + s * gridDim.x) * size_t(p.rows);
         const uint32_t st = tiles_u32 + uint32_t(size_t(stage) * stage_doubles * 8);
-#pragma unroll 4
         for (int v = pw; v < p.nvec; v += p.nprod) {
           const double* src = p.vec[v] + row0;
           const uint32_t dst = st + uint32_t(v) * uint32_t(p.stride) * 8u;
-          if (leader)
-            bulk_load(dst, src, vec_bytes, bar);
+#pragma unroll 4
+          for (int r0 = 0; r0 < p.rows; r0 += p.chunk_rows) {
+            const int nr = p.rows - r0 < p.chunk_rows ? p.rows - r0 : p.chunk_rows;
+            if (leader)
+              bulk_load(dst + uint32_t(r0) * 8u, src + r0, uint32_t(nr) * 8u, bar);
+          }
         }
       }
     } else {
@@ -250,15 +255,23 @@ __global__ void __launch_bounds__(GiShape<TI, TJ, BIG>::max_threads, GiShape<TI,
   __syncthreads();
   const int km = p.k * p.m;
   double* out = p.partials + size_t(blockIdx.x) * km;
-  for (int e = tid; e < km; e += blockDim.x) {
-    const int i = e / p.m, j = e % p.m;
-    const int a = i / p.KB, tb_i = i % p.KB;
-    const int b = j / p.MB, tb_j = j % p.MB;
-    const double* src = red + size_t(a * TJ + b) * nact + (tb_i * p.MB + tb_j);
-    double sum = 0.0;
-    for (int gg = 0; gg < p.G; ++gg)
-      sum += src[size_t(gg) * NT];
-    out[e] = sum;
+  {
+    // one warp per output element: lanes take the row groups in turn, then a fixed shuffle tree
+    const int warp_id = tid >> 5, lane_id = tid & 31, nwarps_cta = blockDim.x >> 5;
+    for (int e = warp_id; e < km; e += nwarps_cta) {
+      const int i = e / p.m, j = e % p.m;
+      const int a = i / p.KB, tb_i = i % p.KB;
+      const int b = j / p.MB, tb_j = j % p.MB;
+      const double* src = red + size_t(a * TJ + b) * nact + (tb_i * p.MB + tb_j);
+      double sum = 0.0;
+      for (int gg = lane_id; gg < p.G; gg += 32)
+        sum += src[size_t(gg) * NT];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+        sum += __shfl_down_sync(0xffffffffu, sum, off);
+      if (lane_id == 0)
+        out[e] = sum;
+    }
   }
   if (!p.fused)
     return;
@@ -464,6 +477,10 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
       break;
   }
   p.rows = rows;
+  {
+    const int chunk_bytes = ctx->opt_gi_chunk > 0 ? ctx->opt_gi_chunk : 2048;
+    p.chunk_rows = std::max(2, (chunk_bytes / 8 / 2) * 2);
+  }
   p.stride = rows + 2;
   p.stages = stages;
   p.nfull = (long long)(n / size_t(rows));

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--opt", action="append", default=[])
     ap.add_argument("--only", default="")
     ap.add_argument("--json", default="")
+    ap.add_argument("--sweep", action="append", default=[], help="NAME=v1,v2,...: rerun the selected ops for each value")
     args = ap.parse_args()
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -76,6 +77,28 @@ def main():
 
     lib = ctx.lib
     from iterative_solver_b200.api import _ptr_array, _dbl
+    sweeps = [("", [None])]
+    if args.sweep:
+        sweeps = []
+        for sw in args.sweep:
+            k, vs = sw.split("=")
+            sweeps.append((k, [int(v) for v in vs.split(",")]))
+    for sweep_name, sweep_values in sweeps:
+      for sweep_value in sweep_values:
+        if sweep_name:
+            ctx.set_option(sweep_name, sweep_value)
+            print(f"--- {sweep_name}={sweep_value}", flush=True)
+            results.append({"option": sweep_name, "value": sweep_value})
+        run_all(ctx, lib, args, n, nvec, take, run, _ptr_array, _dbl)
+        if sweep_name:
+            ctx.set_option(sweep_name, 0)
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump({"n": n, "options": args.opt, "peak_gbs": peak, "results": results}, f, indent=1)
+    ctx.close()
+
+
+def run_all(ctx, lib, args, n, nvec, take, run, _ptr_array, _dbl):
     out = np.zeros(128 * 128)
 
     def gi(k, m):
@@ -109,10 +132,6 @@ def main():
         if (k + m) * 2 > nvec:
             continue
         run(f"gemm_outer[{k}x{m}]", 8 * n * (k + 2 * m), go(k, m))
-    if args.json:
-        with open(args.json, "w") as f:
-            json.dump({"n": n, "options": args.opt, "peak_gbs": peak, "results": results}, f, indent=1)
-    ctx.close()
 
 
 if __name__ == "__main__":
