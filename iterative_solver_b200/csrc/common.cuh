@@ -78,6 +78,8 @@ struct itsolv_ctx {
   int opt_gi_tile = 0;    // thread tile TI*16+TJ (0 = auto)
   int opt_gi_ctas = 0;    // CTAs per SM (0 = auto)
   int opt_gi_chunk = 0;   // bytes per TMA copy (0 = auto)
+  int opt_gi_nprod = 0;   // producer warps (0 = auto)
+  int opt_gi_loader = 0;  // 0 auto, 1 TMA bulk copies, 2 cp.async pieces
   int opt_go_cols = 0;    // gemm_outer columns per thread (0 = auto)
   int opt_go_ctas = 0;    // gemm_outer CTAs per SM
   int opt_blas1_ctas = 0; // CTAs per SM for streaming kernels

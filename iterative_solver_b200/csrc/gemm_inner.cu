@@ -86,6 +86,25 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// How a tile reaches shared memory
+enum Loader {
+  LOAD_TMA = 0,    // one elected lane per producer warp issues 1-D TMA bulk copies (UBLKCP), one per vector
+  LOAD_CPASYNC16 = 1, // all producer lanes issue 16-byte cp.async (LDGSTS) pieces; completion counted on the mbarrier
+  LOAD_CPASYNC8 = 2   // the same with 8-byte pieces: vectors that are only 8-byte aligned
+};
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(uint32_t dst_smem, const void* src_gmem, uint32_t src_bytes) {
+  if constexpr (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src_gmem), "r"(src_bytes));
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src_gmem), "r"(src_bytes));
+}
+//! the calling thread arrives on the mbarrier once all of its earlier cp.async copies have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <int TI, int TJ>
 __device__ __forceinline__ void consume_tile(const double* __restrict__ st, int npairs, int g, int G, const int (&xoff)[TI],
                                              const int (&yoff)[TJ], double (&acc)[TI][TJ]) {
@@ -128,7 +147,7 @@ struct GiShape {
   static constexpr int min_ctas = BIG ? 1 : 2;
 };
 
-template <int TI, int TJ, bool ASYNC, bool BIG>
+template <int TI, int TJ, int LOADER, bool BIG>
 __global__ void __launch_bounds__(GiShape<TI, TJ, BIG>::max_threads, GiShape<TI, TJ, BIG>::min_ctas)
     gemm_inner_kernel(const __grid_constant__ GiParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -169,15 +188,18 @@ __global__ void __launch_bounds__(GiShape<TI, TJ, BIG>::max_threads, GiShape<TI,
   const size_t stage_doubles = size_t(p.nvec) * p.stride;
   const int npairs = p.rows / 2;
 
-  if (ASYNC) {
-    if (tid == 0) {
-      for (int s = 0; s < p.stages; ++s) {
-        mbar_init(&full_bar[s], p.nprod);
-        mbar_init(&empty_bar[s], nconsumer_warps);
-      }
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (tid == 0) {
+    // full: TMA -> one arrive.expect_tx per producer warp (+ bytes); cp.async -> one deferred arrive per producer thread
+    const uint32_t full_count = LOADER == LOAD_TMA ? uint32_t(p.nprod) : uint32_t(32 * p.nprod);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], full_count);
+      mbar_init(&empty_bar[s], nconsumer_warps);
     }
-    __syncthreads();
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if constexpr (LOADER == LOAD_TMA) {
     if (is_producer) {
       // Warp-uniform control flow and addresses (everything derives from kernel parameters and the loop counters), so
       // the copies are issued from the uniform datapath; one elected lane executes the arrive and the UBLKCPs.
@@ -207,39 +229,78 @@ __global__ void __launch_bounds__(GiShape<TI, TJ, BIG>::max_threads, GiShape<TI,
           }
         }
       }
-    } else {
-      const int lane = tid & 31;
-      for (long long s = 0; s < my_tiles; ++s) {
+    }
+  } else {
+    if (is_producer) {
+      // Every producer lane moves 16-byte (or 8-byte) pieces: piece q of a tile is rows [q % PV * W, +W) of vector q / PV,
+      // so a warp instruction covers 512 contiguous bytes of one vector. Rows past the end of the vectors are
+      // zero-filled by the copy itself (src-size operand), which also takes care of the last, partial tile.
+      constexpr int PB = LOADER == LOAD_CPASYNC16 ? 16 : 8; // bytes per piece
+      constexpr int W = PB / 8;                             // rows per piece
+      const int pt = tid - nconsumers;                      // producer thread index
+      const int NP = 32 * p.nprod;
+      const int PV = p.rows / W;                            // pieces per vector per tile
+      const int total = p.nvec * PV;
+      const uint32_t tiles_u32 = smem_u32(tiles);
+      const long long ntiles_all = p.nfull + ((size_t(p.nfull) * size_t(p.rows) < p.n) ? 1 : 0);
+      const long long mine = ntiles_all > (long long)blockIdx.x ? (ntiles_all - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      for (long long s = 0; s < mine; ++s) {
         const int stage = int(s % p.stages);
-        mbar_wait(&full_bar[stage], uint32_t((s / p.stages) & 1));
-        if (active)
-          consume_tile<TI, TJ>(tiles + size_t(stage) * stage_doubles, npairs, g, p.G, xoff, yoff, acc);
-        __syncwarp();
-        if (lane == 0)
-          mbar_arrive(&empty_bar[stage]);
+        const long long use = s / p.stages;
+        if (use > 0)
+          mbar_wait(&empty_bar[stage], uint32_t((use - 1) & 1));
+        const size_t row0 = size_t(blockIdx.x + s * gridDim.x) * size_t(p.rows);
+        const size_t left = p.n - row0; // rows of the vectors from row0 to their end (>= 1)
+        const uint32_t st = tiles_u32 + uint32_t(size_t(stage) * stage_doubles * 8);
+        int v = pt / PV, r = pt % PV;
+#pragma unroll 4
+        for (int q = pt; q < total; q += NP) {
+          const size_t row = size_t(r) * W;
+          const long long valid = (long long)left - (long long)row; // rows available from this piece on
+          const uint32_t nbytes = valid >= W ? uint32_t(PB) : (valid > 0 ? uint32_t(valid) * 8u : 0u);
+          const double* src = p.vec[v] + row0 + (valid > 0 ? row : 0);
+          cp_async_zfill<PB>(st + (uint32_t(v) * uint32_t(p.stride) + uint32_t(row)) * 8u, src, nbytes);
+          r += NP;
+          while (r >= PV) {
+            r -= PV;
+            ++v;
+          }
+        }
+        cp_async_arrive(&full_bar[stage]);
       }
     }
-    __syncthreads();
-  } else {
-    // pointers not 16-byte aligned: plain loads by all threads, one stage
-    for (long long s = 0; s < my_tiles; ++s) {
-      const size_t row0 = size_t(blockIdx.x + s * gridDim.x) * size_t(p.rows);
-      cooperative_fill(p, tiles, row0, p.rows);
+  }
+
+  if (!is_producer) {
+    const int lane = tid & 31;
+    // the cp.async loaders also bring the last, partial tile (zero-filled); the TMA loader leaves it to the code below
+    long long ntiles_c = my_tiles;
+    if constexpr (LOADER != LOAD_TMA) {
+      const long long ntiles_all = p.nfull + ((size_t(p.nfull) * size_t(p.rows) < p.n) ? 1 : 0);
+      ntiles_c = ntiles_all > (long long)blockIdx.x ? (ntiles_all - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    }
+    for (long long s = 0; s < ntiles_c; ++s) {
+      const int stage = int(s % p.stages);
+      mbar_wait(&full_bar[stage], uint32_t((s / p.stages) & 1));
+      if (active)
+        consume_tile<TI, TJ>(tiles + size_t(stage) * stage_doubles, npairs, g, p.G, xoff, yoff, acc);
+      __syncwarp();
+      if (lane == 0)
+        mbar_arrive(&empty_bar[stage]);
+    }
+  }
+  __syncthreads();
+
+  if constexpr (LOADER == LOAD_TMA) {
+    // the last, partial tile belongs to the CTA that would own tile number nfull
+    const size_t tail0 = size_t(p.nfull) * size_t(p.rows);
+    if (tail0 < p.n && int(p.nfull % gridDim.x) == int(blockIdx.x)) {
+      cooperative_fill(p, tiles, tail0, int(p.n - tail0));
       __syncthreads();
       if (active)
         consume_tile<TI, TJ>(tiles, npairs, g, p.G, xoff, yoff, acc);
       __syncthreads();
     }
-  }
-
-  // the last, partial tile belongs to the CTA that would own tile number nfull
-  const size_t tail0 = size_t(p.nfull) * size_t(p.rows);
-  if (tail0 < p.n && int(p.nfull % gridDim.x) == int(blockIdx.x)) {
-    cooperative_fill(p, tiles, tail0, int(p.n - tail0));
-    __syncthreads();
-    if (active)
-      consume_tile<TI, TJ>(tiles, npairs, g, p.G, xoff, yoff, acc);
-    __syncthreads();
   }
 
   // reduce the G row groups in group order; red[(a*TJ+b)][g][tile]
@@ -327,20 +388,23 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
 using GiKernel = void (*)(const GiParams);
 
 template <int TI, int TJ>
-static GiKernel pick_variant(bool async, bool big) {
+static GiKernel pick_variant(int loader, bool big) {
   constexpr bool heavy = TI * TJ >= 32;
-  if (!async)
-    return gemm_inner_kernel<TI, TJ, false, heavy>;
-  if constexpr (heavy)
-    return gemm_inner_kernel<TI, TJ, true, true>;
-  else
-    return big ? gemm_inner_kernel<TI, TJ, true, true> : gemm_inner_kernel<TI, TJ, true, false>;
+  if (loader == LOAD_CPASYNC8)
+    return gemm_inner_kernel<TI, TJ, LOAD_CPASYNC8, heavy>;
+  if constexpr (heavy) {
+    return loader == LOAD_TMA ? gemm_inner_kernel<TI, TJ, LOAD_TMA, true> : gemm_inner_kernel<TI, TJ, LOAD_CPASYNC16, true>;
+  } else {
+    if (loader == LOAD_TMA)
+      return big ? gemm_inner_kernel<TI, TJ, LOAD_TMA, true> : gemm_inner_kernel<TI, TJ, LOAD_TMA, false>;
+    return big ? gemm_inner_kernel<TI, TJ, LOAD_CPASYNC16, true> : gemm_inner_kernel<TI, TJ, LOAD_CPASYNC16, false>;
+  }
 }
 
-static GiKernel pick_kernel(int ti, int tj, bool async, bool big) {
+static GiKernel pick_kernel(int ti, int tj, int loader, bool big) {
 #define CASE(I, J)                                                                                                     \
   if (ti == I && tj == J)                                                                                              \
-  return pick_variant<I, J>(async, big)
+  return pick_variant<I, J>(loader, big)
   CASE(1, 1);
   CASE(1, 2);
   CASE(2, 1);
@@ -414,9 +478,14 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
   }
   auto ntiles = [&](int a, int b) { return ((k + a - 1) / a) * ((m + b - 1) / b); };
   // ---- CTA shape: panels of many vectors run one large CTA per SM (bigger tiles -> bigger TMA copies, more producers)
-  bool big = async && (p.nvec > 24 || ntiles(ti, tj) > 256);
+  // ---- loader: TMA bulk copies pay ~200 issue cycles per copy and suit few, large copies; cp.async pieces suit the
+  // rest and are the only choice for vectors that are not 16-byte aligned
+  int loader = !async ? LOAD_CPASYNC8 : LOAD_CPASYNC16;
+  if (async && ctx->opt_gi_loader == 1)
+    loader = LOAD_TMA;
+  bool big = (p.nvec > 24 || ntiles(ti, tj) > 256);
   if (ctx->opt_gi_ctas == 1)
-    big = async;
+    big = true;
   else if (ctx->opt_gi_ctas >= 2)
     big = false;
   auto grow = [&](int cap) {
@@ -447,15 +516,21 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
   const int NT = p.KB * p.MB;
   p.G = std::max(1, max_consumers / NT);
   const int nconsumers = ((NT * p.G + 31) / 32) * 32;
-  const int ctas_per_sm = (big || !async) && heavy ? 1 : (big ? 1 : 2);
-  p.nprod = !async ? 1 : (big ? (p.nvec > 64 ? 4 : (p.nvec > 24 ? 2 : 1)) : (p.nvec > 12 ? 2 : 1));
+  const int ctas_per_sm = big ? 1 : 2;
+  if (loader == LOAD_TMA)
+    p.nprod = big ? 4 : 2;
+  else
+    p.nprod = big ? 4 : 2;
+  if (ctx->opt_gi_nprod > 0)
+    p.nprod = std::min(ctx->opt_gi_nprod, big ? kMaxProducerWarps : 2);
+  p.nprod = std::min(p.nprod, std::max(1, loader == LOAD_TMA ? p.nvec : kMaxProducerWarps));
 
   // ---- shared-memory tile: rows per stage and stages
   const size_t reduce_bytes = size_t(ti) * tj * NT * p.G * sizeof(double);
   const size_t smem_cap = size_t(ctx->max_smem_optin) - 2048;
   const size_t budget = (ctas_per_sm == 1 ? smem_cap : (smem_cap - 2048) / 2) & ~size_t(127);
   ITSOLV_REQUIRE(reduce_bytes <= budget, "gemm_inner: reduction scratch does not fit");
-  int stages = async ? (ctx->opt_gi_stages > 0 ? ctx->opt_gi_stages : (p.nvec > 96 ? 2 : 3)) : 1;
+  int stages = ctx->opt_gi_stages > 0 ? ctx->opt_gi_stages : (p.nvec > 96 ? 2 : 3);
   stages = std::max(1, std::min(stages, kMaxStages));
   int rows;
   if (ctx->opt_gi_rows > 0) {
@@ -478,7 +553,7 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
   }
   p.rows = rows;
   {
-    const int chunk_bytes = ctx->opt_gi_chunk > 0 ? ctx->opt_gi_chunk : 2048;
+    const int chunk_bytes = ctx->opt_gi_chunk > 0 ? ctx->opt_gi_chunk : (1 << 20);
     p.chunk_rows = std::max(2, (chunk_bytes / 8 / 2) * 2);
   }
   p.stride = rows + 2;
@@ -505,7 +580,7 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
     *host_direct = true;
   }
 
-  GiKernel kernel = pick_kernel(ti, tj, async, big);
+  GiKernel kernel = pick_kernel(ti, tj, loader, big);
   ITSOLV_REQUIRE(kernel != nullptr, "gemm_inner: thread tile not instantiated");
   if (ensure_dynamic_smem(ctx, reinterpret_cast<const void*>(kernel), smem_bytes))
     return 1;
