@@ -22,7 +22,7 @@
 namespace itsolv {
 
 constexpr int kMaxStages = 8;
-constexpr int kMaxProducerWarps = 4;
+constexpr int kMaxProducerWarps = 8;
 
 struct GiParams {
   const double* vec[2 * ITSOLV_MAX_PANEL]; // distinct vectors of the call
@@ -142,8 +142,9 @@ __device__ __forceinline__ void cooperative_fill(const GiParams& p, double* st, 
 template <int TI, int TJ, bool BIG>
 struct GiShape {
   static constexpr bool heavy = TI * TJ >= 32; // 32 or 64 accumulators per thread
-  static constexpr int max_consumers = BIG ? (heavy ? 256 : 512) : 256;
-  static constexpr int max_threads = max_consumers + 32 * (BIG ? kMaxProducerWarps : 2);
+  static constexpr int max_consumers = 256;
+  static constexpr int max_producers = BIG ? (heavy ? 4 : kMaxProducerWarps) : 2;
+  static constexpr int max_threads = max_consumers + 32 * max_producers;
   static constexpr int min_ctas = BIG ? 1 : 2;
 };
 
@@ -480,14 +481,18 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
   // ---- CTA shape: panels of many vectors run one large CTA per SM (bigger tiles -> bigger TMA copies, more producers)
   // ---- loader: TMA bulk copies pay ~200 issue cycles per copy and suit few, large copies; cp.async pieces suit the
   // rest and are the only choice for vectors that are not 16-byte aligned
-  int loader = !async ? LOAD_CPASYNC8 : LOAD_CPASYNC16;
-  if (async && ctx->opt_gi_loader == 1)
-    loader = LOAD_TMA;
-  bool big = (p.nvec > 24 || ntiles(ti, tj) > 256);
+  int loader = !async ? LOAD_CPASYNC8 : LOAD_TMA;
+  if (async && ctx->opt_gi_loader == 2)
+    loader = LOAD_CPASYNC16;
+  // ---- CTA shape: panels of more than a few vectors run ONE CTA per SM with up to 8 producer warps (TMA copies
+  // cost ~200 issue cycles each per issuing warp, so the issue rate, not the byte rate, has to be spread)
+  bool big = p.nvec > 10;
   if (ctx->opt_gi_ctas == 1)
     big = true;
   else if (ctx->opt_gi_ctas >= 2)
     big = false;
+  if (loader == LOAD_CPASYNC8)
+    big = false; // instantiated for the two-CTA shape only (heavy tiles excepted, below)
   auto grow = [&](int cap) {
     while (ntiles(ti, tj) > cap) {
       if (tj <= ti && tj < 8)
@@ -500,7 +505,7 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
         break;
     }
   };
-  int max_consumers = big ? 512 : 256;
+  int max_consumers = 256;
   grow(max_consumers);
   const bool heavy = ti * tj >= 32;
   if (heavy) { // 32 or 64 accumulators per thread: 256 consumers, one CTA per SM
@@ -517,13 +522,12 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
   p.G = std::max(1, max_consumers / NT);
   const int nconsumers = ((NT * p.G + 31) / 32) * 32;
   const int ctas_per_sm = big ? 1 : 2;
-  if (loader == LOAD_TMA)
-    p.nprod = big ? 4 : 2;
-  else
-    p.nprod = big ? 4 : 2;
+  const int max_prod = big ? (heavy ? 4 : kMaxProducerWarps) : 2;
+  p.nprod = max_prod;
   if (ctx->opt_gi_nprod > 0)
-    p.nprod = std::min(ctx->opt_gi_nprod, big ? kMaxProducerWarps : 2);
-  p.nprod = std::min(p.nprod, std::max(1, loader == LOAD_TMA ? p.nvec : kMaxProducerWarps));
+    p.nprod = std::min(ctx->opt_gi_nprod, max_prod);
+  if (loader == LOAD_TMA)
+    p.nprod = std::max(1, std::min(p.nprod, p.nvec)); // one vector per producer warp at least
 
   // ---- shared-memory tile: rows per stage and stages
   const size_t reduce_bytes = size_t(ti) * tj * NT * p.G * sizeof(double);
