@@ -18,6 +18,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "gi_finalize.cuh"
 
 namespace itsolv {
 
@@ -28,11 +29,7 @@ struct GiParams {
   const double* vec[2 * ITSOLV_MAX_PANEL]; // distinct vectors of the call
   unsigned char xslot[ITSOLV_MAX_PANEL];   // xx[i] -> index into vec
   unsigned char yslot[ITSOLV_MAX_PANEL];   // yy[j] -> index into vec
-  double* partials;                        // [gridDim.x][k*m]
-  double* out;                             // final k*m sums when the last CTA reduces (device or mapped host memory)
-  unsigned int* counter;                   // CTAs that have published their partial sums (reset by the last one)
-  unsigned long long* flag;                // mapped host word that receives `seq` once `out` is complete (or null)
-  unsigned long long seq;
+  GiFinalize fin;                          // per-CTA partial sums and how they become the final result
   size_t n;
   long long nfull; // number of full tiles of `rows` rows
   int nvec, k, m;
@@ -43,7 +40,6 @@ struct GiParams {
   int chunk_rows; // rows per TMA copy: a vector's tile travels as ceil(rows / chunk_rows) copies (many small copies in
                   // flight stream faster than a few large ones)
   int nprod;     // producer warps (each issues the TMA copies of the vectors v == warp (mod nprod))
-  int fused;     // 1: the last CTA to finish adds the per-CTA partial sums in CTA order and writes `out`
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -316,7 +312,7 @@ __global__ void __launch_bounds__(GiShape<TI, TJ, BIG>::max_threads, GiShape<TI,
   }
   __syncthreads();
   const int km = p.k * p.m;
-  double* out = p.partials + size_t(blockIdx.x) * km;
+  double* out = p.fin.partials + size_t(blockIdx.x) * km;
   {
     // one warp per output element: lanes take the row groups in turn, then a fixed shuffle tree
     const int warp_id = tid >> 5, lane_id = tid & 31, nwarps_cta = blockDim.x >> 5;
@@ -335,38 +331,7 @@ __global__ void __launch_bounds__(GiShape<TI, TJ, BIG>::max_threads, GiShape<TI,
         out[e] = sum;
     }
   }
-  if (!p.fused)
-    return;
-
-  // The last CTA to publish its partial sums adds all of them in CTA order (deterministic: the order does not depend on
-  // which CTA happens to be last) and hands the result to the host.
-  __threadfence();
-  __syncthreads();
-  if (tid == 0)
-    s_is_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1) ? 1 : 0;
-  __syncthreads();
-  if (!s_is_last)
-    return;
-  __threadfence();
-  const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-  for (int e = warp; e < km; e += nwarps) {
-    double sum = 0.0;
-    for (int c = lane; c < int(gridDim.x); c += 32)
-      sum += __ldcg(p.partials + size_t(c) * km + e);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
-      sum += __shfl_down_sync(0xffffffffu, sum, off);
-    if (lane == 0)
-      p.out[e] = sum;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    *p.counter = 0u;
-    if (p.flag) {
-      __threadfence_system();
-      *reinterpret_cast<volatile unsigned long long*>(p.flag) = p.seq;
-    }
-  }
+  gi_finalize(p.fin, km, &s_is_last);
 }
 
 //! out[e] = sum over CTAs (in CTA order within each lane, then a fixed shuffle tree) of partials[c][e]; one warp per element
@@ -385,6 +350,27 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
   if (lane == 0)
     out[warp] = sum;
 }
+
+//! decide where the per-CTA partial sums go and how they are finished (fused last-CTA reduction for small outputs)
+void fill_finalize(itsolv_ctx* ctx, int grid, int km, GiFinalize* f, bool* host_direct) {
+  f->partials = ctx->d_partials;
+  f->fused = (size_t(grid) * km <= size_t(128) * 1024) ? 1 : 0;
+  f->counter = ctx->d_counter;
+  f->flag = nullptr;
+  f->seq = 0;
+  f->out = ctx->d_result;
+  *host_direct = false;
+  if (f->fused && itsolv_comm_size(ctx) == 1) {
+    f->out = ctx->h_result; // mapped pinned memory: the kernel delivers the result, no copy, no stream synchronisation
+    f->flag = ctx->h_flag;
+    f->seq = ++ctx->flag_seq;
+    *host_direct = true;
+  }
+}
+
+int launch_reduce_partials(itsolv_ctx* ctx, int grid, int km);
+int gemm_inner_direct_device(itsolv_ctx* ctx, const double* const* xx, int k, const double* const* yy, int m, size_t n,
+                             bool* host_direct, bool* handled);
 
 using GiKernel = void (*)(const GiParams);
 
@@ -442,6 +428,13 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
   if (n == 0) {
     ITSOLV_CUDA(cudaMemsetAsync(ctx->d_result, 0, size_t(km) * sizeof(double), ctx->stream));
     return 0;
+  }
+  {
+    bool handled = false;
+    if (gemm_inner_direct_device(ctx, xx, k, yy, m, n, host_direct, &handled))
+      return 1;
+    if (handled)
+      return 0;
   }
   GiParams p;
   p.nvec = 0;
@@ -570,19 +563,7 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
   const int grid = int(std::min<long long>(total_tiles, (long long)ctx->num_sms * ctas_per_sm));
   if (ensure_partials(ctx, size_t(grid) * km))
     return 1;
-  p.partials = ctx->d_partials;
-  p.fused = (size_t(grid) * km <= size_t(128) * 1024) ? 1 : 0;
-  const bool single_rank = itsolv_comm_size(ctx) == 1;
-  p.counter = ctx->d_counter;
-  p.flag = nullptr;
-  p.seq = 0;
-  p.out = ctx->d_result;
-  if (p.fused && single_rank) {
-    p.out = ctx->h_result; // mapped pinned memory: the kernel delivers the result, no copy, no stream synchronisation
-    p.flag = ctx->h_flag;
-    p.seq = ++ctx->flag_seq;
-    *host_direct = true;
-  }
+  fill_finalize(ctx, grid, km, &p.fin, host_direct);
 
   GiKernel kernel = pick_kernel(ti, tj, loader, big);
   ITSOLV_REQUIRE(kernel != nullptr, "gemm_inner: thread tile not instantiated");
@@ -591,12 +572,16 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
   kernel<<<grid, nconsumers + 32 * p.nprod, smem_bytes, ctx->stream>>>(p);
   ITSOLV_CUDA(cudaGetLastError());
   ctx->counters.launches += 1;
-  if (!p.fused) {
-    const int rblocks = (km * 32 + 255) / 256;
-    reduce_partials_kernel<<<rblocks, 256, 0, ctx->stream>>>(ctx->d_partials, grid, km, ctx->d_result);
-    ITSOLV_CUDA(cudaGetLastError());
-    ctx->counters.launches += 1;
-  }
+  if (!p.fin.fused)
+    return launch_reduce_partials(ctx, grid, km);
+  return 0;
+}
+
+int launch_reduce_partials(itsolv_ctx* ctx, int grid, int km) {
+  const int rblocks = (km * 32 + 255) / 256;
+  reduce_partials_kernel<<<rblocks, 256, 0, ctx->stream>>>(ctx->d_partials, grid, km, ctx->d_result);
+  ITSOLV_CUDA(cudaGetLastError());
+  ctx->counters.launches += 1;
   return 0;
 }
 
