@@ -47,6 +47,18 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel family, from the newest committed
+    ncu capture of this same command (profiles/ncu_dram_bench_rNN.json, written by tools/summarize_profiles.py)"""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_dram_bench_r*.json")))
+    if not files:
+        return None, None
+    with open(files[-1]) as f:
+        d = json.load(f)
+    return d["gemm_inner_family"]["dram_bytes_per_launch"], os.path.relpath(files[-1], ROOT)
+
+
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons sampled during the timed region"""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -199,6 +211,7 @@ def main():
             agg["sgo"] += res.seconds_gemm_outer
             agg["bb1"] += res.bytes_blas1
             agg["sb1"] += res.seconds_blas1
+            agg["ngi"] = agg.get("ngi", 0) + res.n_dot + res.n_gemm_inner
         ms = ctx.timer_stop()
         lib.itsolv_comm_barrier(ctx.handle)
         torch.cuda.synchronize()
@@ -206,6 +219,7 @@ def main():
     converged, eig = res.converged, [res.eigenvalues[i] for i in range(args.roots)]
     ms_max = float(ctx.allreduce_host(np.array([ms]), op_max=True)[0])
     sums = ctx.allreduce_host(np.array([agg["bytes"], agg["bgi"], agg["bgo"], agg["bb1"], float(launches)]))
+    gi_launches = float(agg.get("ngi", 0)) * world
     maxs = ctx.allreduce_host(np.array([agg["secs"], agg["sgi"], agg["sgo"], agg["sb1"]]), op_max=True)
     value = world * iterations / (ms_max * 1e-3)  # shard-iterations per second: every rank iterates over its 1e7-row shard
     problem.close()
@@ -267,6 +281,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         gi_gbs = agg_gbs(sums[1] / world, maxs[1])
+        traffic, traffic_src = ncu_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, args.min_warmup),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -278,7 +293,8 @@ def main():
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(sums[4]),
             "roofline": {"bound": "hbm", "kernel": "gemm_inner_kernel (gemm_inner and its 1x1 case dot)",
                          "achieved": gi_gbs, "peak": peak, "unit": "GB/s", "frac": gi_gbs / peak if peak else None,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": sums[1] / max(gi_launches, 1.0),
                          "launch_share_of_handler_time": maxs[1] / maxs[0] if maxs[0] else None},
             "cpu_baseline": cpu,
             "subspace_update": {"gbs_per_gpu": agg_gbs(sums[0] / world, maxs[0]),

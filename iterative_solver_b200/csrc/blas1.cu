@@ -139,6 +139,7 @@ using namespace itsolv;
 #define LAUNCH_STREAM(kernel, vec, ...)                                                                                \
   do {                                                                                                                 \
     const int grid__ = stream_grid(ctx, n);                                                                            \
+    mark_launch(ctx);                                                                                                  \
     if (vec)                                                                                                           \
       kernel<true><<<grid__, kThreads, 0, ctx->stream>>>(__VA_ARGS__);                                                 \
     else                                                                                                               \

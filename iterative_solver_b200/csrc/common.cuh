@@ -36,6 +36,8 @@ struct Comm; // NCCL communicator wrapper (comm.cu)
 
 enum OpClass { OP_BLAS1 = 0, OP_GEMM_INNER = 1, OP_GEMM_OUTER = 2, OP_OTHER = 3 };
 
+struct CallScope;
+
 struct PendingEvent {
   cudaEvent_t start, stop;
   int cls;
@@ -88,6 +90,7 @@ struct itsolv_ctx {
 
   std::vector<std::pair<const void*, size_t>> smem_optin; // kernel -> largest dynamic shared memory size opted in
 
+  itsolv::CallScope* active_scope = nullptr;
   itsolv_counters counters{};
   bool profiling = false;
   std::vector<itsolv::PendingEvent> pending;
@@ -102,12 +105,15 @@ struct CallScope {
   itsolv_ctx* ctx;
   int cls;
   cudaEvent_t start = nullptr;
+  bool armed = false; // profiling on: the opening event is recorded by mark_launch() right before the first kernel launch
   CallScope(itsolv_ctx* c, int cls, double bytes);
   //! record the closing event now (after the last kernel launch, before any host synchronisation)
   void stop();
   ~CallScope();
 };
 void drain_pending(itsolv_ctx* ctx);
+//! call immediately before a kernel launch: opens the event pair of the active CallScope (host preparation excluded)
+void mark_launch(itsolv_ctx* ctx);
 
 //! Reserve a staging slot (pinned host + matching device region) of at least `bytes`; caller fills host, then commit copies.
 int stage_acquire(itsolv_ctx* ctx, size_t bytes, char** host, char** dev, int* slot);

@@ -30,22 +30,33 @@ CallScope::CallScope(itsolv_ctx* c, int cls_, double bytes) : ctx(c), cls(cls_) 
   default:
     break;
   }
-  if (ctx->profiling) {
-    if (ctx->event_pool.empty()) {
-      cudaEvent_t e;
-      if (cudaEventCreate(&e) != cudaSuccess)
-        return;
-      ctx->event_pool.push_back(e);
-    }
-    start = ctx->event_pool.back();
-    ctx->event_pool.pop_back();
-    cudaEventRecord(start, ctx->stream);
+  if (ctx->profiling && !ctx->active_scope) {
+    armed = true;
+    ctx->active_scope = this;
   }
+}
+
+void mark_launch(itsolv_ctx* ctx) {
+  CallScope* s = ctx->active_scope;
+  if (!s || !s->armed || s->start)
+    return;
+  if (ctx->event_pool.empty()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess)
+      return;
+    ctx->event_pool.push_back(e);
+  }
+  s->start = ctx->event_pool.back();
+  ctx->event_pool.pop_back();
+  cudaEventRecord(s->start, ctx->stream);
 }
 
 CallScope::~CallScope() { stop(); }
 
 void CallScope::stop() {
+  if (armed && ctx->active_scope == this)
+    ctx->active_scope = nullptr;
+  armed = false;
   if (!start)
     return;
   cudaEvent_t stop;

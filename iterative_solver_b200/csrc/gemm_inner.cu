@@ -569,6 +569,7 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
   ITSOLV_REQUIRE(kernel != nullptr, "gemm_inner: thread tile not instantiated");
   if (ensure_dynamic_smem(ctx, reinterpret_cast<const void*>(kernel), smem_bytes))
     return 1;
+  mark_launch(ctx);
   kernel<<<grid, nconsumers + 32 * p.nprod, smem_bytes, ctx->stream>>>(p);
   ITSOLV_CUDA(cudaGetLastError());
   ctx->counters.launches += 1;
@@ -652,9 +653,9 @@ extern "C" {
 
 int itsolv_gemm_inner_f64(itsolv_ctx* ctx, const double* const* xx, int k, const double* const* yy, int m, size_t n,
                           double* out) {
-  ctx->counters.n_gemm_inner++;
   if (k <= 0 || m <= 0)
     return 0;
+  ctx->counters.n_gemm_inner++;
   // panels wider than ITSOLV_MAX_PANEL are processed block by block
   for (int i0 = 0; i0 < k; i0 += ITSOLV_MAX_PANEL) {
     const int kb = std::min(ITSOLV_MAX_PANEL, k - i0);

@@ -177,6 +177,7 @@ int gemm_inner_direct_device(itsolv_ctx* ctx, const double* const* xx, int k, co
   if (ensure_partials(ctx, size_t(grid) * km))
     return 1;
   fill_finalize(ctx, grid, km, &p.fin, host_direct);
+  mark_launch(ctx);
   kernel<<<grid, kDirectThreads, 0, ctx->stream>>>(p);
   ITSOLV_CUDA(cudaGetLastError());
   ctx->counters.launches += 1;

@@ -239,6 +239,7 @@ int itsolv_gemm_outer_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, co
       size_t grid = std::min<size_t>((units + kGoThreads - 1) / kGoThreads, size_t(ctx->num_sms) * per_sm);
       if (grid == 0)
         grid = 1;
+      mark_launch(ctx);
       kernel<<<int(grid), kGoThreads, smem, ctx->stream>>>(p);
       ITSOLV_CUDA(cudaGetLastError());
       ctx->counters.launches += 1;

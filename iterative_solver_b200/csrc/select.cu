@@ -176,6 +176,7 @@ int itsolv_select_f64(itsolv_ctx* ctx, const double* x, const double* y, size_t 
     int idx_bytes = 1;
     while (idx_bytes < 8 && ((global_offset + n - 1) >> (8 * idx_bytes)) != 0)
       ++idx_bytes;
+    mark_launch(ctx);
     for (int dgt = 0; dgt < 16; ++dgt) {
       if (dgt >= 8 && dgt - 8 < 8 - idx_bytes)
         continue;
