@@ -84,6 +84,7 @@ struct itsolv_ctx {
   int opt_gi_loader = 0;  // 0 auto, 1 TMA bulk copies, 2 cp.async pieces
   int opt_gi_direct = 0;  // 0 auto (register-streaming kernel for k*m <= 4), 2 never
   int opt_gi_direct_ctas = 0; // CTAs per SM of the register-streaming kernel
+  int opt_gi_mma = 0;     // FP64 tensor-core path: 0 auto (k*m >= 320), >0 minimum k*m, <0 never
   int opt_go_cols = 0;    // gemm_outer columns per thread (0 = auto)
   int opt_go_ctas = 0;    // gemm_outer CTAs per SM
   int opt_blas1_ctas = 0; // CTAs per SM for streaming kernels

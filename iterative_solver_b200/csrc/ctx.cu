@@ -200,6 +200,7 @@ static int ctx_init(itsolv_ctx* ctx, int device, cudaStream_t stream, bool own) 
   ctx->opt_gi_loader = env_int("ITSOLV_GI_LOADER", 0);
   ctx->opt_gi_direct = env_int("ITSOLV_GI_DIRECT", 0);
   ctx->opt_gi_direct_ctas = env_int("ITSOLV_GI_DIRECT_CTAS", 0);
+  ctx->opt_gi_mma = env_int("ITSOLV_GI_MMA", 0);
   ctx->opt_go_cols = env_int("ITSOLV_GO_COLS", 0);
   ctx->opt_go_ctas = env_int("ITSOLV_GO_CTAS", 0);
   ctx->opt_blas1_ctas = env_int("ITSOLV_BLAS1_CTAS", 0);
@@ -280,7 +281,8 @@ int itsolv_ctx_set_option(itsolv_ctx* ctx, const char* name, int value) {
                {"GI_THREADS", &ctx->opt_gi_threads}, {"GI_TILE", &ctx->opt_gi_tile},
                {"GI_CTAS", &ctx->opt_gi_ctas},       {"GI_CHUNK", &ctx->opt_gi_chunk},
                {"GI_NPROD", &ctx->opt_gi_nprod},     {"GI_LOADER", &ctx->opt_gi_loader},
-               {"GI_DIRECT", &ctx->opt_gi_direct},   {"GI_DIRECT_CTAS", &ctx->opt_gi_direct_ctas},       {"GO_COLS", &ctx->opt_go_cols},
+               {"GI_DIRECT", &ctx->opt_gi_direct},   {"GI_DIRECT_CTAS", &ctx->opt_gi_direct_ctas},
+               {"GI_MMA", &ctx->opt_gi_mma},       {"GO_COLS", &ctx->opt_go_cols},
                {"GO_CTAS", &ctx->opt_go_ctas},       {"BLAS1_CTAS", &ctx->opt_blas1_ctas}};
   for (auto& t : table)
     if (std::strcmp(t.n, name) == 0) {
