@@ -417,7 +417,7 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
   const size_t smem_cap = size_t(ctx->max_smem_optin) - 2048;
   const size_t budget = (ctas_per_sm == 1 ? smem_cap : (smem_cap - 2048) / 2) & ~size_t(127);
   ITSOLV_REQUIRE(reduce_bytes <= budget, "gemm_inner: reduction scratch does not fit");
-  int stages = ctx->opt_gi_stages > 0 ? ctx->opt_gi_stages : (p.nvec > 96 ? 2 : 3);
+  int stages = ctx->opt_gi_stages > 0 ? ctx->opt_gi_stages : (p.nvec > 64 ? 2 : 3);
   stages = std::max(1, std::min(stages, kMaxStages));
   int rows;
   if (ctx->opt_gi_rows > 0) {

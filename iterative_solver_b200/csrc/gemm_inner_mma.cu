@@ -185,7 +185,7 @@ static const MmaShape* mma_shapes(int* count) {
 int gemm_inner_mma_device(itsolv_ctx* ctx, const double* const* xx, int k, const double* const* yy, int m, size_t n,
                           bool* host_direct, bool* handled) {
   *handled = false;
-  const int min_outputs = ctx->opt_gi_mma > 0 ? ctx->opt_gi_mma : 320; // 16 x 24 and wider
+  const int min_outputs = ctx->opt_gi_mma > 0 ? ctx->opt_gi_mma : 256; // 16 x 16 and wider
   if (ctx->opt_gi_mma < 0 || k * m < min_outputs || n < 4096)
     return 0;
   GiParams p;
@@ -248,7 +248,8 @@ int gemm_inner_mma_device(itsolv_ctx* ctx, const double* const* xx, int k, const
   const size_t smem_cap = size_t(ctx->max_smem_optin) - 2048;
   if (reduce_bytes > smem_cap)
     return 0;
-  int stages = ctx->opt_gi_stages > 0 ? ctx->opt_gi_stages : (p.nvec > 96 ? 2 : 3);
+  // copies shrink with the number of vectors (one per vector per tile); beyond 64 vectors two deeper stages beat three
+  int stages = ctx->opt_gi_stages > 0 ? ctx->opt_gi_stages : (p.nvec > 64 ? 2 : 3);
   stages = std::max(1, std::min(stages, kMaxStages));
   int rows = ctx->opt_gi_rows > 0 ? ctx->opt_gi_rows
                                   : int(std::min<size_t>(smem_cap / (size_t(stages) * p.nvec * sizeof(double)), 1024));

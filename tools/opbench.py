@@ -124,7 +124,7 @@ def run_all(ctx, lib, args, n, nvec, take, run, _ptr_array, _dbl):
     diag = torch.arange(1, n + 1, dtype=torch.float64, device="cuda")
     run("precondition[w=4]", 8 * n * 9, lambda: ctx.precondition(take(4), diag, [0.1, 0.2, 0.3, 0.4]))
     for k, m in [(4, 1), (1, 4), (4, 4), (4, 8), (4, 12), (4, 16), (4, 20), (8, 8), (16, 16), (16, 24), (16, 40), (16, 64),
-                 (8, 100), (16, 128), (64, 64), (128, 128)]:
+                 (8, 100), (16, 128), (32, 32), (64, 64), (128, 128)]:
         if (k + m) > nvec:
             continue
         run(f"gemm_inner[{k}x{m}]", 8 * n * (k + m), gi(k, m))
