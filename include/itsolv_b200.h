@@ -76,6 +76,12 @@ int itsolv_mem_info(itsolv_ctx* ctx, size_t* free_bytes, size_t* total_bytes);
  * (array/DistrArray.h:100,109). The unique id is created on rank 0 and broadcast by the host (torch.distributed, MPI, ...) ---- */
 int itsolv_comm_unique_id(void* id /* ITSOLV_UNIQUE_ID_BYTES */);
 int itsolv_comm_init(itsolv_ctx* ctx, int rank, int nranks, const void* id);
+/* Peer-memory all-reduce fused into the Gram kernels (one process per GPU on one NVSwitch box): every rank exports the
+ * IPC handle of its exchange buffer, the host gathers the handles of all ranks (rank order, ITSOLV_IPC_HANDLE_BYTES
+ * each) and every rank imports them. Without this step dot/gemm_inner fall back to ncclAllReduce + copy + sync. */
+#define ITSOLV_IPC_HANDLE_BYTES 64
+int itsolv_comm_p2p_export(itsolv_ctx* ctx, void* handle);
+int itsolv_comm_p2p_import(itsolv_ctx* ctx, const void* handles /* nranks * ITSOLV_IPC_HANDLE_BYTES */);
 int itsolv_comm_rank(itsolv_ctx* ctx);
 int itsolv_comm_size(itsolv_ctx* ctx);
 int itsolv_comm_barrier(itsolv_ctx* ctx);

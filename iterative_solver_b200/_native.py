@@ -15,6 +15,7 @@ c_void_pp = C.POINTER(C.c_void_p)
 
 MAX_PANEL = 128
 UNIQUE_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 MAX_ROOTS = 64
 
 
@@ -80,6 +81,8 @@ KERNEL_API = {
     "itsolv_mem_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "itsolv_comm_unique_id": (C.c_int, [C.c_void_p]),
     "itsolv_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "itsolv_comm_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "itsolv_comm_p2p_import": (C.c_int, [C.c_void_p, C.c_void_p]),
     "itsolv_comm_rank": (C.c_int, [C.c_void_p]),
     "itsolv_comm_size": (C.c_int, [C.c_void_p]),
     "itsolv_comm_barrier": (C.c_int, [C.c_void_p]),

@@ -103,6 +103,15 @@ class Context:
         self._check(self.lib.itsolv_comm_unique_id(buf))
         return buf.raw
 
+    def p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(N.IPC_HANDLE_BYTES)
+        self._check(self.lib.itsolv_comm_p2p_export(self.handle, buf))
+        return buf.raw
+
+    def p2p_import(self, handles: bytes):
+        buf = C.create_string_buffer(handles, len(handles))
+        self._check(self.lib.itsolv_comm_p2p_import(self.handle, buf))
+
     @property
     def rank(self) -> int:
         return self.lib.itsolv_comm_rank(self.handle)

@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "gi_finalize.cuh"
 
 namespace itsolv {
 
@@ -73,10 +74,17 @@ static NcclApi* nccl_api() {
   return &api;
 }
 
+constexpr size_t kPeerSlotDoubles = size_t(ITSOLV_MAX_PANEL) * ITSOLV_MAX_PANEL;
+
 struct Comm {
   ncclComm_t comm = nullptr;
   int rank = 0, size = 1;
   double* d_small = nullptr; // staging for host all-reduces and halos
+  // peer exchange buffers of the fused all-reduce (gi_finalize.cuh): mine + the IPC-mapped ones of the other ranks
+  char* d_exchange = nullptr; // [2][size][kPeerSlotDoubles] doubles, then [2][size] sequence words
+  void* peer_base[kMaxPeers] = {};
+  bool peers_ready = false;
+  size_t exchange_bytes() const { return 2 * size_t(size) * kPeerSlotDoubles * sizeof(double) + 2 * size_t(size) * 8 + 64; }
 };
 
 #define ITSOLV_NCCL(call)                                                                                              \
@@ -89,9 +97,28 @@ struct Comm {
     }                                                                                                                  \
   } while (0)
 
+bool comm_peers(itsolv_ctx* ctx, GiPeers* peers) {
+  Comm* c = ctx->comm;
+  if (!c || c->size <= 1 || !c->peers_ready || ctx->opt_p2p_allreduce < 0)
+    return false;
+  peers->nranks = c->size;
+  peers->rank = c->rank;
+  peers->slot_doubles = int(kPeerSlotDoubles);
+  const size_t data_bytes = 2 * size_t(c->size) * kPeerSlotDoubles * sizeof(double);
+  for (int r = 0; r < c->size; ++r) {
+    peers->data[r] = reinterpret_cast<double*>(c->peer_base[r]);
+    peers->flags[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->peer_base[r]) + data_bytes);
+  }
+  return true;
+}
+
 void comm_destroy(itsolv_ctx* ctx) {
   if (!ctx->comm)
     return;
+  for (int r = 0; r < ctx->comm->size && r < kMaxPeers; ++r)
+    if (ctx->comm->peers_ready && r != ctx->comm->rank && ctx->comm->peer_base[r])
+      cudaIpcCloseMemHandle(ctx->comm->peer_base[r]);
+  cudaFree(ctx->comm->d_exchange);
   NcclApi* api = nccl_api();
   if (api && ctx->comm->comm && api->CommDestroy)
     api->CommDestroy(ctx->comm->comm);
@@ -151,6 +178,38 @@ int itsolv_comm_init(itsolv_ctx* ctx, int rank, int nranks, const void* id) {
   ncclUniqueId uid;
   std::memcpy(&uid, id, sizeof(uid));
   ITSOLV_NCCL(api->CommInitRank(&c->comm, nranks, uid, rank));
+  return 0;
+}
+
+int itsolv_comm_p2p_export(itsolv_ctx* ctx, void* handle) {
+  ITSOLV_REQUIRE(ctx->comm, "itsolv_comm_p2p_export: no communicator");
+  Comm* c = ctx->comm;
+  ITSOLV_REQUIRE(c->size <= kMaxPeers, "itsolv_comm_p2p_export: more ranks than one NVSwitch box holds");
+  if (!c->d_exchange) {
+    ITSOLV_CUDA(cudaMalloc(&c->d_exchange, c->exchange_bytes()));
+    ITSOLV_CUDA(cudaMemset(c->d_exchange, 0, c->exchange_bytes()));
+    ITSOLV_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  ITSOLV_CUDA(cudaIpcGetMemHandle(&h, c->d_exchange));
+  static_assert(sizeof(h) == ITSOLV_IPC_HANDLE_BYTES, "ipc handle size");
+  std::memcpy(handle, &h, sizeof(h));
+  return 0;
+}
+
+int itsolv_comm_p2p_import(itsolv_ctx* ctx, const void* handles) {
+  ITSOLV_REQUIRE(ctx->comm && ctx->comm->d_exchange, "itsolv_comm_p2p_import: export first");
+  Comm* c = ctx->comm;
+  for (int r = 0; r < c->size; ++r) {
+    if (r == c->rank) {
+      c->peer_base[r] = c->d_exchange;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const char*>(handles) + size_t(r) * ITSOLV_IPC_HANDLE_BYTES, sizeof(h));
+    ITSOLV_CUDA(cudaIpcOpenMemHandle(&c->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  c->peers_ready = true;
   return 0;
 }
 

@@ -88,6 +88,7 @@ struct itsolv_ctx {
   int opt_go_cols = 0;    // gemm_outer columns per thread (0 = auto)
   int opt_go_ctas = 0;    // gemm_outer CTAs per SM
   int opt_blas1_ctas = 0; // CTAs per SM for streaming kernels
+  int opt_p2p_allreduce = 0; // <0: use ncclAllReduce even when the peer buffers are mapped
 
   std::vector<std::pair<const void*, size_t>> smem_optin; // kernel -> largest dynamic shared memory size opted in
 
@@ -129,6 +130,9 @@ int ensure_dynamic_smem(itsolv_ctx* ctx, const void* kernel, size_t bytes);
 //! sum in place over ranks (device buffer); no-op without a communicator
 int comm_allreduce_device(itsolv_ctx* ctx, double* d, size_t count, bool op_max);
 int comm_allgather_device(itsolv_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank);
+struct GiPeers;
+//! fills the peer table when the exchange buffers of all ranks are mapped (itsolv_comm_p2p_import); false otherwise
+bool comm_peers(itsolv_ctx* ctx, GiPeers* peers);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -204,6 +204,7 @@ static int ctx_init(itsolv_ctx* ctx, int device, cudaStream_t stream, bool own) 
   ctx->opt_go_cols = env_int("ITSOLV_GO_COLS", 0);
   ctx->opt_go_ctas = env_int("ITSOLV_GO_CTAS", 0);
   ctx->opt_blas1_ctas = env_int("ITSOLV_BLAS1_CTAS", 0);
+  ctx->opt_p2p_allreduce = env_int("ITSOLV_P2P_ALLREDUCE", 0);
   return 0;
 }
 
@@ -283,7 +284,8 @@ int itsolv_ctx_set_option(itsolv_ctx* ctx, const char* name, int value) {
                {"GI_NPROD", &ctx->opt_gi_nprod},     {"GI_LOADER", &ctx->opt_gi_loader},
                {"GI_DIRECT", &ctx->opt_gi_direct},   {"GI_DIRECT_CTAS", &ctx->opt_gi_direct_ctas},
                {"GI_MMA", &ctx->opt_gi_mma},       {"GO_COLS", &ctx->opt_go_cols},
-               {"GO_CTAS", &ctx->opt_go_ctas},       {"BLAS1_CTAS", &ctx->opt_blas1_ctas}};
+               {"GO_CTAS", &ctx->opt_go_ctas},       {"BLAS1_CTAS", &ctx->opt_blas1_ctas},
+               {"P2P_ALLREDUCE", &ctx->opt_p2p_allreduce}};
   for (auto& t : table)
     if (std::strcmp(t.n, name) == 0) {
       const int prev = *t.p;

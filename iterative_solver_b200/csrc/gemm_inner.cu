@@ -236,16 +236,25 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
 }
 
 //! decide where the per-CTA partial sums go and how they are finished (fused last-CTA reduction for small outputs)
-void fill_finalize(itsolv_ctx* ctx, int grid, int km, GiFinalize* f, bool* host_direct) {
+void fill_finalize(itsolv_ctx* ctx, int grid_bound, int km, GiFinalize* f, bool* host_direct) {
+  // grid_bound = the largest grid this kernel shape can have on this device: the decision must not depend on the
+  // local vector length, all ranks of a communicator have to take the same path
   f->partials = ctx->d_partials;
-  f->fused = (size_t(grid) * km <= size_t(128) * 1024) ? 1 : 0;
+  f->fused = (size_t(grid_bound) * km <= size_t(128) * 1024) ? 1 : 0;
   f->counter = ctx->d_counter;
   f->flag = nullptr;
   f->seq = 0;
   f->out = ctx->d_result;
+  f->local = ctx->d_result;
+  f->peers.nranks = 1;
+  f->peers.rank = 0;
+  f->peers.slot_doubles = 0;
   *host_direct = false;
-  if (f->fused && itsolv_comm_size(ctx) == 1) {
-    f->out = ctx->h_result; // mapped pinned memory: the kernel delivers the result, no copy, no stream synchronisation
+  const int nranks = itsolv_comm_size(ctx);
+  if (f->fused && (nranks == 1 || comm_peers(ctx, &f->peers))) {
+    // mapped pinned memory: the kernel delivers the result (all-reduced over peer memory when there are several ranks),
+    // no NCCL launch, no copy, no stream synchronisation
+    f->out = ctx->h_result;
     f->flag = ctx->h_flag;
     f->seq = ++ctx->flag_seq;
     *host_direct = true;
@@ -257,6 +266,32 @@ int gemm_inner_direct_device(itsolv_ctx* ctx, const double* const* xx, int k, co
                              bool* host_direct, bool* handled);
 int gemm_inner_mma_device(itsolv_ctx* ctx, const double* const* xx, int k, const double* const* yy, int m, size_t n,
                           bool* host_direct, bool* handled);
+
+//! all-reduce over peer memory of sums that are already complete on this rank (f.local), delivered like the fused tail
+__global__ void __launch_bounds__(256) peer_exchange_kernel(const __grid_constant__ GiFinalize f, int km) {
+  const bool ok = gi_peer_allreduce(f.peers, f.local, km, f.seq, f.out);
+  __syncthreads();
+  if (threadIdx.x == 0 && f.flag) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(f.flag) = ok ? f.seq : (f.seq | (1ull << 63));
+  }
+}
+
+//! after a non-fused reduction (or for an empty shard): exchange ctx->d_result with the peers when they are mapped
+int finish_with_peers(itsolv_ctx* ctx, int km, bool* host_direct) {
+  GiFinalize f{};
+  if (itsolv_comm_size(ctx) == 1 || !comm_peers(ctx, &f.peers))
+    return 0; // single rank or no peer mapping: finish_result() copies (after ncclAllReduce when needed)
+  f.local = ctx->d_result;
+  f.out = ctx->h_result;
+  f.flag = ctx->h_flag;
+  f.seq = ++ctx->flag_seq;
+  peer_exchange_kernel<<<1, 256, 0, ctx->stream>>>(f, km);
+  ITSOLV_CUDA(cudaGetLastError());
+  ctx->counters.launches += 1;
+  *host_direct = true;
+  return 0;
+}
 
 using GiKernel = void (*)(const GiParams);
 
@@ -311,9 +346,9 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
   ITSOLV_REQUIRE(k >= 1 && m >= 1 && k <= ITSOLV_MAX_PANEL && m <= ITSOLV_MAX_PANEL, "gemm_inner: panel size out of range");
   const int km = k * m;
   *host_direct = false;
-  if (n == 0) {
+  if (n == 0) { // an empty shard still takes part in the all-reduce
     ITSOLV_CUDA(cudaMemsetAsync(ctx->d_result, 0, size_t(km) * sizeof(double), ctx->stream));
-    return 0;
+    return finish_with_peers(ctx, km, host_direct);
   }
   {
     bool handled = false;
@@ -453,7 +488,7 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
   const int grid = int(std::min<long long>(total_tiles, (long long)ctx->num_sms * ctas_per_sm));
   if (ensure_partials(ctx, size_t(grid) * km))
     return 1;
-  fill_finalize(ctx, grid, km, &p.fin, host_direct);
+  fill_finalize(ctx, ctx->num_sms * ctas_per_sm, km, &p.fin, host_direct);
 
   GiKernel kernel = pick_kernel(ti, tj, loader, big);
   ITSOLV_REQUIRE(kernel != nullptr, "gemm_inner: thread tile not instantiated");
@@ -463,8 +498,11 @@ int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const dou
   kernel<<<grid, nconsumers + 32 * p.nprod, smem_bytes, ctx->stream>>>(p);
   ITSOLV_CUDA(cudaGetLastError());
   ctx->counters.launches += 1;
-  if (!p.fin.fused)
-    return launch_reduce_partials(ctx, grid, km);
+  if (!p.fin.fused) {
+    if (launch_reduce_partials(ctx, grid, km))
+      return 1;
+    return finish_with_peers(ctx, km, host_direct);
+  }
   return 0;
 }
 
@@ -481,8 +519,13 @@ static int wait_host_flag(itsolv_ctx* ctx) {
   volatile unsigned long long* flag = ctx->h_flag;
   const unsigned long long want = ctx->flag_seq;
   for (unsigned long long spins = 0;; ++spins) {
-    if (*flag == want)
+    const unsigned long long seen = *flag;
+    if (seen == want)
       return 0;
+    if (seen == (want | (1ull << 63))) {
+      set_error("gemm_inner: a peer rank did not arrive at the all-reduce (timeout)");
+      return 1;
+    }
     if ((spins & 0x3FFF) == 0x3FFF) {
       const cudaError_t q = cudaStreamQuery(ctx->stream);
       if (q == cudaSuccess) {

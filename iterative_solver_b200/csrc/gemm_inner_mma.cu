@@ -21,8 +21,9 @@
 
 namespace itsolv {
 
-void fill_finalize(itsolv_ctx* ctx, int grid, int km, GiFinalize* f, bool* host_direct); // gemm_inner.cu
+void fill_finalize(itsolv_ctx* ctx, int grid_bound, int km, GiFinalize* f, bool* host_direct); // gemm_inner.cu
 int launch_reduce_partials(itsolv_ctx* ctx, int grid, int km);                             // gemm_inner.cu
+int finish_with_peers(itsolv_ctx* ctx, int km, bool* host_direct);                         // gemm_inner.cu
 
 constexpr int kMmaConsumerWarps = 8;
 
@@ -275,15 +276,19 @@ int gemm_inner_mma_device(itsolv_ctx* ctx, const double* const* xx, int k, const
   const int km = k * m;
   if (ensure_partials(ctx, size_t(grid) * km))
     return 1;
-  fill_finalize(ctx, grid, km, &p.fin, host_direct);
+  fill_finalize(ctx, ctx->num_sms, km, &p.fin, host_direct);
   if (ensure_dynamic_smem(ctx, reinterpret_cast<const void*>(best->kernel), smem_bytes))
     return 1;
   mark_launch(ctx);
   best->kernel<<<grid, 32 * kMmaConsumerWarps + 32 * p.nprod, smem_bytes, ctx->stream>>>(p);
   ITSOLV_CUDA(cudaGetLastError());
   ctx->counters.launches += 1;
-  if (!p.fin.fused && launch_reduce_partials(ctx, grid, km))
-    return 1;
+  if (!p.fin.fused) {
+    if (launch_reduce_partials(ctx, grid, km))
+      return 1;
+    if (finish_with_peers(ctx, km, host_direct))
+      return 1;
+  }
   *handled = true;
   return 0;
 }

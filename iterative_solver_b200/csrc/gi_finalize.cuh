@@ -6,14 +6,84 @@
 
 namespace itsolv {
 
+constexpr int kMaxPeers = 8; // GPUs of one NVSwitch box
+
+/*!
+ * One-shot all-reduce over NVLink peer memory, fused into the tail of the Gram kernels (replaces the reference's
+ * MPI_Allreduce of the k x m block, array/util/gemm.h:179-182): every rank's finishing CTA stores its k x m sums into
+ * slot [parity][my rank] of EVERY rank's exchange buffer (P2P stores through NVSwitch), publishes a sequence word
+ * next to them, waits for the words of all ranks in its own buffer and adds the slots in rank order — so all ranks
+ * obtain bitwise identical results (the host subspace problem is solved redundantly per rank) and no NCCL launch,
+ * device-to-host copy or stream synchronisation is on the path. Two parities make the buffer reusable: a rank can be
+ * at most one call ahead of any other.
+ */
+struct GiPeers {
+  double* data[kMaxPeers];             // rank r's exchange buffer: [2][nranks][slot_doubles]
+  unsigned long long* flags[kMaxPeers]; // rank r's sequence words: [2][nranks]
+  int nranks, rank;
+  int slot_doubles;
+};
+
 struct GiFinalize {
   double* partials;         // [gridDim.x][km]
   double* out;              // km final sums (device or mapped host memory)
+  double* local;            // device scratch for this rank's sums when peers are exchanged (else unused)
   unsigned int* counter;    // CTAs that have published (reset by the last one)
   unsigned long long* flag; // mapped host word that receives `seq` once `out` is complete (or null)
   unsigned long long seq;
   int fused;                // 0: a separate kernel reduces the partials
+  GiPeers peers;            // peers.nranks <= 1: single rank
 };
+
+__device__ __forceinline__ unsigned long long ld_volatile_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+/*!
+ * Executed by ONE CTA per rank: `local` (km doubles, visible to this CTA) -> all peers, wait, sum in rank order -> out.
+ * Returns false on timeout (a peer never arrived); the caller reports it through the host word.
+ */
+__device__ __forceinline__ bool gi_peer_allreduce(const GiPeers& pr, const double* local, int km, unsigned long long seq,
+                                                  double* out) {
+  const int tid = threadIdx.x;
+  const int parity = int(seq & 1ull);
+  const size_t slot = (size_t(parity) * pr.nranks + pr.rank) * pr.slot_doubles;
+  for (int r = 0; r < pr.nranks; ++r)
+    for (int e = tid; e < km; e += blockDim.x)
+      pr.data[r][slot + e] = local[e];
+  __threadfence_system();
+  __syncthreads();
+  if (tid < pr.nranks)
+    *reinterpret_cast<volatile unsigned long long*>(pr.flags[tid] + size_t(parity) * pr.nranks + pr.rank) = seq;
+  __shared__ int s_ok;
+  if (tid == 0)
+    s_ok = 1;
+  __syncthreads();
+  if (tid < pr.nranks) {
+    const unsigned long long* mine = pr.flags[pr.rank] + size_t(parity) * pr.nranks + tid;
+    const long long t0 = clock64();
+    while (ld_volatile_sys(mine) != seq) {
+      if (clock64() - t0 > 8000000000ll) { // ~4 s: a peer is gone
+        s_ok = 0;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (!s_ok)
+    return false;
+  const double* base = pr.data[pr.rank] + size_t(parity) * pr.nranks * pr.slot_doubles;
+  for (int e = tid; e < km; e += blockDim.x) {
+    double sum = 0.0;
+    for (int r = 0; r < pr.nranks; ++r)
+      sum += __ldcv(base + size_t(r) * pr.slot_doubles + e);
+    out[e] = sum;
+  }
+  return true;
+}
 
 //! call by ALL threads of the CTA after the CTA's partial sums were written to f.partials + blockIdx.x * km
 __device__ __forceinline__ void gi_finalize(const GiFinalize& f, int km, int* s_is_last) {
@@ -37,14 +107,19 @@ __device__ __forceinline__ void gi_finalize(const GiFinalize& f, int km, int* s_
     for (int off = 16; off > 0; off >>= 1)
       sum += __shfl_down_sync(0xffffffffu, sum, off);
     if (lane == 0)
-      f.out[e] = sum;
+      (f.peers.nranks > 1 ? f.local : f.out)[e] = sum;
   }
   __syncthreads();
+  bool ok = true;
+  if (f.peers.nranks > 1) {
+    ok = gi_peer_allreduce(f.peers, f.local, km, f.seq, f.out);
+    __syncthreads();
+  }
   if (tid == 0) {
     *f.counter = 0u;
     if (f.flag) {
       __threadfence_system();
-      *reinterpret_cast<volatile unsigned long long*>(f.flag) = f.seq;
+      *reinterpret_cast<volatile unsigned long long*>(f.flag) = ok ? f.seq : (f.seq | (1ull << 63));
     }
   }
 }

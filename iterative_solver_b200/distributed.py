@@ -25,7 +25,7 @@ def broadcast_bytes(payload: bytes | None, nbytes: int, src: int = 0) -> bytes:
     return bytes(t.cpu().numpy().tobytes())
 
 
-def attach_communicator(ctx: Context) -> None:
+def attach_communicator(ctx: Context, peer_memory: bool = True) -> None:
     """Give the context a communicator spanning the torch.distributed world (no-op for a single process)."""
     import torch.distributed as dist
 
@@ -35,3 +35,12 @@ def attach_communicator(ctx: Context) -> None:
     uid = ctx.unique_id() if dist.get_rank() == 0 else None
     uid = broadcast_bytes(uid, 128, 0)
     ctx.init_comm(dist.get_rank(), dist.get_world_size(), uid)
+    if peer_memory and dist.get_world_size() <= 8 and dist.get_backend() == "nccl":
+        # the fused all-reduce of the Gram kernels writes into the other ranks' exchange buffers over NVLink:
+        # gather every rank's CUDA IPC handle (64 bytes) and map them
+        import torch
+        mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).cuda()
+        allh = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+        dist.all_gather(allh, mine)
+        ctx.p2p_import(b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh))
+        dist.barrier()
