@@ -70,6 +70,8 @@ int itsolv_free(itsolv_ctx* ctx, double* p);
 int itsolv_upload(itsolv_ctx* ctx, double* dst_device, const double* src_host, size_t n);   /* synchronous */
 int itsolv_download(itsolv_ctx* ctx, double* dst_host, const double* src_device, size_t n); /* synchronous */
 int itsolv_upload_bytes(itsolv_ctx* ctx, void* dst_device, const void* src_host, size_t bytes);  /* synchronous */
+/* bytes currently handed out by itsolv_alloc and their high-water mark (memory planning of the large configurations) */
+int itsolv_mem_usage(itsolv_ctx* ctx, size_t* live_bytes, size_t* peak_bytes, int reset_peak);
 int itsolv_mem_info(itsolv_ctx* ctx, size_t* free_bytes, size_t* total_bytes);
 
 /* ---- communicator: row-sharded vectors, one rank per GPU; replaces the reference's MPI communicator

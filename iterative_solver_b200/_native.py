@@ -78,6 +78,7 @@ KERNEL_API = {
     "itsolv_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "itsolv_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "itsolv_upload_bytes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "itsolv_mem_usage": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_int]),
     "itsolv_mem_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "itsolv_comm_unique_id": (C.c_int, [C.c_void_p]),
     "itsolv_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

@@ -74,6 +74,11 @@ class Context:
     def set_option(self, name: str, value: int) -> int:
         return self.lib.itsolv_ctx_set_option(self.handle, name.encode(), int(value))
 
+    def mem_usage(self, reset_peak: bool = False):
+        live, peak = C.c_size_t(), C.c_size_t()
+        self._check(self.lib.itsolv_mem_usage(self.handle, C.byref(live), C.byref(peak), int(reset_peak)))
+        return live.value, peak.value
+
     def counters(self) -> N.Counters:
         c = N.Counters()
         self.lib.itsolv_ctx_counters(self.handle, C.byref(c))

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -52,6 +53,8 @@ struct itsolv_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaMemPool_t pool = nullptr;
+  std::unordered_map<const void*, size_t> alloc_bytes; // live vectors handed out by itsolv_alloc
+  size_t live_bytes = 0, peak_bytes = 0;
 
   // workspace for per-CTA partial Gram matrices and reduced results (device), pinned host mirror for results
   double* d_partials = nullptr;

@@ -325,13 +325,30 @@ int itsolv_ctx_timer_stop(itsolv_ctx* ctx, int id, double* milliseconds) {
 
 int itsolv_alloc(itsolv_ctx* ctx, size_t n, double** out) {
   void* p = nullptr;
-  ITSOLV_CUDA(cudaMallocAsync(&p, (n ? n : 1) * sizeof(double), ctx->stream));
+  const size_t bytes = (n ? n : 1) * sizeof(double);
+  ITSOLV_CUDA(cudaMallocAsync(&p, bytes, ctx->stream));
   *out = static_cast<double*>(p);
+  ctx->alloc_bytes[p] = bytes;
+  ctx->live_bytes += bytes;
+  ctx->peak_bytes = ctx->live_bytes > ctx->peak_bytes ? ctx->live_bytes : ctx->peak_bytes;
   return 0;
 }
 int itsolv_free(itsolv_ctx* ctx, double* p) {
-  if (p)
+  if (p) {
+    auto it = ctx->alloc_bytes.find(p);
+    if (it != ctx->alloc_bytes.end()) {
+      ctx->live_bytes -= it->second;
+      ctx->alloc_bytes.erase(it);
+    }
     ITSOLV_CUDA(cudaFreeAsync(p, ctx->stream));
+  }
+  return 0;
+}
+int itsolv_mem_usage(itsolv_ctx* ctx, size_t* live_bytes, size_t* peak_bytes, int reset_peak) {
+  *live_bytes = ctx->live_bytes;
+  *peak_bytes = ctx->peak_bytes;
+  if (reset_peak)
+    ctx->peak_bytes = ctx->live_bytes;
   return 0;
 }
 int itsolv_upload(itsolv_ctx* ctx, double* dst, const double* src, size_t n) {
