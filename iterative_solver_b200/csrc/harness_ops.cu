@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256) banded_fill_kernel(int kind, int k, long long off, long long n, double* __restrict__ out) {
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
     const long long i = off + r;
-    out[r] = kind == 0 ? double(i + 1) : 1.0 + double((i + k) % (k + 3)) / double(k + 3);
+    out[r] = kind == 0 ? double(i + 1) : double((i * (k + 2) + k) % (2 * k + 5)) / double(2 * k + 5) - 0.5;
   }
 }
 

@@ -66,26 +66,29 @@ public:
 
   void gemm_outer(const Matrix<value_type> alphas, const CVecRef<AR>& xx, const VecRef<AL>& yy) override {
     this->m_counter->gemm_outer++;
-    // shape rules of the reference's distributed implementation (array/util/gemm.h:66-71)
-    if (alphas.rows() != xx.size())
+    // Shape rules of the reference's loops (array/util/gemm.h:186-203, 258-265): one x per row of alphas, one y per
+    // column; the drivers may pass MORE y vectors than columns (construct_solution hands all R buffers with
+    // roots.size() columns, itsolv/IterativeSolverTemplate.h:44-64) and only the first alphas.cols() are touched.
+    if (alphas.rows() > xx.size())
       throw std::out_of_range("gemm_outer: dimensions of xx and alphas are different.");
-    if (alphas.cols() != yy.size())
+    if (alphas.cols() > yy.size())
       throw std::out_of_range("gemm_outer: dimensions of yy and alphas are different.");
-    if (xx.empty() || yy.empty())
+    const size_t nx = alphas.rows(), ny = alphas.cols();
+    if (nx == 0 || ny == 0)
       return;
-    std::vector<const double*> px(xx.size());
-    std::vector<double*> py(yy.size());
+    std::vector<const double*> px(nx);
+    std::vector<double*> py(ny);
     const AL& first = yy[0].get();
-    for (size_t i = 0; i < xx.size(); ++i) {
+    for (size_t i = 0; i < nx; ++i) {
       first.require_compatible(xx[i].get(), "gemm_outer");
       px[i] = xx[i].get().data();
     }
-    for (size_t j = 0; j < yy.size(); ++j) {
+    for (size_t j = 0; j < ny; ++j) {
       first.require_compatible(yy[j].get(), "gemm_outer");
       py[j] = yy[j].get().data();
     }
-    check(itsolv_gemm_outer_f64(first.context(), alphas.data().data(), int(xx.size()), int(yy.size()), px.data(),
-                                py.data(), first.local_size(), 0),
+    check(itsolv_gemm_outer_f64(first.context(), alphas.data().data(), int(nx), int(ny), px.data(), py.data(),
+                                first.local_size(), 0),
           "ArrayHandlerCUDA::gemm_outer");
   }
 
@@ -189,18 +192,19 @@ public:
   //! alphas: rows <-> sparse xx, columns <-> dense yy (reference array/util/gemm.h:207-224)
   void gemm_outer(const Matrix<value_type> alphas, const CVecRef<AR>& xx, const VecRef<AL>& yy) override {
     this->m_counter->gemm_outer++;
-    if (alphas.rows() != xx.size() || alphas.cols() != yy.size())
+    if (alphas.rows() > xx.size() || alphas.cols() > yy.size())
       throw std::out_of_range("gemm_outer: dimensions of alphas do not match xx, yy");
-    if (xx.empty() || yy.empty())
+    const size_t nx = alphas.rows(), ny = alphas.cols(); // more y vectors than columns is allowed, see ArrayHandlerCUDA
+    if (nx == 0 || ny == 0)
       return;
-    Packed p(xx);
-    std::vector<double*> py(yy.size());
+    Packed p(CVecRef<AR>(xx.begin(), xx.begin() + nx));
+    std::vector<double*> py(ny);
     const AL& first = yy[0].get();
-    for (size_t j = 0; j < yy.size(); ++j) {
+    for (size_t j = 0; j < ny; ++j) {
       first.require_compatible(yy[j].get(), "gemm_outer");
       py[j] = yy[j].get().data();
     }
-    check(itsolv_sparse_gemm_outer_f64(first.context(), alphas.data().data(), int(xx.size()), int(yy.size()),
+    check(itsolv_sparse_gemm_outer_f64(first.context(), alphas.data().data(), int(nx), int(ny),
                                        p.ptr.data(), p.idx.data(), p.val.data(), py.data(), first.local_size(),
                                        first.local_start()),
           "ArrayHandlerCUDASparse::gemm_outer");

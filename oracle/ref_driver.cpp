@@ -160,7 +160,7 @@ public:
         }
     }
   }
-  static double rhs_solution(int k, int64_t i) { return 1.0 + double((i + k) % (k + 3)) / double(k + 3); }
+  static double rhs_solution(int k, int64_t i) { return double((i * (k + 2) + k) % (2 * k + 5)) / double(2 * k + 5) - 0.5; }
   void make_rhs(int k, Vec& out) const {
     Vec u(n);
     for (int64_t i = 0; i < n; ++i)
