@@ -34,9 +34,15 @@ __global__ void __launch_bounds__(256)
     const long long i = off + r;
     const long long lo = i - b > 0 ? i - b : 0;
     const long long hi = i + b < n_global - 1 ? i + b : n_global - 1;
+    // (i + j) mod 7 with one 64-bit remainder per row: j = i + d, so (i + j) mod 7 = (2 (i mod 7) + d) mod 7
+    const int i7 = int(i % 7);
+    int e7 = (2 * i7 + int(lo - i) + 7 * ((b + 6) / 7 + 1)) % 7;
     double acc = 0.0;
-    for (long long j = lo; j <= hi; ++j)
-      acc = __dadd_rn(acc, __dmul_rn(band_entry(i, j, eps), x_at(j, off, n, b, x, x_lo, x_hi)));
+    for (long long j = lo; j <= hi; ++j) {
+      const double aij = i == j ? double(i + 1) : __dmul_rn(eps, double(1 + e7));
+      acc = __dadd_rn(acc, __dmul_rn(aij, x_at(j, off, n, b, x, x_lo, x_hi)));
+      e7 = e7 == 6 ? 0 : e7 + 1;
+    }
     y[r] = acc;
   }
 }

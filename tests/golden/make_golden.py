@@ -38,7 +38,7 @@ SOLVE_CASES = {
     "banded_lineq_n50000_r1": dict(n=50000, kind=N.KIND_LINEQ, nroots=1, hermitian=1),
     "banded_lineq_n1000_r3": dict(n=1000, kind=N.KIND_LINEQ, nroots=3, hermitian=1),
     "banded_lineq_n100000_r3": dict(n=100000, kind=N.KIND_LINEQ, nroots=3, hermitian=1),
-    "banded_lineq_n100000_r8": dict(n=100000, kind=N.KIND_LINEQ, nroots=8, hermitian=1),
+    "banded_lineq_n20000_r8": dict(n=20000, kind=N.KIND_LINEQ, nroots=8, hermitian=1),
     "banded_lineq_n20000_r8_qcap12": dict(n=20000, kind=N.KIND_LINEQ, nroots=8, hermitian=1, max_size_qspace=12),
     "banded_diis_n50000": dict(n=50000, kind=N.KIND_DIIS, max_size_qspace=6),
 }

@@ -115,6 +115,7 @@ def run_all(ctx, lib, args, n, nvec, take, run, _ptr_array, _dbl):
             ctx.gemm_outer(alpha, take(k), take(m))
         return f
 
+    run("spmv_generated[b=4]", 16 * n, lambda: (lambda v: ctx.banded_apply(v[0], v[1], n, 0, 4, 1e-3))(take(2)))
     run("fill", 8 * n, lambda: ctx.fill(1.0, take(1)[0]))
     run("scal", 16 * n, lambda: ctx.scal(1.0000001, take(1)[0]))
     run("copy", 16 * n, lambda: ctx.copy(*take(2)))
