@@ -103,6 +103,19 @@ int itsolv_copy_f64(itsolv_ctx* ctx, double* dst, const double* src, size_t n);
 int itsolv_axpy_f64(itsolv_ctx* ctx, double alpha, const double* x, double* y, size_t n);
 int itsolv_dot_f64(itsolv_ctx* ctx, const double* x, const double* y, size_t n, double* result);
 
+/* ---- batched forms used by the fused driver path (iterative_solver_b200/host/FusedDavidson.h): the same arithmetic as
+ * w separate calls of the functions above, in one pass / one launch ---- */
+/* x_k *= alpha[k] */
+int itsolv_scal_batch_f64(itsolv_ctx* ctx, const double* alpha, double* const* x, int w, size_t n);
+/* y_k = y_k + alpha[k]*x_k for w independent pairs (residual construction, LinearEigensystemDavidson.h:186-192) */
+int itsolv_axpy_batch_f64(itsolv_ctx* ctx, const double* alpha, const double* const* x, double* const* y, int w, size_t n);
+/* one step of the R-R modified Gram-Schmidt (propose_rspace.h:451-463): ri *= inv_norm; rj[k] += (-ov[k])*ri */
+int itsolv_mgs_step_f64(itsolv_ctx* ctx, double inv_norm, double* ri, const double* ov, double* const* rj, int m, size_t n);
+/* counter that every call which may write a vector advances (and DistrArrayCUDA::data() non-const): results cached
+ * on the host side (ArrayHandlerCUDA's primed dots) are valid only while it stands still */
+unsigned long long itsolv_ctx_write_epoch(itsolv_ctx* ctx);
+void itsolv_ctx_note_write(itsolv_ctx* ctx);
+
 /* ---- panel contractions (reference ArrayHandler.h:195,200; CPU path array/util/gemm.h:157-203, 258-279) ---- */
 /* out[i*m+j] = sum_r xx[i][r]*yy[j][r]; each HBM byte of the k+m vectors is read once */
 int itsolv_gemm_inner_f64(itsolv_ctx* ctx, const double* const* xx, int k, const double* const* yy, int m, size_t n,

@@ -45,7 +45,7 @@ typedef struct itsolv_solve_spec {
   int32_t verbosity;            /* 0..3 as IterativeSolver::set_verbosity(int) */
   int32_t trace;                /* record every dot/gemm_inner result for parity checks */
   int32_t explicit_csr;         /* banded operator: 1 = stored CSR arrays, 0 = entries generated in the kernel */
-  int32_t reserved;
+  int32_t fused;                /* Davidson on the CUDA backend: 1 = fused driver path (FusedDavidson.h); ignored by the oracle */
 } itsolv_solve_spec;
 
 typedef struct itsolv_solve_result {

@@ -33,7 +33,7 @@ class SolveSpec(C.Structure):
                 ("nbuffers", C.c_int32), ("half_bandwidth", C.c_int32), ("hermitian", C.c_int32), ("eps", C.c_double),
                 ("convergence_threshold", C.c_double), ("max_iter", C.c_int32), ("max_size_qspace", C.c_int32),
                 ("reset_D", C.c_int32), ("max_p", C.c_int32), ("verbosity", C.c_int32), ("trace", C.c_int32),
-                ("explicit_csr", C.c_int32), ("reserved", C.c_int32)]
+                ("explicit_csr", C.c_int32), ("fused", C.c_int32)]
 
 
 class SolveResult(C.Structure):
@@ -95,6 +95,11 @@ KERNEL_API = {
     "itsolv_copy_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "itsolv_axpy_f64": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_size_t]),
     "itsolv_dot_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, c_double_p]),
+    "itsolv_scal_batch_f64": (C.c_int, [C.c_void_p, c_double_p, c_void_pp, C.c_int, C.c_size_t]),
+    "itsolv_axpy_batch_f64": (C.c_int, [C.c_void_p, c_double_p, c_void_pp, c_void_pp, C.c_int, C.c_size_t]),
+    "itsolv_mgs_step_f64": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, c_double_p, c_void_pp, C.c_int, C.c_size_t]),
+    "itsolv_ctx_write_epoch": (C.c_ulonglong, [C.c_void_p]),
+    "itsolv_ctx_note_write": (None, [C.c_void_p]),
     "itsolv_gemm_inner_f64": (C.c_int, [C.c_void_p, c_void_pp, C.c_int, c_void_pp, C.c_int, C.c_size_t, c_double_p]),
     "itsolv_gemm_outer_f64": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_int, c_void_pp, c_void_pp, C.c_size_t,
                                         C.c_int]),

@@ -143,6 +143,20 @@ class Context:
     def axpy(self, alpha: float, x, y):
         self._check(self.lib.itsolv_axpy_f64(self.handle, alpha, _ptr(x), _ptr(y), x.numel()))
 
+    def scal_batch(self, alpha: Sequence[float], xs: Sequence):
+        a = np.ascontiguousarray(alpha, dtype=np.float64)
+        self._check(self.lib.itsolv_scal_batch_f64(self.handle, _dbl(a), _ptr_array(xs), len(xs), xs[0].numel()))
+
+    def axpy_batch(self, alpha: Sequence[float], xs: Sequence, ys: Sequence):
+        a = np.ascontiguousarray(alpha, dtype=np.float64)
+        self._check(self.lib.itsolv_axpy_batch_f64(self.handle, _dbl(a), _ptr_array(xs), _ptr_array(ys), len(ys),
+                                                   ys[0].numel()))
+
+    def mgs_step(self, inv_norm: float, ri, ov: Sequence[float], rjs: Sequence):
+        o = np.ascontiguousarray(ov, dtype=np.float64)
+        self._check(self.lib.itsolv_mgs_step_f64(self.handle, inv_norm, _ptr(ri), _dbl(o) if len(rjs) else None,
+                                                 _ptr_array(rjs), len(rjs), ri.numel()))
+
     def dot(self, x, y) -> float:
         r = C.c_double()
         self._check(self.lib.itsolv_dot_f64(self.handle, _ptr(x), _ptr(y), x.numel(), C.byref(r)))

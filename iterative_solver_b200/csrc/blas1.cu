@@ -19,6 +19,23 @@ struct PrecondParams {
   int w;
 };
 
+struct BatchParams {
+  double* y[ITSOLV_MAX_PANEL];
+  const double* x[ITSOLV_MAX_PANEL];
+  double alpha[ITSOLV_MAX_PANEL];
+  size_t n;
+  int w;
+};
+
+struct MgsStepParams {
+  double* rj[ITSOLV_MAX_PANEL];
+  double ov[ITSOLV_MAX_PANEL];
+  double* ri;
+  double inv_norm;
+  size_t n;
+  int m;
+};
+
 // ---- generic driver: VEC = all pointers 16-byte aligned -> double2 path for the even prefix, scalar for the last odd row
 template <bool VEC, class OpPair, class OpOne>
 __device__ __forceinline__ void stream_rows(size_t n, OpPair op2, OpOne op1) {
@@ -123,6 +140,81 @@ __global__ void __launch_bounds__(kThreads, 4) precondition_kernel(const __grid_
       });
 }
 
+// y_k[i] = y_k[i] * alpha_k for w vectors in one launch (the normalisation of a working set,
+// reference itsolv/propose_rspace.h:17-28: w separate scal sweeps)
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 4) scal_batch_kernel(const __grid_constant__ BatchParams prm) {
+  const int w = prm.w;
+  stream_rows<VEC>(
+      prm.n,
+      [&](size_t p) {
+        for (int k = 0; k < w; ++k) {
+          double2* yk = reinterpret_cast<double2*>(prm.y[k]);
+          double2 v = yk[p];
+          v.x = __dmul_rn(v.x, prm.alpha[k]);
+          v.y = __dmul_rn(v.y, prm.alpha[k]);
+          yk[p] = v;
+        }
+      },
+      [&](size_t i) {
+        for (int k = 0; k < w; ++k)
+          prm.y[k][i] = __dmul_rn(prm.y[k][i], prm.alpha[k]);
+      });
+}
+
+// y_k[i] = y_k[i] + alpha_k * x_k[i] for w independent pairs in one launch (residual construction,
+// reference itsolv/LinearEigensystemDavidson.h:186-192: one axpy sweep per root); product rounded before the sum
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 4) axpy_batch_kernel(const __grid_constant__ BatchParams prm) {
+  const int w = prm.w;
+  stream_rows<VEC>(
+      prm.n,
+      [&](size_t p) {
+        for (int k = 0; k < w; ++k) {
+          const double2 xv = reinterpret_cast<const double2*>(prm.x[k])[p];
+          double2* yk = reinterpret_cast<double2*>(prm.y[k]);
+          double2 yv = yk[p];
+          yv.x = __dadd_rn(yv.x, __dmul_rn(prm.alpha[k], xv.x));
+          yv.y = __dadd_rn(yv.y, __dmul_rn(prm.alpha[k], xv.y));
+          yk[p] = yv;
+        }
+      },
+      [&](size_t i) {
+        for (int k = 0; k < w; ++k)
+          prm.y[k][i] = __dadd_rn(prm.y[k][i], __dmul_rn(prm.alpha[k], prm.x[k][i]));
+      });
+}
+
+// One step of the R-R modified Gram-Schmidt (reference itsolv/propose_rspace.h:451-463): r_i is scaled to unit norm and
+// removed from the m later vectors, r_i read once: r_i *= inv_norm; r_j += (-ov_j) * r_i. Element for element the
+// arithmetic of the reference's scal followed by its axpys.
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 4) mgs_step_kernel(const __grid_constant__ MgsStepParams prm) {
+  const int m = prm.m;
+  stream_rows<VEC>(
+      prm.n,
+      [&](size_t p) {
+        double2* ri = reinterpret_cast<double2*>(prm.ri);
+        double2 v = ri[p];
+        v.x = __dmul_rn(v.x, prm.inv_norm);
+        v.y = __dmul_rn(v.y, prm.inv_norm);
+        ri[p] = v;
+        for (int k = 0; k < m; ++k) {
+          double2* rj = reinterpret_cast<double2*>(prm.rj[k]);
+          double2 y = rj[p];
+          y.x = __dadd_rn(y.x, __dmul_rn(-prm.ov[k], v.x));
+          y.y = __dadd_rn(y.y, __dmul_rn(-prm.ov[k], v.y));
+          rj[p] = y;
+        }
+      },
+      [&](size_t i) {
+        const double v = __dmul_rn(prm.ri[i], prm.inv_norm);
+        prm.ri[i] = v;
+        for (int k = 0; k < m; ++k)
+          prm.rj[k][i] = __dadd_rn(prm.rj[k][i], __dmul_rn(-prm.ov[k], v));
+      });
+}
+
 static int stream_grid(itsolv_ctx* ctx, size_t n) {
   const int per_sm = ctx->opt_blas1_ctas > 0 ? ctx->opt_blas1_ctas : 4; // 4 x 256 threads, 4 row pairs in flight each
   const size_t want = (n / 2 + size_t(kThreads) * kUnroll - 1) / (size_t(kThreads) * kUnroll);
@@ -183,6 +275,75 @@ int itsolv_axpy_f64(itsolv_ctx* ctx, double alpha, const double* x, double* y, s
     return 0;
   CallScope scope(ctx, OP_BLAS1, 24.0 * n);
   LAUNCH_STREAM(axpy_kernel, aligned16(x) && aligned16(y), alpha, x, y, n);
+  return 0;
+}
+
+int itsolv_scal_batch_f64(itsolv_ctx* ctx, const double* alpha, double* const* x, int w, size_t n) {
+  ctx->counters.n_scal += w > 0 ? w : 0;
+  if (n == 0 || w <= 0)
+    return 0;
+  for (int start = 0; start < w; start += ITSOLV_MAX_PANEL) {
+    const int cnt = (w - start) < ITSOLV_MAX_PANEL ? (w - start) : ITSOLV_MAX_PANEL;
+    BatchParams prm;
+    bool vec = true;
+    for (int k = 0; k < cnt; ++k) {
+      prm.y[k] = x[start + k];
+      prm.alpha[k] = alpha[start + k];
+      vec = vec && aligned16(prm.y[k]);
+    }
+    prm.n = n;
+    prm.w = cnt;
+    CallScope scope(ctx, OP_BLAS1, 16.0 * n * cnt);
+    LAUNCH_STREAM(scal_batch_kernel, vec, prm);
+  }
+  return 0;
+}
+
+int itsolv_axpy_batch_f64(itsolv_ctx* ctx, const double* alpha, const double* const* x, double* const* y, int w, size_t n) {
+  ctx->counters.n_axpy += w > 0 ? w : 0;
+  if (n == 0 || w <= 0)
+    return 0;
+  for (int a = 0; a < w; ++a)
+    for (int b = 0; b < w; ++b)
+      ITSOLV_REQUIRE(x[a] != y[b] && (a == b || y[a] != y[b]), "itsolv_axpy_batch_f64: the pairs must not alias each other");
+  for (int start = 0; start < w; start += ITSOLV_MAX_PANEL) {
+    const int cnt = (w - start) < ITSOLV_MAX_PANEL ? (w - start) : ITSOLV_MAX_PANEL;
+    BatchParams prm;
+    bool vec = true;
+    for (int k = 0; k < cnt; ++k) {
+      prm.y[k] = y[start + k];
+      prm.x[k] = x[start + k];
+      prm.alpha[k] = alpha[start + k];
+      vec = vec && aligned16(prm.y[k]) && aligned16(prm.x[k]);
+    }
+    prm.n = n;
+    prm.w = cnt;
+    CallScope scope(ctx, OP_BLAS1, 24.0 * n * cnt);
+    LAUNCH_STREAM(axpy_batch_kernel, vec, prm);
+  }
+  return 0;
+}
+
+int itsolv_mgs_step_f64(itsolv_ctx* ctx, double inv_norm, double* ri, const double* ov, double* const* rj, int m, size_t n) {
+  ctx->counters.n_scal += 1;
+  ctx->counters.n_axpy += m > 0 ? m : 0;
+  if (n == 0)
+    return 0;
+  ITSOLV_REQUIRE(m >= 0 && m <= ITSOLV_MAX_PANEL, "itsolv_mgs_step_f64: too many vectors");
+  MgsStepParams prm;
+  bool vec = aligned16(ri);
+  for (int k = 0; k < m; ++k) {
+    ITSOLV_REQUIRE(rj[k] != ri, "itsolv_mgs_step_f64: a target aliases the pivot vector");
+    prm.rj[k] = rj[k];
+    prm.ov[k] = ov[k];
+    vec = vec && aligned16(rj[k]);
+  }
+  prm.ri = ri;
+  prm.inv_norm = inv_norm;
+  prm.n = n;
+  prm.m = m;
+  CallScope scope(ctx, OP_BLAS1, 16.0 * n * (m + 1));
+  LAUNCH_STREAM(mgs_step_kernel, vec, prm);
   return 0;
 }
 

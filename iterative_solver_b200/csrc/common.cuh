@@ -96,6 +96,7 @@ struct itsolv_ctx {
   std::vector<std::pair<const void*, size_t>> smem_optin; // kernel -> largest dynamic shared memory size opted in
 
   itsolv::CallScope* active_scope = nullptr;
+  unsigned long long write_epoch = 1; // advanced by every launch (see mark_launch): host-side result caches key on it
   itsolv_counters counters{};
   bool profiling = false;
   std::vector<itsolv::PendingEvent> pending;

@@ -37,6 +37,7 @@ CallScope::CallScope(itsolv_ctx* c, int cls_, double bytes) : ctx(c), cls(cls_) 
 }
 
 void mark_launch(itsolv_ctx* ctx) {
+  ++ctx->write_epoch; // conservative: any launch may have written a vector
   CallScope* s = ctx->active_scope;
   if (!s || !s->armed || s->start)
     return;
@@ -266,6 +267,8 @@ void itsolv_ctx_destroy(itsolv_ctx* ctx) {
   delete ctx;
 }
 
+unsigned long long itsolv_ctx_write_epoch(itsolv_ctx* ctx) { return ctx->write_epoch; }
+void itsolv_ctx_note_write(itsolv_ctx* ctx) { ++ctx->write_epoch; }
 void* itsolv_ctx_stream(itsolv_ctx* ctx) { return ctx->stream; }
 int itsolv_ctx_device(itsolv_ctx* ctx) { return ctx->device; }
 
@@ -324,6 +327,7 @@ int itsolv_ctx_timer_stop(itsolv_ctx* ctx, int id, double* milliseconds) {
 }
 
 int itsolv_alloc(itsolv_ctx* ctx, size_t n, double** out) {
+  ++ctx->write_epoch;
   void* p = nullptr;
   const size_t bytes = (n ? n : 1) * sizeof(double);
   ITSOLV_CUDA(cudaMallocAsync(&p, bytes, ctx->stream));
@@ -334,6 +338,7 @@ int itsolv_alloc(itsolv_ctx* ctx, size_t n, double** out) {
   return 0;
 }
 int itsolv_free(itsolv_ctx* ctx, double* p) {
+  ++ctx->write_epoch;
   if (p) {
     auto it = ctx->alloc_bytes.find(p);
     if (it != ctx->alloc_bytes.end()) {
@@ -352,11 +357,13 @@ int itsolv_mem_usage(itsolv_ctx* ctx, size_t* live_bytes, size_t* peak_bytes, in
   return 0;
 }
 int itsolv_upload(itsolv_ctx* ctx, double* dst, const double* src, size_t n) {
+  ++ctx->write_epoch;
   ITSOLV_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   ITSOLV_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 int itsolv_upload_bytes(itsolv_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  ++ctx->write_epoch;
   ITSOLV_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   ITSOLV_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;

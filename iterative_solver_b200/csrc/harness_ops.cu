@@ -124,6 +124,7 @@ extern "C" {
 
 int itsolv_banded_apply_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offset, size_t n, int b, double eps,
                             const double* x, const double* x_lo, const double* x_hi, double* y) {
+  ++ctx->write_epoch;
   if (n == 0)
     return 0;
   ITSOLV_REQUIRE(x != y, "itsolv_banded_apply_f64: in-place application is not supported");
@@ -139,6 +140,7 @@ int itsolv_banded_apply_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offse
 int itsolv_csr_apply_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offset, size_t n, int b, const int64_t* row_ptr,
                          const int32_t* col, const double* val, const double* x, const double* x_lo, const double* x_hi,
                          double* y) {
+  ++ctx->write_epoch;
   if (n == 0)
     return 0;
   ITSOLV_REQUIRE(x != y, "itsolv_csr_apply_f64: in-place application is not supported");
@@ -153,6 +155,7 @@ int itsolv_csr_apply_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offset, 
 }
 
 int itsolv_banded_fill_f64(itsolv_ctx* ctx, int kind, int k, int64_t row_offset, size_t n, double* out) {
+  ++ctx->write_epoch;
   if (n == 0)
     return 0;
   banded_fill_kernel<<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(kind, k, row_offset, (long long)n, out);
@@ -162,6 +165,7 @@ int itsolv_banded_fill_f64(itsolv_ctx* ctx, int kind, int k, int64_t row_offset,
 }
 
 int itsolv_example_apply_f64(itsolv_ctx* ctx, size_t n, const double* x, double* y) {
+  ++ctx->write_epoch;
   if (n == 0)
     return 0;
   ITSOLV_REQUIRE(x != y, "itsolv_example_apply_f64: in-place application is not supported");
@@ -174,6 +178,7 @@ int itsolv_example_apply_f64(itsolv_ctx* ctx, size_t n, const double* x, double*
 int itsolv_banded_p_action_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offset, size_t n, int b, double eps,
                                int nact, double* const* actions, int nP, const int32_t* map_ptr, const int64_t* idx,
                                const double* val, const double* pcoef) {
+  ++ctx->write_epoch;
   if (nact <= 0 || nP <= 0 || n == 0)
     return 0;
   ITSOLV_REQUIRE(nact <= ITSOLV_MAX_PANEL, "itsolv_banded_p_action_f64: too many action vectors");

@@ -131,6 +131,7 @@ extern "C" {
 
 int itsolv_sparse_copy_f64(itsolv_ctx* ctx, double* x, size_t n, size_t global_offset, int nnz, const int64_t* idx,
                            const double* val) {
+  ++ctx->write_epoch;
   ctx->counters.n_sparse++;
   if (itsolv_fill_f64(ctx, 0.0, x, n))
     return 1;
@@ -197,6 +198,7 @@ int itsolv_sparse_gemm_inner_f64(itsolv_ctx* ctx, const double* const* xx, int k
 int itsolv_sparse_gemm_outer_f64(itsolv_ctx* ctx, const double* alpha, int nmap, int ndense, const int32_t* map_ptr,
                                  const int64_t* idx, const double* val, double* const* yy, size_t n,
                                  size_t global_offset) {
+  ++ctx->write_epoch;
   ctx->counters.n_sparse++;
   if (nmap <= 0 || ndense <= 0 || n == 0)
     return 0;

@@ -58,6 +58,7 @@ inline double now_seconds() {
  *   ProblemT& problem();                              Problem<R> with make_rhs(k, R&), seconds_action, seconds_precond
  *   void synchronize();                               wait for outstanding device work (no-op on the host)
  *   void timer_start(); double timer_stop_ms();       device stopwatch around solve() (0 on the host)
+ *   unique_ptr<LinearEigensystemDavidson<R,R,P>> make_davidson(handlers, spec);
  */
 template <class Backend>
 int run_solve(const itsolv_solve_spec& spec, Backend& backend, itsolv_solve_result& res, double* solutions) {
@@ -126,7 +127,8 @@ int run_solve(const itsolv_solve_spec& spec, Backend& backend, itsolv_solve_resu
 
   problem.seconds_action = problem.seconds_precond = 0;
   if (spec.kind == ITSOLV_KIND_DAVIDSON) {
-    its::LinearEigensystemDavidson<R, R, P> solver(handlers);
+    auto solver_ptr = backend.make_davidson(handlers, spec); // the reference's class, or a subclass of it
+    auto& solver = *solver_ptr;
     configure(solver);
     solver.set_n_roots(nroots);
     solver.set_hermiticity(spec.hermitian != 0);

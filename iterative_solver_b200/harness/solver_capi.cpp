@@ -18,6 +18,7 @@
 
 #include "ArrayHandlerCUDA.h"
 #include "DistrArrayCUDA.h"
+#include "FusedDavidson.h"
 
 namespace {
 using itsolv_b200::check;
@@ -237,6 +238,12 @@ struct DeviceBackend {
   size_t n_local() { return prob.nloc; }
   DeviceProblem& problem() { return prob; }
   void synchronize() { check(itsolv_ctx_synchronize(ctx), "synchronize"); }
+  std::unique_ptr<its::LinearEigensystemDavidson<R, R, PMap>>
+  make_davidson(const std::shared_ptr<itsolv_b200::HandlersCUDA>& handlers, const itsolv_solve_spec& spec) {
+    if (spec.fused)
+      return std::make_unique<itsolv_b200::LinearEigensystemDavidsonFused>(handlers);
+    return std::make_unique<its::LinearEigensystemDavidson<R, R, PMap>>(handlers);
+  }
   void timer_start() { check(itsolv_ctx_timer_start(ctx, 0), "timer"); }
   double timer_stop_ms() {
     double ms = 0;

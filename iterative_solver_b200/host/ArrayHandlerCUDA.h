@@ -58,13 +58,114 @@ public:
   }
   value_type dot(const AL& x, const AR& y) override {
     this->m_counter->dot++;
-    const double d = x.dot(y);
+    double d;
+    if (!primed(x, y, d))
+      d = x.dot(y);
     if (m_observer)
       m_observer('d', 1, 1, &d);
     return d;
   }
 
+  // ---- extensions used by the fused driver path (FusedDavidson.h); not part of the reference's contract ----
+
+  //! <x_i, x_i> of every vector in one launch
+  std::vector<double> self_dots(const CVecRef<AL>& xx) {
+    std::vector<double> d(xx.size());
+    if (xx.empty())
+      return d;
+    const auto G = gemm_inner(xx, xx);
+    for (size_t i = 0; i < xx.size(); ++i)
+      d[i] = G(i, i);
+    return d;
+  }
+  //! computes <x_i, x_i> for all i now and answers the caller's coming dot(x_i, x_i) calls from the stored values, as
+  //! long as nothing has been written in between (the context's write epoch stands still)
+  void prime_self_dots(const CVecRef<AL>& xx) {
+    m_primed.clear();
+    if (xx.empty())
+      return;
+    const auto d = self_dots(xx);
+    m_primed_epoch = itsolv_ctx_write_epoch(xx[0].get().context());
+    for (size_t i = 0; i < xx.size(); ++i)
+      m_primed.push_back({xx[i].get().data(), xx[i].get().data(), d[i]});
+  }
+  //! x_k *= alpha[k], one launch
+  void scal_batch(const std::vector<double>& alpha, const VecRef<AL>& xx) {
+    if (xx.empty())
+      return;
+    this->m_counter->scal += int(xx.size());
+    std::vector<double*> px(xx.size());
+    const AL& first = xx[0].get();
+    for (size_t i = 0; i < xx.size(); ++i) {
+      first.require_compatible(xx[i].get(), "scal_batch");
+      px[i] = xx[i].get().data();
+    }
+    check(itsolv_scal_batch_f64(first.context(), alpha.data(), px.data(), int(px.size()), first.local_size()),
+          "ArrayHandlerCUDA::scal_batch");
+  }
+  //! y_k += alpha[k] * x_k for independent pairs, one launch
+  void axpy_batch(const std::vector<double>& alpha, const CVecRef<AR>& xx, const VecRef<AL>& yy) {
+    if (yy.empty())
+      return;
+    this->m_counter->axpy += int(yy.size());
+    std::vector<const double*> px(yy.size());
+    std::vector<double*> py(yy.size());
+    const AL& first = yy[0].get();
+    for (size_t i = 0; i < yy.size(); ++i) {
+      first.require_compatible(xx[i].get(), "axpy_batch");
+      first.require_compatible(yy[i].get(), "axpy_batch");
+      px[i] = xx[i].get().data();
+      py[i] = yy[i].get().data();
+    }
+    check(itsolv_axpy_batch_f64(first.context(), alpha.data(), px.data(), py.data(), int(py.size()), first.local_size()),
+          "ArrayHandlerCUDA::axpy_batch");
+  }
+  //! ri *= inv_norm; rj[k] -= ov[k] * ri  (one step of the R-R modified Gram-Schmidt), one launch
+  void mgs_step(double inv_norm, AL& ri, const std::vector<double>& ov, const VecRef<AL>& rj) {
+    this->m_counter->scal++;
+    this->m_counter->axpy += int(rj.size());
+    std::vector<double*> pj(rj.size());
+    for (size_t j = 0; j < rj.size(); ++j) {
+      ri.require_compatible(rj[j].get(), "mgs_step");
+      pj[j] = rj[j].get().data();
+    }
+    check(itsolv_mgs_step_f64(ri.context(), inv_norm, ri.data(), ov.data(), pj.data(), int(pj.size()), ri.local_size()),
+          "ArrayHandlerCUDA::mgs_step");
+  }
+  //! yy[j] = sum_i alphas(i,j) xx[i]: the targets are written, not read (fill + gemm_outer of the reference in one pass)
+  void gemm_outer_assign(const Matrix<value_type>& alphas, const CVecRef<AR>& xx, const VecRef<AL>& yy) {
+    expand(alphas, xx, yy, true);
+  }
+
   void gemm_outer(const Matrix<value_type> alphas, const CVecRef<AR>& xx, const VecRef<AL>& yy) override {
+    expand(alphas, xx, yy, false);
+  }
+
+protected:
+  struct Primed {
+    const double *x, *y;
+    double value;
+  };
+  std::vector<Primed> m_primed;
+  unsigned long long m_primed_epoch = 0;
+
+  bool primed(const AL& x, const AR& y, double& value) {
+    if (m_primed.empty())
+      return false;
+    if (itsolv_ctx_write_epoch(x.context()) != m_primed_epoch) {
+      m_primed.clear();
+      return false;
+    }
+    const AL& cx = x;
+    for (const auto& e : m_primed)
+      if ((e.x == cx.data() && e.y == y.data()) || (e.x == y.data() && e.y == cx.data())) {
+        value = e.value;
+        return true;
+      }
+    return false;
+  }
+
+  void expand(const Matrix<value_type>& alphas, const CVecRef<AR>& xx, const VecRef<AL>& yy, bool assign) {
     this->m_counter->gemm_outer++;
     // Shape rules of the reference's loops (array/util/gemm.h:186-203, 258-265): one x per row of alphas, one y per
     // column; the drivers may pass MORE y vectors than columns (construct_solution hands all R buffers with
@@ -74,8 +175,14 @@ public:
     if (alphas.cols() > yy.size())
       throw std::out_of_range("gemm_outer: dimensions of yy and alphas are different.");
     const size_t nx = alphas.rows(), ny = alphas.cols();
-    if (nx == 0 || ny == 0)
+    if (ny == 0)
       return;
+    if (nx == 0) {
+      if (assign)
+        for (size_t j = 0; j < ny; ++j)
+          yy[j].get().fill(0.0);
+      return;
+    }
     std::vector<const double*> px(nx);
     std::vector<double*> py(ny);
     const AL& first = yy[0].get();
@@ -88,9 +195,11 @@ public:
       py[j] = yy[j].get().data();
     }
     check(itsolv_gemm_outer_f64(first.context(), alphas.data().data(), int(nx), int(ny), px.data(), py.data(),
-                                first.local_size(), 0),
+                                first.local_size(), assign ? 1 : 0),
           "ArrayHandlerCUDA::gemm_outer");
   }
+
+public:
 
   Matrix<value_type> gemm_inner(const CVecRef<AL>& xx, const CVecRef<AR>& yy) override {
     this->m_counter->gemm_inner++;

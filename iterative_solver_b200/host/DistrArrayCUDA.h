@@ -88,7 +88,12 @@ public:
   size_t local_size() const { return m_local; }
   size_t local_start() const { return m_start; }
   std::pair<size_t, size_t> local_range() const { return {m_start, m_start + m_local}; }
-  double* data() { return m_data; }
+  //! mutable access: assume the caller writes (invalidates results cached by the handlers)
+  double* data() {
+    if (m_ctx)
+      itsolv_ctx_note_write(m_ctx);
+    return m_data;
+  }
   const double* data() const { return m_data; }
   itsolv_ctx* context() const { return m_ctx; }
 

@@ -1,0 +1,354 @@
+// Fused driver path: the same Davidson algorithm, the same public solver API
+// (IterativeSolver::solve / add_vector / solution / end_iteration), with the O(n) work of one iteration batched into a
+// handful of passes instead of the reference's ~60 single-vector calls:
+//
+//   reference call pattern (w = working set, q = |Q|)                      fused here
+//   ---------------------------------------------------------------------------------------------------------------
+//   update_qspace_data: w(w+1)/2 dots + 3..6 gemm_inner                    ONE Gram launch [2w x (2w+2q+2d+rhs)]
+//     (itsolv/subspace/XSpace.h:31-83)
+//   solution: 2r fill + 4 gemm_outer + r axpy + r dots                     2 gemm_outer (targets assigned, not read),
+//     (itsolv/IterativeSolverTemplate.h:34-65,191-215, :96-102)            1 batched axpy, 1 Gram launch for the r norms
+//   propose_rspace: 2 x (w dots + w scal), w(w+1)/2 dots + 3 gemm_inner,   2 x (1 Gram + 1 batched scal), ONE Gram launch
+//     (q+d) x {gemm_inner[w x 1] + gemm_outer[1 x w]},                     [w x (w+q+d)], ONE gemm_outer [(q+d) x w] with
+//     w x (dot + scal) + w(w-1)/2 x (dot + axpy)                           coefficients from forward substitution,
+//     (itsolv/propose_rspace.h:17-28, 272-300, 422-466, 554-624)           w x (1 Gram row + 1 fused scal/axpy step)
+//
+// The arithmetic is the reference's: the same inner products (summed in the kernels' order), the same element-wise updates
+// (bit-identical given the coefficients). The one algebraic rearrangement is the projection against P+Q+D: the reference
+// recomputes <r, x_i> after every single projection; here the overlaps G0 = <r, x_i> of the unprojected r are taken in one
+// pass and the sequential coefficients follow from the stored overlap matrix S of the subspace by forward substitution,
+//   c_i = -(G0_i + sum_{l<i} c_l S_li) / |S_ii|,
+// which is the identical recurrence in exact arithmetic. Everything that decides (thresholds, SVD redundancy test,
+// Q-space limiting, D-space construction and resetting, working-set bookkeeping) runs the reference's own code.
+// Parity of iteration counts and eigenvalues with the unfused path is asserted in tests/test_fused_gpu.py.
+#ifndef ITSOLV_B200_HOST_FUSEDDAVIDSON_H
+#define ITSOLV_B200_HOST_FUSEDDAVIDSON_H
+#include <cmath>
+#include <map>
+#include <memory>
+#include <vector>
+
+#include <molpro/linalg/itsolv/LinearEigensystemDavidson.h>
+
+#include "ArrayHandlerCUDA.h"
+
+namespace itsolv_b200 {
+namespace its = molpro::linalg::itsolv;
+
+//! X space whose new equation-data blocks come from a single Gram launch
+class XSpaceFused : public its::subspace::XSpace<DistrArrayCUDA, DistrArrayCUDA, std::map<size_t, double>> {
+public:
+  using R = DistrArrayCUDA;
+  using P = std::map<size_t, double>;
+  using Base = its::subspace::XSpace<R, R, P>;
+  using Base::Base;
+
+  void update_qspace(const CVecRef<R>& params, const CVecRef<R>& actions) override {
+    using its::subspace::EqnData;
+    auto& handlers = *this->m_handlers;
+    const auto dims = this->m_dim;
+    const size_t w = params.size(), nP = dims.nP, nQ = dims.nQ, nD = dims.nD, nRHS = this->m_rhs.size();
+    const auto qparams = this->cparamsq(), qactions = this->cactionsq(), dparams = this->cparamsd(),
+               dactions = this->cactionsd();
+    // rows: new parameters, then their actions; columns: everything they are contracted with
+    CVecRef<R> rows(params.begin(), params.end());
+    rows.insert(rows.end(), actions.begin(), actions.end());
+    CVecRef<R> cols(params.begin(), params.end());
+    const size_t cQ = cols.size();
+    cols.insert(cols.end(), qparams.begin(), qparams.end());
+    const size_t cD = cols.size();
+    cols.insert(cols.end(), dparams.begin(), dparams.end());
+    const size_t cA = cols.size();
+    cols.insert(cols.end(), actions.begin(), actions.end());
+    const size_t cQA = cols.size();
+    cols.insert(cols.end(), qactions.begin(), qactions.end());
+    const size_t cDA = cols.size();
+    cols.insert(cols.end(), dactions.begin(), dactions.end());
+    const size_t cRHS = cols.size();
+    for (const auto& r : this->m_rhs)
+      cols.emplace_back(std::cref(r));
+    const auto G = handlers.rq().gemm_inner(rows, cols);
+    const bool ada = this->m_action_dot_action;
+    const size_t hrow = ada ? w : 0; // H blocks contract actions (DIIS) or parameters with the stored actions
+
+    its::subspace::xspace::NewData nd(w, dims.nX, nRHS);
+    auto &Sqq = nd.qq[EqnData::S], &Hqq = nd.qq[EqnData::H], &Sqx = nd.qx[EqnData::S], &Hqx = nd.qx[EqnData::H],
+         &Sxq = nd.xq[EqnData::S], &Hxq = nd.xq[EqnData::H];
+    for (size_t i = 0; i < w; ++i) {
+      for (size_t j = 0; j <= i; ++j) { // symmetric blocks are mirrored from the lower triangle as util::overlap does
+        Sqq(i, j) = Sqq(j, i) = G(i, j);
+        if (ada)
+          Hqq(i, j) = Hqq(j, i) = G(w + i, cA + j);
+      }
+      if (!ada)
+        for (size_t j = 0; j < w; ++j)
+          Hqq(i, j) = G(i, cA + j);
+      for (size_t j = 0; j < nQ; ++j) {
+        Sqx(i, dims.oQ + j) = G(i, cQ + j);
+        Hqx(i, dims.oQ + j) = G(hrow + i, cQA + j);
+      }
+      for (size_t j = 0; j < nD; ++j) {
+        Sqx(i, dims.oD + j) = G(i, cD + j);
+        Hqx(i, dims.oD + j) = G(hrow + i, cDA + j);
+      }
+      for (size_t j = 0; j < nRHS; ++j)
+        nd.qq[EqnData::rhs](i, j) = G(i, cRHS + j);
+    }
+    if (nP > 0) { // sparse P vectors: one gather launch for parameters and actions together
+      const auto GP = handlers.rp().gemm_inner(rows, this->cparamsp());
+      for (size_t i = 0; i < w; ++i)
+        for (size_t j = 0; j < nP; ++j) {
+          Sqx(i, dims.oP + j) = GP(i, j);
+          if (this->m_hermitian)
+            Hxq(dims.oP + j, i) = Hqx(i, dims.oP + j) = GP(w + i, j);
+        }
+    }
+    for (size_t i = 0; i < w; ++i) {
+      for (size_t j = 0; j < nQ; ++j)
+        Hxq(dims.oQ + j, i) = this->m_hermitian ? Hqx(i, dims.oQ + j) : G(w + i, cQ + j);
+      for (size_t j = 0; j < nD; ++j)
+        Hxq(dims.oD + j, i) = this->m_hermitian ? Hqx(i, dims.oD + j) : G(w + i, cD + j);
+      for (size_t j = 0; j < dims.nX; ++j)
+        Sxq(j, i) = Sqx(i, j);
+    }
+    this->qspace.update(params, actions, nd.qq, nd.qx, nd.xq, dims, this->data);
+    this->update_dimensions();
+  }
+};
+
+class LinearEigensystemDavidsonFused
+    : public its::LinearEigensystemDavidson<DistrArrayCUDA, DistrArrayCUDA, std::map<size_t, double>> {
+public:
+  using R = DistrArrayCUDA;
+  using P = std::map<size_t, double>;
+  using Base = its::LinearEigensystemDavidson<R, R, P>;
+  using Base::end_iteration;
+  using Base::solution;
+
+  explicit LinearEigensystemDavidsonFused(const std::shared_ptr<HandlersCUDA>& handlers,
+                                          const std::shared_ptr<its::Logger>& logger_ = std::make_shared<its::Logger>())
+      : Base(handlers, logger_) {
+    m_dense = dynamic_cast<ArrayHandlerCUDA*>(&handlers->rr());
+    if (!m_dense || dynamic_cast<ArrayHandlerCUDA*>(&handlers->rq()) != m_dense)
+      throw std::logic_error("LinearEigensystemDavidsonFused needs the handlers of make_handlers()");
+    this->m_xspace = std::make_shared<XSpaceFused>(handlers, logger_);
+    this->set_hermiticity(this->get_hermiticity());
+  }
+
+  //! parameters and residuals of the requested roots (reference IterativeSolverTemplate.h:191-215), batched
+  void solution(const std::vector<int>& roots, const VecRef<R>& parameters, const VecRef<R>& residual) override {
+    this->check_consistent_number_of_roots_and_solutions(roots, parameters.size());
+    if (roots.empty())
+      return;
+    auto& xs = *this->m_xspace;
+    const auto dims = xs.dimensions();
+    const auto& sol = this->m_subspace_solver->solutions();
+    const size_t r = roots.size(), nP = dims.nP, nQ = dims.nQ, nD = dims.nD;
+    const VecRef<R> par(parameters.begin(), parameters.begin() + r), res(residual.begin(), residual.begin() + r);
+    // coefficients of the Q and D vectors stacked: one expansion instead of two
+    Matrix<double> cqd({nQ + nD, r}), cp({nP, r});
+    for (size_t i = 0; i < r; ++i) {
+      for (size_t j = 0; j < nP; ++j)
+        cp(j, i) = sol(roots[i], dims.oP + j);
+      for (size_t j = 0; j < nQ; ++j)
+        cqd(j, i) = sol(roots[i], dims.oQ + j);
+      for (size_t j = 0; j < nD; ++j)
+        cqd(nQ + j, i) = sol(roots[i], dims.oD + j);
+    }
+    auto stack = [](CVecRef<R> a, const CVecRef<R>& b) {
+      a.insert(a.end(), b.begin(), b.end());
+      return a;
+    };
+    const auto xpar = stack(xs.cparamsq(), xs.cparamsd()), xact = stack(xs.cactionsq(), xs.cactionsd());
+    if (nP > 0) { // the P part comes first, as in the reference: zero, scatter-add, then the dense part accumulates
+      for (auto& p : par)
+        this->m_handlers->rr().fill(0, p);
+      this->m_handlers->rp().gemm_outer(cp, xs.cparamsp(), par);
+      m_dense->gemm_outer(cqd, xpar, par);
+    } else {
+      m_dense->gemm_outer_assign(cqd, xpar, par);
+    }
+    m_dense->gemm_outer_assign(cqd, xact, res);
+    if (this->m_normalise_solution)
+      its::detail::normalise(r, parameters, residual, this->m_handlers->rr(), *this->m_logger);
+    if (this->m_apply_p) {
+      auto pvectors = its::detail::construct_vectorP(roots, sol, dims.oP, dims.nP);
+      this->m_apply_p(pvectors, xs.cparamsp(), residual);
+    }
+    construct_residual(roots, its::cwrap(parameters), residual);
+    // the caller asks for <res_i, res_i> of every root next (update_errors, IterativeSolverTemplate.h:96-102):
+    // all of them in one launch, answered from the handler's primed results
+    m_dense->prime_self_dots(its::cwrap(res));
+    its::read_handler_counts(this->m_stats, this->m_handlers);
+  }
+
+  size_t end_iteration(const VecRef<R>& parameters, const VecRef<R>& action) override {
+    if (this->m_dspace_resetter.do_reset(this->m_stats->iterations, this->m_xspace->dimensions())) {
+      this->m_resetting_in_progress = true;
+      this->m_working_set = this->m_dspace_resetter.run(
+          parameters, *this->m_xspace, this->m_subspace_solver->solutions(), this->propose_rspace_norm_thresh,
+          this->propose_rspace_svd_thresh, *this->m_handlers, *this->m_logger);
+    } else {
+      this->m_resetting_in_progress = false;
+      this->m_working_set = propose_rspace_fused(parameters, action);
+    }
+    this->m_stats->iterations++;
+    its::read_handler_counts(this->m_stats, this->m_handlers);
+    this->m_end_iteration_needed = false;
+    return this->working_set().size();
+  }
+
+protected:
+  //! res_i -= lambda_i * x_i for all roots in one pass (reference LinearEigensystemDavidson.h:186-192)
+  void construct_residual(const std::vector<int>& roots, const CVecRef<R>& params, const VecRef<R>& actions) override {
+    const auto eigvals = this->eigenvalues();
+    std::vector<double> alpha(roots.size());
+    for (size_t i = 0; i < roots.size(); ++i)
+      alpha[i] = -eigvals.at(roots[i]);
+    m_dense->axpy_batch(alpha, CVecRef<R>(params.begin(), params.begin() + roots.size()),
+                        VecRef<R>(actions.begin(), actions.begin() + roots.size()));
+  }
+
+  //! ||p|| -> 1 for every vector of the set: one Gram launch for the norms, one launch for the scaling
+  void normalise_set(const VecRef<R>& params, double thresh = 1.0e-14) {
+    if (params.empty())
+      return;
+    const auto d = m_dense->self_dots(its::cwrap(params));
+    std::vector<double> alpha(params.size(), 1.0);
+    for (size_t i = 0; i < params.size(); ++i) {
+      const double norm = std::sqrt(std::abs(d[i]));
+      if (norm > thresh)
+        alpha[i] = 1. / norm;
+      else
+        this->m_logger->msg("parameter's length is too small for normalisation, dot = " + its::Logger::scientific(norm),
+                            its::Logger::Warn);
+    }
+    m_dense->scal_batch(alpha, params);
+  }
+
+  /*!
+   * New R vectors from the preconditioned residuals (reference itsolv/propose_rspace.h:554-624). The decisions are the
+   * reference's own functions; the vector work is batched as described at the top of this file.
+   */
+  std::vector<int> propose_rspace_fused(const VecRef<R>& parameters, const VecRef<R>& residuals) {
+    namespace det = its::detail;
+    using its::subspace::EqnData;
+    auto& xspace = *this->m_xspace;
+    auto& handlers = *this->m_handlers;
+    auto& logger = *this->m_logger;
+    auto& subspace_solver = *this->m_subspace_solver;
+    auto solutions = subspace_solver.solutions();
+    // Q-space limit -> D space: rare, left to the reference's routines (they go through the same handlers)
+    auto q_delete = det::limit_qspace_size(xspace.dimensions(), this->m_max_size_qspace, solutions, logger);
+    if (!q_delete.empty()) {
+      auto [dparams, dactions] = det::construct_dspace(solutions, xspace, q_delete, this->propose_rspace_norm_thresh,
+                                                       this->propose_rspace_svd_thresh, handlers.qq(), logger);
+      std::sort(begin(q_delete), end(q_delete), std::greater<int>());
+      for (auto iq : q_delete)
+        xspace.eraseq(iq);
+      auto wdparams = its::wrap(dparams);
+      auto wdactions = its::wrap(dactions);
+      xspace.update_dspace(wdparams, wdactions);
+      subspace_solver.solve(xspace, solutions.rows());
+    }
+    auto wresidual = its::wrap(residuals.begin(), residuals.begin() + this->working_set().size());
+    normalise_set(wresidual);
+
+    const auto dims = xspace.dimensions();
+    const size_t nP = dims.nP, nQ = dims.nQ, nD = dims.nD, nX = dims.nX;
+    size_t nN = wresidual.size();
+    const size_t nN0 = nN; // columns of G keep their positions when vectors are dropped below
+    const auto pparams = xspace.cparamsp();
+    const auto qparams = xspace.cparamsq(), dparams = xspace.cparamsd();
+    CVecRef<R> xdense(qparams.begin(), qparams.end());
+    xdense.insert(xdense.end(), dparams.begin(), dparams.end());
+    // overlap of the new vectors with themselves and with Q, D in one launch; with P through the sparse handler
+    CVecRef<R> cols = its::cwrap(wresidual);
+    cols.insert(cols.end(), xdense.begin(), xdense.end());
+    const auto G = m_dense->gemm_inner(its::cwrap(wresidual), cols); // nN x (nN + nQ + nD)
+    Matrix<double> GP({nN, nP});
+    if (nP > 0)
+      GP = handlers.rp().gemm_inner(its::cwrap(wresidual), pparams);
+    const auto& S = xspace.data.at(EqnData::S);
+    auto ov = S;
+    ov.resize({nX + nN, nX + nN});
+    auto g0 = [&, nN0](size_t i, size_t x) { // <r_i, x> for x running over P, Q, D in subspace order
+      if (x < dims.oP + nP && x >= dims.oP)
+        return GP(i, x - dims.oP);
+      return x >= dims.oD ? G(i, nN0 + nQ + (x - dims.oD)) : G(i, nN0 + (x - dims.oQ));
+    };
+    for (size_t i = 0; i < nN; ++i) {
+      for (size_t j = 0; j <= i; ++j)
+        ov(nX + i, nX + j) = ov(nX + j, nX + i) = G(i, j);
+      for (size_t x = 0; x < nX; ++x)
+        ov(nX + i, x) = ov(x, nX + i) = g0(i, x);
+    }
+    auto redundant = det::redundant_parameters(ov, nX, nN, this->propose_rspace_svd_thresh, logger);
+    // keep the rows of the overlap block that belong to the surviving vectors
+    std::vector<size_t> kept(nN);
+    for (size_t i = 0; i < nN; ++i)
+      kept[i] = i;
+    {
+      auto sorted = redundant;
+      std::sort(sorted.begin(), sorted.end(), std::greater<int>());
+      for (auto i : sorted)
+        kept.erase(kept.begin() + i);
+    }
+    its::util::delete_parameters(redundant, wresidual);
+    nN = wresidual.size();
+
+    // projection against P, Q, D: sequential coefficients by forward substitution, applied in one expansion
+    if (nN > 0 && nX > 0) {
+      Matrix<double> c({nX, nN});
+      for (size_t j = 0; j < nN; ++j)
+        for (size_t i = 0; i < nX; ++i) {
+          double t = g0(kept[j], i);
+          for (size_t l = 0; l < i; ++l)
+            t += c(l, j) * S(l, i);
+          c(i, j) = -t / std::abs(S(i, i));
+        }
+      if (nP > 0) {
+        Matrix<double> cpm({nP, nN});
+        for (size_t i = 0; i < nP; ++i)
+          for (size_t j = 0; j < nN; ++j)
+            cpm(i, j) = c(dims.oP + i, j);
+        handlers.rp().gemm_outer(cpm, pparams, wresidual);
+      }
+      if (nQ + nD > 0) {
+        Matrix<double> cd({nQ + nD, nN});
+        for (size_t j = 0; j < nN; ++j) {
+          for (size_t i = 0; i < nQ; ++i)
+            cd(i, j) = c(dims.oQ + i, j);
+          for (size_t i = 0; i < nD; ++i)
+            cd(nQ + i, j) = c(dims.oD + i, j);
+        }
+        m_dense->gemm_outer(cd, xdense, wresidual);
+      }
+    }
+    // R-R modified Gram-Schmidt: per pivot one Gram row (norm and overlaps with the later vectors) and one fused update
+    std::vector<int> null_params;
+    for (size_t i = 0; i < nN; ++i) {
+      CVecRef<R> later(wresidual.begin() + i, wresidual.end());
+      const auto row = m_dense->gemm_inner(CVecRef<R>{std::cref(wresidual[i].get())}, later); // 1 x (nN - i)
+      const double norm = std::sqrt(std::abs(row(0, 0)));
+      if (norm > this->propose_rspace_norm_thresh) {
+        std::vector<double> o(nN - i - 1);
+        for (size_t j = 0; j < o.size(); ++j)
+          o[j] = row(0, j + 1) / norm; // <r_i / |r_i|, r_j>
+        m_dense->mgs_step(1. / norm, wresidual[i].get(), o, VecRef<R>(wresidual.begin() + i + 1, wresidual.end()));
+      } else {
+        null_params.push_back(int(i));
+      }
+    }
+    its::util::delete_parameters(null_params, wresidual);
+    normalise_set(wresidual);
+    for (size_t i = 0; i < wresidual.size(); ++i)
+      handlers.rr().copy(parameters.at(i), wresidual.at(i));
+    return det::get_new_working_set(this->working_set(), its::cwrap(residuals), its::cwrap(wresidual));
+  }
+
+  ArrayHandlerCUDA* m_dense = nullptr;
+};
+
+} // namespace itsolv_b200
+#endif

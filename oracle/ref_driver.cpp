@@ -202,6 +202,9 @@ struct HostBackend {
   void synchronize() {}
   void timer_start() {}
   double timer_stop_ms() { return 0; }
+  auto make_davidson(const std::shared_ptr<its::ArrayHandlers<Vec, Vec, PMap>>& handlers, const itsolv_solve_spec&) {
+    return std::make_unique<its::LinearEigensystemDavidson<Vec, Vec, PMap>>(handlers);
+  }
 };
 
 Vec to_vec(const double* p, size_t n) { return Vec(p, p + n); }
