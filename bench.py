@@ -156,8 +156,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="rows per GPU")
     ap.add_argument("--roots", type=int, default=NROOTS)
+    ap.add_argument("--path", default="fused", choices=["fused", "unfused"],
+                    help="fused: LinearEigensystemDavidsonFused (batched passes, same algorithm and API); "
+                         "unfused: the reference's LinearEigensystemDavidson class on the CUDA handlers, call for call")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-path", action="store_true")
     ap.add_argument("--min-warmup", type=int, default=3, help="profiling runs only: allow fewer than 3 warm-up steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -182,8 +186,9 @@ def main():
     D.attach_communicator(ctx)
 
     n_global = args.n * world
+    fused = 1 if args.path == "fused" else 0
     spec = H.make_spec(n_global, kind=N.KIND_DAVIDSON, nroots=args.roots, hermitian=1, half_bandwidth=HALF_BANDWIDTH,
-                       eps=EPS, explicit_csr=1)
+                       eps=EPS, explicit_csr=1, fused=fused)
     borders = pkg.distribution(n_global, world)
     lo, hi = int(borders[rank]), int(borders[rank + 1])
 
@@ -217,6 +222,25 @@ def main():
         torch.cuda.synchronize()
     ctx.set_profiling(False)
     converged, eig = res.converged, [res.eigenvalues[i] for i in range(args.roots)]
+    # the other driver path on the same operator, for the record (same timing protocol, fewer steps)
+    other = None
+    if not args.no_other_path:
+        spec_o = H.make_spec(n_global, kind=N.KIND_DAVIDSON, nroots=args.roots, hermitian=1,
+                             half_bandwidth=HALF_BANDWIDTH, eps=EPS, explicit_csr=1, fused=1 - fused)
+        for _ in range(2):
+            problem.solve(spec_o)
+        lib.itsolv_comm_barrier(ctx.handle)
+        o_steps, o_iter, o_launch = max(1, min(args.steps, 3)), 0, 0
+        ctx.timer_start()
+        for _ in range(o_steps):
+            r_o = problem.solve(spec_o)
+            o_iter += r_o.iterations
+            o_launch += r_o.kernel_launches
+        o_ms = float(ctx.allreduce_host(np.array([ctx.timer_stop()]), op_max=True)[0])
+        other = {"path": "unfused" if fused else "fused", "value": world * o_iter / (o_ms * 1e-3), "unit": UNIT,
+                 "ms_per_step": o_ms / o_steps, "gpu_launches_per_step": o_launch / o_steps,
+                 "iterations_per_solve": o_iter / o_steps,
+                 "eigenvalues_agree_to": max(abs(r_o.eigenvalues[i] / eig[i] - 1) for i in range(args.roots))}
     ms_max = float(ctx.allreduce_host(np.array([ms]), op_max=True)[0])
     sums = ctx.allreduce_host(np.array([agg["bytes"], agg["bgi"], agg["bgo"], agg["bb1"], float(launches)]))
     gi_launches = float(agg.get("ngi", 0)) * world
@@ -232,7 +256,7 @@ def main():
         pinned = [torch.from_numpy(a).pin_memory() for a in (row_ptr, col, val, diag)]
         row_ptr, col, val, diag = [t.numpy() for t in pinned]
         spec_e = H.make_spec(n_global, kind=N.KIND_DAVIDSON, nroots=args.roots, hermitian=1,
-                             half_bandwidth=HALF_BANDWIDTH, eps=EPS)
+                             half_bandwidth=HALF_BANDWIDTH, eps=EPS, fused=fused)
         sol = torch.empty((args.roots, hi - lo), dtype=torch.float64).pin_memory()
         sol_np = sol.numpy()
         e_steps = max(1, min(args.steps, 3))
@@ -288,6 +312,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.n, args.roots), "n_per_gpu": args.n, "n_global": n_global,
                        "nroots": args.roots, "sharding": f"rows/{world}" if world > 1 else "none",
+                       "driver_path": ("fused (LinearEigensystemDavidsonFused: the reference's algorithm and API, O(n) work "
+                                       "batched)" if fused else "unfused (the reference's LinearEigensystemDavidson class)"),
                        "l2": "inputs larger than L2 (each vector 80 MB, ~40 live vectors)",
                        "value_unit_note": "iterations/s x number of 1e7-row shards (weak scaling)"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(sums[4]),
@@ -303,6 +329,7 @@ def main():
                                 "streaming_gbs": agg_gbs(sums[3] / world, maxs[3]),
                                 "device_seconds_per_step": maxs[0] / args.steps},
             "iterations_per_solve": iterations / args.steps, "converged": int(converged), "eigenvalues": eig,
+            "driver_path": args.path, "other_driver_path": other,
         }
         print(json.dumps(line), flush=True)
     ctx.close()
