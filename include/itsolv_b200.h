@@ -162,6 +162,11 @@ int itsolv_banded_apply_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offse
 int itsolv_csr_apply_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offset, size_t n, int b, const int64_t* row_ptr,
                          const int32_t* col, const double* val, const double* x, const double* x_lo, const double* x_hi,
                          double* y);
+/* the same for w vectors in one pass over the matrix (Problem::action receives the whole working set) */
+int itsolv_csr_apply_multi_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offset, size_t n, int b,
+                               const int64_t* row_ptr, const int32_t* col, const double* val, int w,
+                               const double* const* x, const double* const* x_lo, const double* const* x_hi,
+                               double* const* y);
 /* d[i] = row_offset+i+1 ; fills a vector with f(global index): kind 0 = diagonal, 1 = rhs_solution(k) (harness RHS generator) */
 int itsolv_banded_fill_f64(itsolv_ctx* ctx, int kind, int k, int64_t row_offset, size_t n, double* out);
 /* P-space part of the action (reference Problem::p_action, itsolv/IterativeSolver.h:160-171; example

@@ -118,6 +118,9 @@ KERNEL_API = {
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "itsolv_csr_apply_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "itsolv_csr_apply_multi_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_size_t, C.c_int, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_int, c_void_pp, c_void_pp, c_void_pp,
+                                             c_void_pp]),
     "itsolv_banded_fill_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_size_t, C.c_void_p]),
     "itsolv_banded_p_action_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_size_t, C.c_int, C.c_double, C.c_int,
                                              c_void_pp, C.c_int, c_int32_p, c_int64_p, c_double_p, c_double_p]),

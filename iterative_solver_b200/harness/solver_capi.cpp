@@ -73,6 +73,7 @@ public:
   size_t nloc = 0;
   mutable double seconds_action = 0, seconds_precond = 0;
   mutable R scratch;
+  mutable R halos; // halo rows of a whole working set (multi-vector SpMV)
   double* halo = nullptr; // [b lower halo | b upper halo]
   // stored operator (explicit CSR)
   int64_t* d_row_ptr = nullptr;
@@ -138,8 +139,31 @@ public:
 
   void action(const CVecRef<R>& parameters, const VecRef<R>& actions) const override {
     const double t0 = now_seconds();
-    for (size_t k = 0; k < parameters.size(); ++k)
-      apply(parameters[k].get(), actions[k].get());
+    const size_t w = parameters.size();
+    if (d_row_ptr && w > 1 && kind == ITSOLV_PROBLEM_BANDED) {
+      // stored CSR: all vectors of the working set in one pass over the matrix
+      if (nranks > 1 && b > 0 && halos.size() < 2 * size_t(b) * w) {
+        halos = R(2 * size_t(b) * w * size_t(nranks), ctx); // local length >= 2 b w
+      }
+      std::vector<const double*> x(w), lo(w, nullptr), hi(w, nullptr);
+      std::vector<double*> y(w);
+      for (size_t k = 0; k < w; ++k) {
+        x[k] = parameters[k].get().data();
+        y[k] = actions[k].get().data();
+        if (nranks > 1 && b > 0) {
+          double* h = halos.data() + 2 * size_t(b) * k;
+          check(itsolv_comm_halo_exchange(ctx, x[k], x[k] + (nloc - size_t(b)), h, h + b, size_t(b)), "halo exchange");
+          lo[k] = rank > 0 ? h : nullptr;
+          hi[k] = rank < nranks - 1 ? h + b : nullptr;
+        }
+      }
+      check(itsolv_csr_apply_multi_f64(ctx, n, start, nloc, b, d_row_ptr, d_col, d_val, int(w), x.data(), lo.data(),
+                                       hi.data(), y.data()),
+            "csr apply");
+    } else {
+      for (size_t k = 0; k < w; ++k)
+        apply(parameters[k].get(), actions[k].get());
+    }
     seconds_action += now_seconds() - t0;
   }
 
