@@ -128,6 +128,21 @@ int itsolv_gemm_outer_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, co
  * r_k[i] = r_k[i] / (diag[i] - shift[k] + 1e-15), w vectors in one pass over diag ---- */
 int itsolv_precondition_f64(itsolv_ctx* ctx, double* const* r, int w, const double* diag, const double* shift, size_t n);
 
+/* ---- fused solution -> residual -> error norm -> preconditioner step of one Davidson iteration
+ * (reference itsolv/IterativeSolverTemplate.h:34-65 construct_solution x 2, LinearEigensystemDavidson.h:186-192
+ * construct_residual, IterativeSolverTemplate.h:96-102 update_errors, IterativeSolver.h:46-55 precondition_default),
+ * one pass over the k subspace vectors q_i and their actions a_i, for m roots:
+ *   x_j = sum_i coef[i*m+j]*q[i];  r_j = sum_i coef[i*m+j]*a[i];  r_j = r_j + (-lambda[j])*x_j;  norm2[j] = <r_j, r_j>
+ *   out_r[j] = diag ? r_j / (diag - shift[j] + 1e-15) : r_j;       out_x[j] = x_j when out_x != NULL
+ * Every operation is rounded as in the separate calls (gemm_outer with beta_zero, axpy, precondition), so the vectors
+ * are bit-identical to that sequence; norm2 (HOST, m values, all-reduced over ranks) is taken BEFORE preconditioning,
+ * norm2_out[j] = <out_r[j], out_r[j]> of what was written (either may be NULL).
+ * 8n(2k + m + 1) bytes instead of 8n(2k + 8m + 1). ---- */
+int itsolv_davidson_residual_f64(itsolv_ctx* ctx, const double* coef, int k, int m, const double* const* q,
+                                 const double* const* a, const double* lambda, const double* diag, const double* shift,
+                                 double* const* out_x, double* const* out_r, size_t n, double* norm2,
+                                 double* norm2_out);
+
 /* ---- select / select_max_dot (reference array/util/select.h:28-55, ArrayHandler.h:212,222): the nsel entries that are
  * largest under the reference's (key, index) pair ordering, key = max ? v : -v (|v| when ignore_sign); for
  * select_max_dot pass y != NULL: v = |x[i]*y[i]|, max. Indices are global (global_offset + local). With a communicator

@@ -27,7 +27,7 @@ def _ptr(t) -> int:
 def _ptr_array(ts: Sequence) -> C.Array:
     arr = (C.c_void_p * max(1, len(ts)))()
     for i, t in enumerate(ts):
-        arr[i] = _ptr(t)
+        arr[i] = None if t is None else _ptr(t)
     return arr
 
 
@@ -185,6 +185,20 @@ class Context:
         self._check(self.lib.itsolv_precondition_f64(self.handle, _ptr_array(residuals), len(residuals), _ptr(diag),
                                                      _dbl(s), diag.numel()))
 
+    def davidson_residual(self, coef: np.ndarray, q: Sequence, a: Sequence, lam: Sequence[float], out_r: Sequence,
+                          diag=None, out_x: Sequence | None = None):
+        """Fused solution/residual/norm/preconditioner pass (itsolv_davidson_residual_f64); returns
+        (<r_j, r_j> before preconditioning, <out_r_j, out_r_j>)."""
+        k, m = len(q), len(out_r)
+        c = np.ascontiguousarray(coef, dtype=np.float64).reshape(k, m)
+        l = np.ascontiguousarray(lam, dtype=np.float64)
+        n2, n2w = np.zeros(m), np.zeros(m)
+        self._check(self.lib.itsolv_davidson_residual_f64(
+            self.handle, _dbl(c), k, m, _ptr_array(q), _ptr_array(a), _dbl(l), _ptr(diag) if diag is not None else None,
+            _dbl(l), _ptr_array(out_x) if out_x is not None else None, _ptr_array(out_r), out_r[0].numel(), _dbl(n2),
+            _dbl(n2w)))
+        return n2, n2w
+
     def select(self, x, nsel: int, max: bool = False, ignore_sign: bool = False, y=None, global_offset: int = 0):
         idx = np.zeros(nsel, dtype=np.int64)
         val = np.zeros(nsel)
@@ -198,6 +212,16 @@ class Context:
         self._check(self.lib.itsolv_banded_apply_f64(self.handle, n_global, row_offset, x.numel(), b, eps, _ptr(x),
                                                      _ptr(x_lo) if x_lo is not None else None,
                                                      _ptr(x_hi) if x_hi is not None else None, _ptr(y)))
+
+
+    def csr_apply_multi(self, row_ptr, col, val, xs: Sequence, ys: Sequence, n_global: int, row_offset: int, b: int,
+                        x_lo: Sequence | None = None, x_hi: Sequence | None = None):
+        """ys[k] = A xs[k] for the rows of this shard (itsolv_csr_apply_multi_f64); row_ptr int64, col int32, val
+        float64 device tensors; x_lo / x_hi: per vector the b halo rows below / above the shard (or None)."""
+        self._check(self.lib.itsolv_csr_apply_multi_f64(
+            self.handle, n_global, row_offset, ys[0].numel(), b, _ptr(row_ptr), _ptr(col), _ptr(val), len(xs),
+            _ptr_array(xs), _ptr_array(x_lo) if x_lo is not None else None,
+            _ptr_array(x_hi) if x_hi is not None else None, _ptr_array(ys)))
 
 
 def distribution(n: int, nranks: int) -> np.ndarray:

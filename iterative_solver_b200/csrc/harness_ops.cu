@@ -71,9 +71,130 @@ struct CsrMultiParams {
   int b, w;
 };
 
-//! y_k = A x_k for w vectors at once: the matrix (12 bytes per entry) is read once instead of w times
+//! y_k = A x_k for w vectors at once: the matrix (12 bytes per entry) is read once instead of w times.
+//! A CTA takes kCsrRows consecutive rows per trip. Their entries are contiguous in val/col and the x values they touch
+//! lie in a window of kCsrRows + 2b columns, so everything is staged into shared memory with asynchronous copies
+//! (cp.async / LDGSTS: all loads of a trip are in flight at once, no register staging) and each thread then walks its own
+//! row entirely out of shared memory. Columns outside the window (a matrix that is not banded) are read from global
+//! memory. Row sums keep the ascending-column order with the product rounded before the sum (bit-identical to the CPU twin).
+constexpr int kCsrRows = 256;
+constexpr int kCsrChunk = kCsrRows * 10; // entries staged at a time; rows with more entries take several rounds
+constexpr int kCsrMaxHalfBand = 128;     // widest x window staged in shared memory
+
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+static size_t csr_smem_bytes(int w, int b) {
+  const int win = kCsrRows + 2 * b;
+  return size_t(kCsrChunk) * 12 + size_t(w) * win * 8 + size_t(kCsrRows + 2) * 8;
+}
+
 template <int W>
-__global__ void __launch_bounds__(256) csr_apply_multi_kernel(const __grid_constant__ CsrMultiParams p) {
+__global__ void __launch_bounds__(kCsrRows) csr_apply_multi_kernel(const __grid_constant__ CsrMultiParams p) {
+  extern __shared__ __align__(16) unsigned char csr_smem[];
+  const int win = kCsrRows + 2 * p.b;
+  double* s_val = reinterpret_cast<double*>(csr_smem);
+  double* s_x = s_val + kCsrChunk;                                  // [W][win]
+  long long* s_rp = reinterpret_cast<long long*>(s_x + W * win);    // [kCsrRows + 1]
+  int* s_col = reinterpret_cast<int*>(s_rp + kCsrRows + 2);         // [kCsrChunk]
+  const int t = threadIdx.x;
+  const long long nblocks = (p.n + kCsrRows - 1) / kCsrRows;
+  long long blk = blockIdx.x;
+  long long e0 = 0, e1 = 0;
+  if (blk < nblocks) {
+    const long long r0 = blk * kCsrRows, r1 = r0 + kCsrRows < p.n ? r0 + kCsrRows : p.n;
+    e0 = p.row_ptr[r0];
+    e1 = p.row_ptr[r1];
+  }
+  for (; blk < nblocks; blk += gridDim.x) {
+    const long long r0 = blk * kCsrRows;
+    const int nrows = int(r0 + kCsrRows < p.n ? kCsrRows : p.n - r0);
+    // row pointers of the block and the x window [r0 - b, r0 + nrows + b) of every vector
+    cp_async8(&s_rp[t], &p.row_ptr[r0 + (t < nrows ? t : nrows)]);
+    if (t == 0)
+      cp_async8(&s_rp[nrows], &p.row_ptr[r0 + nrows]);
+    for (int i = t; i < nrows + 2 * p.b; i += kCsrRows) {
+      const long long l = r0 - p.b + i; // local row of the shard
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        if (k < p.w) {
+          if (l >= 0 && l < p.n)
+            cp_async8(&s_x[k * win + i], &p.x[k][l]);
+          else if (l < 0)
+            s_x[k * win + i] = p.x_lo[k] ? p.x_lo[k][p.b + l] : 0.0;
+          else
+            s_x[k * win + i] = p.x_hi[k] ? p.x_hi[k][l - p.n] : 0.0;
+        }
+      }
+    }
+    // the next block's entry range, requested now and used after this block's arithmetic
+    long long ne0 = 0, ne1 = 0;
+    const long long nblk = blk + gridDim.x;
+    if (nblk < nblocks) {
+      const long long q0 = nblk * kCsrRows, q1 = q0 + kCsrRows < p.n ? q0 + kCsrRows : p.n;
+      ne0 = p.row_ptr[q0];
+      ne1 = p.row_ptr[q1];
+    }
+    double acc[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k)
+      acc[k] = 0.0;
+    const long long wlo = p.off + r0 - p.b; // global column of s_x[.][0]
+    for (long long c0 = e0; c0 < e1 || c0 == e0; c0 += kCsrChunk) {
+      const long long c1 = c0 + kCsrChunk < e1 ? c0 + kCsrChunk : e1;
+      if (c0 > e0)
+        __syncthreads(); // the previous round's entries have been consumed
+      for (long long e = c0 + t; e < c1; e += kCsrRows) {
+        cp_async8(&s_val[e - c0], &p.val[e]);
+        cp_async4(&s_col[e - c0], &p.col[e]);
+      }
+      cp_async_wait_all();
+      __syncthreads();
+      if (t < nrows) {
+        const long long my0 = s_rp[t], my1 = s_rp[t + 1];
+        const long long lo = my0 > c0 ? my0 : c0, hi = my1 < c1 ? my1 : c1;
+        for (long long e = lo; e < hi; ++e) {
+          const double a = s_val[e - c0];
+          const long long c = s_col[e - c0];
+          const long long wi = c - wlo;
+          if (wi >= 0 && wi < nrows + 2 * p.b) {
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+              if (k < p.w)
+                acc[k] = __dadd_rn(acc[k], __dmul_rn(a, s_x[k * win + int(wi)]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+              if (k < p.w)
+                acc[k] = __dadd_rn(acc[k], __dmul_rn(a, x_at(c, p.off, p.n, p.b, p.x[k], p.x_lo[k], p.x_hi[k])));
+          }
+        }
+      }
+      if (c1 >= e1)
+        break;
+    }
+    if (t < nrows) {
+#pragma unroll
+      for (int k = 0; k < W; ++k)
+        if (k < p.w)
+          p.y[k][r0 + t] = acc[k];
+    }
+    __syncthreads(); // shared memory is refilled by the next trip
+    e0 = ne0;
+    e1 = ne1;
+  }
+}
+
+//! the same without shared-memory staging, for half bandwidths whose x window does not fit
+template <int W>
+__global__ void __launch_bounds__(256) csr_apply_multi_wide_kernel(const __grid_constant__ CsrMultiParams p) {
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < p.n; r += (long long)gridDim.x * blockDim.x) {
     double acc[W];
 #pragma unroll
@@ -172,6 +293,11 @@ int itsolv_banded_apply_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offse
   return 0;
 }
 
+int itsolv_csr_apply_multi_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offset, size_t n, int b,
+                               const int64_t* row_ptr, const int32_t* col, const double* val, int w,
+                               const double* const* x, const double* const* x_lo, const double* const* x_hi,
+                               double* const* y);
+
 int itsolv_csr_apply_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offset, size_t n, int b, const int64_t* row_ptr,
                          const int32_t* col, const double* val, const double* x, const double* x_lo, const double* x_hi,
                          double* y) {
@@ -181,12 +307,11 @@ int itsolv_csr_apply_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offset, 
   ITSOLV_REQUIRE(x != y, "itsolv_csr_apply_f64: in-place application is not supported");
   ITSOLV_REQUIRE((row_offset == 0 || x_lo) && (row_offset + int64_t(n) == n_global || x_hi),
                  "itsolv_csr_apply_f64: interior shard needs halo rows");
-  csr_apply_kernel<<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(row_offset, (long long)n, b,
-                                                               reinterpret_cast<const long long*>(row_ptr), col, val, x,
-                                                               x_lo, x_hi, y);
-  ITSOLV_CUDA(cudaGetLastError());
-  ctx->counters.launches += 1;
-  return 0;
+  const double* xs[1] = {x};
+  const double* los[1] = {x_lo};
+  const double* his[1] = {x_hi};
+  double* ys[1] = {y};
+  return itsolv_csr_apply_multi_f64(ctx, n_global, row_offset, n, b, row_ptr, col, val, 1, xs, los, his, ys);
 }
 
 int itsolv_csr_apply_multi_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_offset, size_t n, int b,
@@ -215,12 +340,28 @@ int itsolv_csr_apply_multi_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_of
     p.n = (long long)n;
     p.b = b;
     p.w = cnt;
-    if (cnt <= 2)
-      csr_apply_multi_kernel<2><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(p);
-    else if (cnt <= 4)
-      csr_apply_multi_kernel<4><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(p);
-    else
-      csr_apply_multi_kernel<8><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(p);
+    const int wt = cnt <= 1 ? 1 : (cnt <= 2 ? 2 : (cnt <= 4 ? 4 : 8));
+    if (b <= kCsrMaxHalfBand) {
+      using Kernel = void (*)(const CsrMultiParams);
+      const Kernel kernel = wt == 1   ? csr_apply_multi_kernel<1>
+                            : wt == 2 ? csr_apply_multi_kernel<2>
+                            : wt == 4 ? csr_apply_multi_kernel<4>
+                                      : csr_apply_multi_kernel<8>;
+      const size_t smem = csr_smem_bytes(wt, b);
+      if (ensure_dynamic_smem(ctx, reinterpret_cast<const void*>(kernel), smem))
+        return 1;
+      const int per_sm = std::max(1, std::min(8, int(size_t(ctx->max_smem_optin) / (smem + 1024))));
+      const int grid = int(std::max<size_t>(1, std::min<size_t>((n + kCsrRows - 1) / kCsrRows, size_t(ctx->num_sms) * per_sm)));
+      kernel<<<grid, kCsrRows, smem, ctx->stream>>>(p);
+    } else if (wt == 1) {
+      csr_apply_multi_wide_kernel<1><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(p);
+    } else if (wt == 2) {
+      csr_apply_multi_wide_kernel<2><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(p);
+    } else if (wt == 4) {
+      csr_apply_multi_wide_kernel<4><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(p);
+    } else {
+      csr_apply_multi_wide_kernel<8><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(p);
+    }
     ITSOLV_CUDA(cudaGetLastError());
     ctx->counters.launches += 1;
   }

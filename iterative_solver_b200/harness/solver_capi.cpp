@@ -39,7 +39,7 @@ inline double band_entry_host(int64_t i, int64_t j, double eps) {
  * The harness problem on the device. Operator kinds: generated banded, stored CSR (device arrays), or the reference's
  * dense ExampleProblem (single rank). Everything O(n) is a kernel launch on the context's stream.
  */
-class DeviceProblem : public its::Problem<R> {
+class DeviceProblem : public its::Problem<R>, public itsolv_b200::UsesDefaultDiagonalPreconditioner {
 public:
   DeviceProblem(itsolv_ctx* ctx, const itsolv_solve_spec& spec)
       : ctx(ctx), n(spec.n), b(spec.half_bandwidth), eps(spec.eps), kind(spec.problem), scratch(size_t(spec.n), ctx) {

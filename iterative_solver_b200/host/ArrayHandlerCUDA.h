@@ -41,6 +41,8 @@ public:
 
   AL copy(const AR& source) override {
     this->m_counter->copy++;
+    if (m_take_on_copy && !source.empty()) // see TakeOnCopy below
+      return const_cast<AR&>(source).take_contents();
     return AL{source};
   }
   void copy(AL& x, const AR& y) override {
@@ -132,6 +134,74 @@ public:
     check(itsolv_mgs_step_f64(ri.context(), inv_norm, ri.data(), ov.data(), pj.data(), int(pj.size()), ri.local_size()),
           "ArrayHandlerCUDA::mgs_step");
   }
+  /*!
+   * While an object of this type lives, copy(const AR&) -> AL hands over the source's allocation instead of copying it
+   * and leaves the source with unspecified contents. The fused driver opens it around QSpace::update
+   * (reference itsolv/subspace/QSpace.h:80-84), whose sources are R vectors that the solver overwrites next
+   * (IterativeSolverTemplate.h:532): 2w vector copies per iteration become pointer swaps.
+   */
+  struct TakeOnCopy {
+    explicit TakeOnCopy(ArrayHandlerCUDA& h) : handler(h), previous(h.m_take_on_copy) { h.m_take_on_copy = true; }
+    ~TakeOnCopy() { handler.m_take_on_copy = previous; }
+    TakeOnCopy(const TakeOnCopy&) = delete;
+    TakeOnCopy& operator=(const TakeOnCopy&) = delete;
+    ArrayHandlerCUDA& handler;
+    bool previous;
+  };
+
+  struct ResidualNorms {
+    std::vector<double> residual; //!< <r_j, r_j> before preconditioning
+    std::vector<double> written;  //!< <out_j, out_j> of the vectors that were written
+  };
+  /*!
+   * Solutions, residuals, their norms and the diagonal preconditioner of all roots in ONE pass over the subspace
+   * (itsolv_davidson_residual_f64): x_j = sum_i c(i,j) q_i, r_j = sum_i c(i,j) a_i - lambda_j x_j,
+   * out_r[j] = diag ? r_j / (diag - lambda_j + 1e-15) : r_j. `solutions` may be empty (x_j is then not stored).
+   */
+  ResidualNorms davidson_residual(const Matrix<value_type>& c, const CVecRef<AR>& q, const CVecRef<AR>& a,
+                                  const std::vector<double>& lambda, const AR* diag, const VecRef<AL>& solutions,
+                                  const VecRef<AL>& residuals) {
+    const size_t k = c.rows(), m = c.cols();
+    if (k > q.size() || k > a.size() || m > residuals.size() || m > lambda.size() ||
+        (!solutions.empty() && m > solutions.size()))
+      throw std::out_of_range("davidson_residual: dimensions of the coefficients and the vector sets are different.");
+    ResidualNorms norms{std::vector<double>(m), std::vector<double>(m)};
+    if (m == 0)
+      return norms;
+    if (k == 0)
+      throw std::out_of_range("davidson_residual: empty subspace");
+    this->m_counter->gemm_outer += 2;
+    this->m_counter->axpy += int(m);
+    this->m_counter->dot += int(m);
+    const AL& first = residuals[0].get();
+    std::vector<const double*> pq(k), pa(k);
+    std::vector<double*> px(solutions.empty() ? 0 : m), pr(m);
+    for (size_t i = 0; i < k; ++i) {
+      first.require_compatible(q[i].get(), "davidson_residual");
+      first.require_compatible(a[i].get(), "davidson_residual");
+      pq[i] = q[i].get().data();
+      pa[i] = a[i].get().data();
+    }
+    for (size_t j = 0; j < m; ++j) {
+      first.require_compatible(residuals[j].get(), "davidson_residual");
+      pr[j] = residuals[j].get().data();
+      if (!solutions.empty()) {
+        first.require_compatible(solutions[j].get(), "davidson_residual");
+        px[j] = solutions[j].get().data();
+      }
+    }
+    if (diag)
+      first.require_compatible(*diag, "davidson_residual");
+    check(itsolv_davidson_residual_f64(first.context(), c.data().data(), int(k), int(m), pq.data(), pa.data(),
+                                       lambda.data(), diag ? diag->data() : nullptr, lambda.data(),
+                                       solutions.empty() ? nullptr : px.data(), pr.data(), first.local_size(),
+                                       norms.residual.data(), norms.written.data()),
+          "ArrayHandlerCUDA::davidson_residual");
+    if (m_observer)
+      m_observer('g', 1, m, norms.residual.data());
+    return norms;
+  }
+
   //! yy[j] = sum_i alphas(i,j) xx[i]: the targets are written, not read (fill + gemm_outer of the reference in one pass)
   void gemm_outer_assign(const Matrix<value_type>& alphas, const CVecRef<AR>& xx, const VecRef<AL>& yy) {
     expand(alphas, xx, yy, true);
@@ -148,6 +218,7 @@ protected:
   };
   std::vector<Primed> m_primed;
   unsigned long long m_primed_epoch = 0;
+  bool m_take_on_copy = false;
 
   bool primed(const AL& x, const AR& y, double& value) {
     if (m_primed.empty())

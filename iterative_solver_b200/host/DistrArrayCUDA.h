@@ -139,6 +139,16 @@ public:
     std::swap(m_data, o.m_data);
   }
 
+  //! Hands this vector's contents to a new array without moving a byte: the new array owns the old allocation, this one
+  //! continues with a fresh allocation of the same shape whose contents are unspecified. For callers that are about to
+  //! overwrite this vector anyway (the fused driver path: R vectors entering the Q space).
+  DistrArrayCUDA take_contents() {
+    DistrArrayCUDA fresh(m_dimension, m_ctx);
+    std::swap(m_data, fresh.m_data);
+    itsolv_ctx_note_write(m_ctx);
+    return fresh;
+  }
+
   void require_compatible(const DistrArrayCUDA& o, const char* op) const {
     if (!m_data || !o.m_data || !compatible(o))
       throw std::runtime_error(std::string("DistrArrayCUDA::") + op + ": incompatible arrays");

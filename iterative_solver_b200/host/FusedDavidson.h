@@ -23,8 +23,12 @@
 // Parity of iteration counts and eigenvalues with the unfused path is asserted in tests/test_fused_gpu.py.
 #ifndef ITSOLV_B200_HOST_FUSEDDAVIDSON_H
 #define ITSOLV_B200_HOST_FUSEDDAVIDSON_H
+#include <algorithm>
 #include <cmath>
+#include <iostream>
 #include <map>
+#include <numeric>
+#include <stdexcept>
 #include <memory>
 #include <vector>
 
@@ -34,6 +38,16 @@
 
 namespace itsolv_b200 {
 namespace its = molpro::linalg::itsolv;
+
+/*!
+ * Tag for Problem classes whose precondition(residual, shift, diagonals) IS the reference's default diagonal update
+ * (precondition_default, reference itsolv/IterativeSolver.h:46-55: r_k[i] /= diag[i] - shift_k + 1e-15). The fused
+ * solve() then applies it inside the residual kernel instead of calling precondition(); a Problem without the tag keeps
+ * its own precondition() call.
+ */
+struct UsesDefaultDiagonalPreconditioner {
+  virtual ~UsesDefaultDiagonalPreconditioner() = default;
+};
 
 //! X space whose new equation-data blocks come from a single Gram launch
 class XSpaceFused : public its::subspace::XSpace<DistrArrayCUDA, DistrArrayCUDA, std::map<size_t, double>> {
@@ -135,6 +149,97 @@ public:
     this->set_hermiticity(this->get_hermiticity());
   }
 
+  using Base::solve;
+  /*!
+   * The reference's one-call driver (IterativeSolverTemplate.h:322-408), statement for statement, with three changes that
+   * do not alter what is computed:
+   *  - the R vectors that enter the Q space hand over their allocations instead of being copied (they are overwritten by
+   *    the solution step that follows), and the proposal step swaps its result into the parameters instead of copying;
+   *  - solutions, residuals, error norms and - for a Problem tagged UsesDefaultDiagonalPreconditioner - the diagonal
+   *    preconditioner of all roots are one pass over the subspace (ArrayHandlerCUDA::davidson_residual). The solution
+   *    vectors themselves are formed only once the working set is empty: during the iterations the reference overwrites
+   *    them before anything reads them (parameters[0] receives the diagonal, :391, and the proposal step the new
+   *    parameters);
+   *  - the diagonal is handed to the preconditioner as it is instead of through a copy in parameters[0].
+   */
+  bool solve(const VecRef<R>& parameters, const VecRef<R>& actions, const its::Problem<R>& problem,
+             bool generate_initial_guess = false) override {
+    if (parameters.empty())
+      throw std::runtime_error("Empty container passed to IterativeSolver::solve()");
+    if (parameters.size() != actions.size())
+      throw std::runtime_error("Inconsistent container sizes in IterativeSolver::solve()");
+    struct InSolve {
+      bool& flag;
+      explicit InSolve(bool& f) : flag(f) { flag = true; }
+      ~InSolve() { flag = false; }
+    } in_solve(m_in_fused_solve);
+    const bool default_preconditioner = dynamic_cast<const UsesDefaultDiagonalPreconditioner*>(&problem) != nullptr;
+    this->m_logger->max_trace_level = its::Logger::None;
+    if (this->m_verbosity == its::Verbosity::Detailed) {
+      this->m_logger->max_trace_level = its::Logger::Info;
+      this->m_logger->data_dump = true;
+    }
+    const bool use_diagonals = problem.diagonals(actions.at(0));
+    std::unique_ptr<R> diagonals;
+    if (use_diagonals)
+      diagonals.reset(new R{this->m_handlers->qr().copy(actions.at(0))});
+    if (generate_initial_guess) {
+      if (!use_diagonals)
+        throw std::runtime_error("Default initial guess requested, but diagonal elements are not available");
+      auto guess = this->m_handlers->qq().select(parameters.size(), *diagonals);
+      size_t root = 0;
+      for (const auto& g : guess)
+        this->m_handlers->rp().copy(parameters[root++], P{{g.first, 1}});
+    }
+    int nwork = int(parameters.size());
+    std::vector<P> pspace;
+    if (use_diagonals && this->m_max_p > 0) {
+      auto selectp = this->m_handlers->qq().select(this->m_max_p, *diagonals);
+      for (auto s = selectp.begin(); s != selectp.end(); s++)
+        if (s->second > selectp.begin()->second + this->m_p_threshold) {
+          selectp.erase(s, selectp.end());
+          break;
+        }
+      for (const auto& s : selectp)
+        pspace.emplace_back(P{{s.first, 1}});
+      typename Base::fapply_on_p_type apply_on_p = [&problem](const std::vector<std::vector<double>>& pcoeff,
+                                                              const CVecRef<P>& pparams, const VecRef<R>& act) {
+        problem.p_action(pcoeff, pparams, act);
+      };
+      auto action_matrix = problem.pp_action_matrix(pspace);
+      nwork = int(this->add_p(its::cwrap(pspace),
+                              molpro::linalg::array::Span<double>(action_matrix.data(), action_matrix.size()), parameters,
+                              actions, apply_on_p));
+    }
+    for (int iter = 0; iter < this->m_max_iter && nwork > 0; iter++) {
+      bool preconditioned = false;
+      if (iter > 0 || pspace.empty()) {
+        problem.action(its::cwrap(parameters.begin(), parameters.begin() + nwork),
+                       its::wrap(actions.begin(), actions.begin() + nwork));
+        nwork = add_vector_fused(parameters, actions, default_preconditioner ? diagonals.get() : nullptr, preconditioned);
+      }
+      while (this->end_iteration_needed()) {
+        if (nwork > 0 && !preconditioned) {
+          if (use_diagonals) {
+            this->m_handlers->rq().copy(parameters.at(0), *diagonals);
+            problem.precondition(its::wrap(actions.begin(), actions.begin() + nwork), this->working_set_eigenvalues(),
+                                 parameters.at(0));
+          } else
+            problem.precondition(its::wrap(actions.begin(), actions.begin() + nwork), this->working_set_eigenvalues());
+        }
+        nwork = int(this->end_iteration(parameters, actions));
+      }
+      if (this->m_verbosity >= its::Verbosity::Iteration)
+        this->report();
+    }
+    if (this->m_verbosity == its::Verbosity::Summary)
+      this->report();
+    const double worst = *std::max_element(this->m_errors.begin(), this->m_errors.end());
+    if (this->m_verbosity >= its::Verbosity::Summary && worst > this->m_convergence_threshold)
+      std::cerr << "Solver has not converged to threshold " << this->m_convergence_threshold << std::endl;
+    return nwork == 0 && worst <= this->m_convergence_threshold;
+  }
+
   //! parameters and residuals of the requested roots (reference IterativeSolverTemplate.h:191-215), batched
   void solution(const std::vector<int>& roots, const VecRef<R>& parameters, const VecRef<R>& residual) override {
     this->check_consistent_number_of_roots_and_solutions(roots, parameters.size());
@@ -199,6 +304,84 @@ public:
   }
 
 protected:
+  /*!
+   * add_vector of the reference (IterativeSolverTemplate.h:140-166 with solve_and_generate_working_set, :518-563) for the
+   * fused solve(): on return the first working_set().size() actions hold the residuals of the working set, already
+   * preconditioned when `preconditioned` comes back true; the parameters hold the solutions only when the working set
+   * is empty.
+   */
+  int add_vector_fused(const VecRef<R>& parameters, const VecRef<R>& actions, const R* diagonals, bool& preconditioned) {
+    preconditioned = false;
+    if (this->m_xspace->dimensions().nP != 0 && !this->m_apply_p)
+      throw std::runtime_error(
+          "Solver contains P space but no valid apply_p function. Make sure add_p was called correctly.");
+    const auto nW = std::min(this->m_working_set.size(), parameters.size());
+    const auto cwparams = its::cwrap(parameters.begin(), parameters.begin() + nW);
+    const auto cwactions = its::cwrap(actions.begin(), actions.begin() + nW);
+    this->m_stats->r_creations += nW;
+    {
+      ArrayHandlerCUDA::TakeOnCopy take(*m_dense);
+      this->m_xspace->update_qspace(cwparams, cwactions);
+    }
+    this->m_stats->q_creations += 2 * nW;
+    this->m_subspace_solver->solve(*this->m_xspace, this->n_roots());
+    const auto nsol = this->m_subspace_solver->size();
+    const auto dims = this->m_xspace->dimensions();
+    if (dims.nP != 0 || nsol == 0 || nsol > parameters.size() || this->m_normalise_solution || dims.nQ + dims.nD == 0) {
+      // several batches of roots, a P space or normalised solutions: the general routine (it solves the same subspace
+      // problem again, which is cheap next to these cases' vector work)
+      const auto nwork = this->solve_and_generate_working_set(parameters, actions);
+      its::read_handler_counts(this->m_stats, this->m_handlers);
+      this->m_end_iteration_needed = true;
+      return int(nwork);
+    }
+    auto& xs = *this->m_xspace;
+    const auto& sol = this->m_subspace_solver->solutions();
+    std::vector<int> roots(nsol);
+    std::iota(roots.begin(), roots.end(), 0);
+    Matrix<double> c({dims.nQ + dims.nD, nsol});
+    std::vector<double> lambda(nsol);
+    const auto eigvals = this->eigenvalues();
+    for (size_t i = 0; i < nsol; ++i) {
+      lambda[i] = eigvals.at(i);
+      for (size_t j = 0; j < dims.nQ; ++j)
+        c(j, i) = sol(i, dims.oQ + j);
+      for (size_t j = 0; j < dims.nD; ++j)
+        c(dims.nQ + j, i) = sol(i, dims.oD + j);
+    }
+    auto stack = [](CVecRef<R> a, const CVecRef<R>& b) {
+      a.insert(a.end(), b.begin(), b.end());
+      return a;
+    };
+    const auto norms = m_dense->davidson_residual(c, stack(xs.cparamsq(), xs.cparamsd()), stack(xs.cactionsq(), xs.cactionsd()),
+                                                  lambda, diagonals, VecRef<R>{},
+                                                  VecRef<R>(actions.begin(), actions.begin() + nsol));
+    std::vector<double> errors(nsol);
+    for (size_t i = 0; i < nsol; ++i)
+      errors[i] = std::sqrt(std::abs(norms.residual[i]));
+    this->m_subspace_solver->set_error(roots, errors);
+    this->set_value_errors();
+    this->m_errors = this->m_subspace_solver->errors();
+    this->m_working_set =
+        its::detail::select_working_set(parameters.size(), this->m_errors, this->m_convergence_threshold,
+                                        this->m_value_errors, this->m_convergence_threshold_value);
+    m_written_norms.clear();
+    for (size_t i = 0; i < this->m_working_set.size(); ++i) {
+      const size_t root = this->m_working_set[i];
+      if (root < i)
+        throw std::logic_error("incorrect ordering of roots");
+      if (root > i)
+        this->m_handlers->rr().copy(actions[i], actions[root]);
+      m_written_norms.push_back(norms.written[root]);
+    }
+    preconditioned = diagonals != nullptr;
+    if (this->m_working_set.empty()) // converged: leave solutions and residuals in the caller's vectors as the reference does
+      solution(roots, parameters, actions);
+    its::read_handler_counts(this->m_stats, this->m_handlers);
+    this->m_end_iteration_needed = true;
+    return int(this->m_working_set.size());
+  }
+
   //! res_i -= lambda_i * x_i for all roots in one pass (reference LinearEigensystemDavidson.h:186-192)
   void construct_residual(const std::vector<int>& roots, const CVecRef<R>& params, const VecRef<R>& actions) override {
     const auto eigvals = this->eigenvalues();
@@ -342,12 +525,19 @@ protected:
     }
     its::util::delete_parameters(null_params, wresidual);
     normalise_set(wresidual);
-    for (size_t i = 0; i < wresidual.size(); ++i)
-      handlers.rr().copy(parameters.at(i), wresidual.at(i));
-    return det::get_new_working_set(this->working_set(), its::cwrap(residuals), its::cwrap(wresidual));
+    auto new_working_set = det::get_new_working_set(this->working_set(), its::cwrap(residuals), its::cwrap(wresidual));
+    for (size_t i = 0; i < wresidual.size(); ++i) {
+      if (m_in_fused_solve) // the residual buffers are scratch until the next action() fills them: no copy needed
+        parameters.at(i).get().swap(wresidual.at(i).get());
+      else
+        handlers.rr().copy(parameters.at(i), wresidual.at(i));
+    }
+    return new_working_set;
   }
 
   ArrayHandlerCUDA* m_dense = nullptr;
+  bool m_in_fused_solve = false;
+  std::vector<double> m_written_norms; //!< <r,r> of the working set's preconditioned residuals, from the residual kernel
 };
 
 } // namespace itsolv_b200

@@ -48,6 +48,45 @@ def test_batched_kernels_bit_exact(ctx, oracle, n):
     assert np.array_equal(host(rs), want)
 
 
+@pytest.mark.parametrize("n,k,m", [(1, 1, 1), (2, 3, 2), (33, 5, 3), (1000, 4, 4), (4097, 9, 5), (50001, 12, 8),
+                                   (20000, 7, 16), (3001, 6, 19)])
+@pytest.mark.parametrize("precondition", [False, True])
+def test_davidson_residual_kernel_equals_the_unfused_sequence(ctx, oracle, n, k, m, precondition):
+    """itsolv_davidson_residual_f64 against the oracle's sequence of the reference's steps: two expansions (FMA chains
+    from zero, as gemm_outer with beta_zero), r -= lambda x as an axpy, the norms, precondition_default. Vectors bit for
+    bit; norms to 1e-12 relative (summation order)."""
+    rng = np.random.default_rng(1000 * n + 10 * k + m)
+    Q, A = rng.standard_normal((k, n)), rng.standard_normal((k, n))
+    coef = rng.standard_normal((k, m))
+    lam = np.arange(1, m + 1) + 0.25 * rng.standard_normal(m)
+    diag = np.arange(1, n + 1, dtype=np.float64)
+    want_x = oracle.c.gemm_outer(coef, Q, np.zeros((m, n)), fma=True)
+    want_r = oracle.c.gemm_outer(coef, A, np.zeros((m, n)), fma=True)
+    want_r = np.stack([oracle.c.axpy(-lam[j], want_x[j], want_r[j]) for j in range(m)])
+    want_n2 = np.array([oracle.c.dot(want_r[j], want_r[j]) for j in range(m)])
+    want_out = oracle.c.precondition(want_r, lam, diag) if precondition else want_r
+    want_n2w = np.array([oracle.c.dot(want_out[j], want_out[j]) for j in range(m)])
+    q, a = dev_rows(Q), dev_rows(A)
+    for with_x in (False, True):
+        out_r = [torch.full((n,), np.nan, dtype=torch.float64, device="cuda") for _ in range(m)]
+        out_x = [torch.full((n,), np.nan, dtype=torch.float64, device="cuda") for _ in range(m)] if with_x else None
+        n2, n2w = ctx.davidson_residual(coef, q, a, lam, out_r, diag=dev_rows(diag[None])[0] if precondition else None,
+                                        out_x=out_x)
+        assert np.array_equal(host(out_r), want_out)
+        if with_x:
+            assert np.array_equal(host(out_x), want_x)
+        assert np.abs(n2 - want_n2).max() <= 1e-12 * want_n2.max()
+        assert np.abs(n2w - want_n2w).max() <= 1e-12 * want_n2w.max()
+    assert np.array_equal(host(q), Q) and np.array_equal(host(a), A), "inputs must not be touched"
+
+
+def test_davidson_residual_rejects_aliased_outputs(ctx):
+    q = [torch.ones(64, dtype=torch.float64, device="cuda") for _ in range(2)]
+    a = [torch.ones(64, dtype=torch.float64, device="cuda") for _ in range(2)]
+    with pytest.raises(RuntimeError):
+        ctx.davidson_residual(np.ones((2, 1)), q, a, [1.0], [q[1]])
+
+
 @pytest.mark.parametrize("name", DAVIDSON)
 def test_fused_solve_matches_reference_golden(ctx, name):
     want = GOLDEN[name]

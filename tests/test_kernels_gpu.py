@@ -272,3 +272,76 @@ def test_full_size_properties(ctx):
     ctx.gemm_outer(alpha, xs, ys)
     G2 = ctx.gemm_inner(xs, ys)
     assert np.abs(G2 - (G + S @ alpha)).max() <= 1e-11 * n
+
+
+def csr_reference(row_ptr, col, val, x):
+    """row sums in ascending entry order, product and sum rounded separately (the CPU twin's arithmetic)"""
+    n = row_ptr.size - 1
+    y = np.zeros(n)
+    length = np.diff(row_ptr)
+    for j in range(int(length.max()) if n else 0):
+        rows = np.nonzero(length > j)[0]
+        e = row_ptr[rows] + j
+        y[rows] = y[rows] + val[e] * x[col[e]]
+    return y
+
+
+@pytest.mark.parametrize("n,b,w,kind", [(1, 0, 1, "band"), (255, 4, 1, "band"), (256, 4, 2, "band"), (257, 4, 3, "band"),
+                                        (5000, 4, 4, "band"), (5000, 7, 5, "band"), (3000, 4, 8, "band"),
+                                        (3000, 4, 9, "band"), (2000, 130, 2, "band"), (4000, 3, 4, "scattered"),
+                                        (1500, 12, 3, "long_rows"), (1000, 2, 2, "empty_rows")])
+def test_csr_apply_multi_bit_exact(ctx, n, b, w, kind):
+    """the stored-CSR operator kernel (shared-memory staged rows and x window; global fallback for columns outside the
+    window; several rounds for rows with many entries) against the sequential row sums"""
+    rng = np.random.default_rng(n + 17 * b + w)
+    rows_cols = []
+    for i in range(n):
+        if kind == "empty_rows" and i % 3 == 0:
+            rows_cols.append(np.zeros(0, dtype=np.int64))
+            continue
+        lo, hi = max(0, i - b), min(n - 1, i + b)
+        c = np.arange(lo, hi + 1)
+        if kind == "scattered":  # a few entries far outside the band: read through the global fallback
+            c = np.unique(np.concatenate([c, rng.integers(0, n, 3)]))
+        if kind == "long_rows" and i % 50 == 0:  # more entries in 256 rows than one staging round holds
+            c = np.arange(max(0, i - 10 * b), min(n - 1, i + 10 * b) + 1)
+        rows_cols.append(c)
+    row_ptr = np.zeros(n + 1, dtype=np.int64)
+    row_ptr[1:] = np.cumsum([c.size for c in rows_cols])
+    col = np.concatenate(rows_cols).astype(np.int32) if n else np.zeros(0, dtype=np.int32)
+    val = rng.standard_normal(col.size)
+    X = rng.standard_normal((w, n))
+    band = 10 * b if kind == "long_rows" else b  # "scattered": the window stays 2b wide, the rest is read globally
+    d_rp, d_col, d_val = torch.from_numpy(row_ptr).cuda(), torch.from_numpy(col).cuda(), dev(val)
+    xs = dev_rows(X)
+    ys = [torch.full((n,), np.nan, dtype=torch.float64, device="cuda") for _ in range(w)]
+    ctx.csr_apply_multi(d_rp.data_ptr(), d_col.data_ptr() if col.size else 0, d_val, xs, ys, n, 0, min(band, n))
+    want = np.stack([csr_reference(row_ptr, col, val, X[k]) for k in range(w)])
+    assert np.array_equal(host(ys), want)
+
+
+def test_csr_apply_multi_sharded_with_halos(ctx):
+    n, b, w, cut = 3000, 5, 3, 1234
+    rng = np.random.default_rng(5)
+    cols = [np.arange(max(0, i - b), min(n - 1, i + b) + 1) for i in range(n)]
+    X = rng.standard_normal((w, n))
+
+    def shard(r0, r1):
+        row_ptr = np.zeros(r1 - r0 + 1, dtype=np.int64)
+        row_ptr[1:] = np.cumsum([cols[i].size for i in range(r0, r1)])
+        col = np.concatenate(cols[r0:r1]).astype(np.int32)
+        return row_ptr, col
+
+    full_ptr, full_col = shard(0, n)
+    val = rng.standard_normal(full_col.size)
+    want = np.stack([csr_reference(full_ptr, full_col, val, X[k]) for k in range(w)])
+    for r0, r1 in ((0, cut), (cut, n)):
+        row_ptr, col = shard(r0, r1)
+        v = val[full_ptr[r0]:full_ptr[r1]]
+        d_rp, d_col, d_val = torch.from_numpy(row_ptr).cuda(), torch.from_numpy(col).cuda(), dev(v)
+        xs = dev_rows(X[:, r0:r1])
+        lo = dev_rows(X[:, r0 - b:r0]) if r0 > 0 else None
+        hi = dev_rows(X[:, r1:r1 + b]) if r1 < n else None
+        ys = [torch.full((r1 - r0,), np.nan, dtype=torch.float64, device="cuda") for _ in range(w)]
+        ctx.csr_apply_multi(d_rp.data_ptr(), d_col.data_ptr(), d_val, xs, ys, n, r0, b, x_lo=lo, x_hi=hi)
+        assert np.array_equal(host(ys), want[:, r0:r1])
