@@ -111,6 +111,10 @@ int itsolv_scal_batch_f64(itsolv_ctx* ctx, const double* alpha, double* const* x
 int itsolv_axpy_batch_f64(itsolv_ctx* ctx, const double* alpha, const double* const* x, double* const* y, int w, size_t n);
 /* one step of the R-R modified Gram-Schmidt (propose_rspace.h:451-463): ri *= inv_norm; rj[k] += (-ov[k])*ri */
 int itsolv_mgs_step_f64(itsolv_ctx* ctx, double inv_norm, double* ri, const double* ov, double* const* rj, int m, size_t n);
+/* the same step that also returns, from the values it has just written, the inner products the next step needs:
+ * dots[0] = <ri', ri'>, dots[1+t] = <rj[0]', rj[t]'> for t in [0, m) (HOST, m+1 values, all-reduced over ranks); m <= 16 */
+int itsolv_mgs_step_dots_f64(itsolv_ctx* ctx, double inv_norm, double* ri, const double* ov, double* const* rj, int m,
+                             size_t n, double* dots);
 /* counter that every call which may write a vector advances (and DistrArrayCUDA::data() non-const): results cached
  * on the host side (ArrayHandlerCUDA's primed dots) are valid only while it stands still */
 unsigned long long itsolv_ctx_write_epoch(itsolv_ctx* ctx);
@@ -123,6 +127,12 @@ int itsolv_gemm_inner_f64(itsolv_ctx* ctx, const double* const* xx, int k, const
 /* yy[j] += sum_i alpha[i*m+j]*xx[i] (i ascending, as the reference's loop); beta_zero!=0: yy[j] = sum (yy not read) */
 int itsolv_gemm_outer_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* xx,
                           double* const* yy, size_t n, int beta_zero);
+
+/* yy[j] = yscale[j]*yy[j] + sum_i alpha[i*m+j]*xx[i]: the product yscale*yy is rounded first, then the sum runs as in
+ * itsolv_gemm_outer_f64, i.e. the result is bit-identical to itsolv_scal_batch_f64 followed by itsolv_gemm_outer_f64
+ * (normalise + Gram-Schmidt projection of the new vectors, reference itsolv/propose_rspace.h:17-28, 430-443) */
+int itsolv_gemm_outer_scaled_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* xx,
+                                 double* const* yy, size_t n, const double* yscale);
 
 /* ---- Davidson diagonal preconditioner (reference itsolv/IterativeSolver.h:46-55):
  * r_k[i] = r_k[i] / (diag[i] - shift[k] + 1e-15), w vectors in one pass over diag ---- */

@@ -103,6 +103,10 @@ KERNEL_API = {
     "itsolv_gemm_inner_f64": (C.c_int, [C.c_void_p, c_void_pp, C.c_int, c_void_pp, C.c_int, C.c_size_t, c_double_p]),
     "itsolv_gemm_outer_f64": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_int, c_void_pp, c_void_pp, C.c_size_t,
                                         C.c_int]),
+    "itsolv_mgs_step_dots_f64": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, c_double_p, c_void_pp, C.c_int,
+                                           C.c_size_t, c_double_p]),
+    "itsolv_gemm_outer_scaled_f64": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_int, c_void_pp, c_void_pp,
+                                               C.c_size_t, c_double_p]),
     "itsolv_precondition_f64": (C.c_int, [C.c_void_p, c_void_pp, C.c_int, C.c_void_p, c_double_p, C.c_size_t]),
     "itsolv_davidson_residual_f64": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_int, c_void_pp, c_void_pp, c_double_p,
                                                C.c_void_p, c_double_p, c_void_pp, c_void_pp, C.c_size_t, c_double_p,

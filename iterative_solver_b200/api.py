@@ -157,6 +157,14 @@ class Context:
         self._check(self.lib.itsolv_mgs_step_f64(self.handle, inv_norm, _ptr(ri), _dbl(o) if len(rjs) else None,
                                                  _ptr_array(rjs), len(rjs), ri.numel()))
 
+    def mgs_step_dots(self, inv_norm: float, ri, ov: Sequence[float], rjs: Sequence) -> np.ndarray:
+        """mgs_step that also returns [<ri', ri'>, <rjs[0]', rjs[t]'> for t in range(len(rjs))]"""
+        o = np.ascontiguousarray(ov, dtype=np.float64)
+        dots = np.zeros(len(rjs) + 1)
+        self._check(self.lib.itsolv_mgs_step_dots_f64(self.handle, inv_norm, _ptr(ri), _dbl(o) if len(rjs) else None,
+                                                      _ptr_array(rjs), len(rjs), ri.numel(), _dbl(dots)))
+        return dots
+
     def dot(self, x, y) -> float:
         r = C.c_double()
         self._check(self.lib.itsolv_dot_f64(self.handle, _ptr(x), _ptr(y), x.numel(), C.byref(r)))
@@ -179,6 +187,16 @@ class Context:
         n = yy[0].numel() if n is None else n
         self._check(self.lib.itsolv_gemm_outer_f64(self.handle, _dbl(a), k, m, _ptr_array(xx), _ptr_array(yy), n,
                                                    1 if beta_zero else 0))
+
+    def gemm_outer_scaled(self, alpha: np.ndarray, xx: Sequence, yy: Sequence, yscale: Sequence[float]):
+        """yy[j] = yscale[j]*yy[j] + sum_i alpha[i,j] xx[i]  (scal_batch followed by gemm_outer, in one pass)"""
+        k, m = len(xx), len(yy)
+        a = np.ascontiguousarray(alpha, dtype=np.float64).reshape(k, m)
+        s = np.ascontiguousarray(yscale, dtype=np.float64)
+        if m == 0:
+            return
+        self._check(self.lib.itsolv_gemm_outer_scaled_f64(self.handle, _dbl(a), k, m, _ptr_array(xx), _ptr_array(yy),
+                                                          yy[0].numel(), _dbl(s)))
 
     def precondition(self, residuals: Sequence, diag, shift: Sequence[float]):
         s = np.ascontiguousarray(shift, dtype=np.float64)

@@ -25,6 +25,7 @@ struct GoParams {
   int k, m;
   int ld; // leading dimension of alpha in shared memory (m rounded up to a multiple of MJ)
   int beta_zero;
+  int scaled; // row k of the staged coefficients holds a factor per y: y_j is multiplied by it (rounded) before the sums
 };
 
 template <class RV>
@@ -37,12 +38,17 @@ struct RowOps<double2> {
     acc.x = fma(a, x.x, acc.x);
     acc.y = fma(a, x.y, acc.y);
   }
+  static __device__ __forceinline__ void scale(double2& acc, double s) {
+    acc.x = __dmul_rn(acc.x, s);
+    acc.y = __dmul_rn(acc.y, s);
+  }
 };
 template <>
 struct RowOps<double> {
   static constexpr int width = 1;
   static __device__ __forceinline__ double zero() { return 0.0; }
   static __device__ __forceinline__ void fma_to(double& acc, double a, const double& x) { acc = fma(a, x, acc); }
+  static __device__ __forceinline__ void scale(double& acc, double s) { acc = __dmul_rn(acc, s); }
 };
 
 //! MJ consecutive coefficients of one alpha row; the address is warp-uniform (broadcast) and 16-byte aligned for MJ >= 2
@@ -72,6 +78,13 @@ __device__ __forceinline__ void expand_rows(const GoParams& p, const double* __r
         acc[b] = reinterpret_cast<const RV*>(p.y[jc + b])[r];
       else
         acc[b] = Ops::zero();
+    }
+    if (p.scaled) {
+      double sv[MJ];
+      load_alpha_row<MJ>(sa + size_t(p.k) * p.ld + jc, sv);
+#pragma unroll
+      for (int b = 0; b < MJ; ++b)
+        Ops::scale(acc[b], sv[b]);
     }
     int i = 0;
     for (; i + kGoUnroll <= p.k; i += kGoUnroll) {
@@ -105,8 +118,8 @@ __device__ __forceinline__ void expand_rows(const GoParams& p, const double* __r
 
 template <int MJ, bool VEC>
 __global__ void __launch_bounds__(kGoThreads, 2) gemm_outer_kernel(const __grid_constant__ GoParams p) {
-  extern __shared__ __align__(16) double sa[]; // k x ld, zero padded columns
-  for (int e = threadIdx.x; e < p.k * p.ld; e += blockDim.x) {
+  extern __shared__ __align__(16) double sa[]; // k (+1 when scaled) x ld, zero padded columns
+  for (int e = threadIdx.x; e < (p.k + p.scaled) * p.ld; e += blockDim.x) {
     const int i = e / p.ld, j = e % p.ld;
     sa[e] = j < p.m ? p.alpha[size_t(i) * p.m + j] : 0.0;
   }
@@ -152,8 +165,27 @@ using namespace itsolv;
 
 extern "C" {
 
+static int gemm_outer_impl(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* xx,
+                           double* const* yy, size_t n, int beta_zero, const double* yscale);
+
 int itsolv_gemm_outer_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* xx,
                           double* const* yy, size_t n, int beta_zero) {
+  return gemm_outer_impl(ctx, alpha, k, m, xx, yy, n, beta_zero, nullptr);
+}
+
+int itsolv_gemm_outer_scaled_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* xx,
+                                 double* const* yy, size_t n, const double* yscale) {
+  ITSOLV_REQUIRE(yscale != nullptr, "itsolv_gemm_outer_scaled_f64: null scale factors");
+  if (k <= 0) { // nothing to add: the scaling alone
+    ctx->counters.n_gemm_outer++;
+    return m > 0 ? itsolv_scal_batch_f64(ctx, yscale, yy, m, n) : 0;
+  }
+  ctx->counters.n_scal += m > 0 ? m : 0;
+  return gemm_outer_impl(ctx, alpha, k, m, xx, yy, n, 0, yscale);
+}
+
+static int gemm_outer_impl(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* xx,
+                           double* const* yy, size_t n, int beta_zero, const double* yscale) {
   ctx->counters.n_gemm_outer++;
   if (m <= 0)
     return 0;
@@ -178,6 +210,8 @@ int itsolv_gemm_outer_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, co
         aliased = true;
   }
   if (aliased) {
+    if (yscale && itsolv_scal_batch_f64(ctx, yscale, yy, m, n))
+      return 1;
     if (beta_zero)
       for (int j = 0; j < m; ++j)
         if (itsolv_fill_f64(ctx, 0.0, yy[j], n))
@@ -207,13 +241,17 @@ int itsolv_gemm_outer_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, co
       }
       char *h = nullptr, *d = nullptr;
       int slot = 0;
-      const size_t abytes = size_t(kb) * mb * sizeof(double);
+      const bool scaled = yscale != nullptr && i0 == 0; // the factor is applied with the first block of x vectors
+      const size_t abytes = size_t(kb + (scaled ? 1 : 0)) * mb * sizeof(double);
       if (stage_acquire(ctx, abytes, &h, &d, &slot))
         return 1;
       double* ha = reinterpret_cast<double*>(h);
       for (int i = 0; i < kb; ++i)
         for (int j = 0; j < mb; ++j)
           ha[size_t(i) * mb + j] = alpha[size_t(i0 + i) * m + (j0 + j)];
+      if (scaled)
+        for (int j = 0; j < mb; ++j)
+          ha[size_t(kb) * mb + j] = yscale[j0 + j];
       if (stage_commit(ctx, slot, abytes))
         return 1;
       p.alpha = reinterpret_cast<const double*>(d);
@@ -221,6 +259,7 @@ int itsolv_gemm_outer_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, co
       p.k = kb;
       p.m = mb;
       p.beta_zero = bz ? 1 : 0;
+      p.scaled = scaled ? 1 : 0;
       int mj = 1;
       while (mj < mb && mj < 16)
         mj *= 2;
@@ -229,7 +268,7 @@ int itsolv_gemm_outer_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, co
       p.ld = ((mb + mj - 1) / mj) * mj;
       GoKernel kernel = go_pick(mj, vec);
       ITSOLV_REQUIRE(kernel != nullptr, "gemm_outer: column tile not instantiated");
-      const size_t smem = size_t(kb) * p.ld * sizeof(double);
+      const size_t smem = size_t(kb + p.scaled) * p.ld * sizeof(double);
       if (ensure_dynamic_smem(ctx, reinterpret_cast<const void*>(kernel), smem))
         return 1;
       int per_sm = ctx->opt_go_ctas > 0 ? ctx->opt_go_ctas : (mj <= 2 ? 6 : mj == 4 ? 4 : mj == 8 ? 3 : 2);

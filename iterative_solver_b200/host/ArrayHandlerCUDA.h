@@ -202,6 +202,50 @@ public:
     return norms;
   }
 
+  //! mgs_step that also returns {<ri', ri'>, <rj[0]', rj[t]'> for every t}: what the next step needs (at most 16 rj)
+  std::vector<double> mgs_step_dots(double inv_norm, AL& ri, const std::vector<double>& ov, const VecRef<AL>& rj) {
+    this->m_counter->scal++;
+    this->m_counter->axpy += int(rj.size());
+    this->m_counter->dot += int(rj.size()) + 1;
+    std::vector<double*> pj(rj.size());
+    for (size_t j = 0; j < rj.size(); ++j) {
+      ri.require_compatible(rj[j].get(), "mgs_step_dots");
+      pj[j] = rj[j].get().data();
+    }
+    std::vector<double> dots(rj.size() + 1);
+    check(itsolv_mgs_step_dots_f64(ri.context(), inv_norm, ri.data(), ov.data(), pj.data(), int(pj.size()),
+                                   ri.local_size(), dots.data()),
+          "ArrayHandlerCUDA::mgs_step_dots");
+    if (m_observer)
+      m_observer('g', 1, dots.size(), dots.data());
+    return dots;
+  }
+  static constexpr size_t max_mgs_step_dots = 16;
+  //! yy[j] = yscale[j] * yy[j] + sum_i alphas(i,j) xx[i]: scal_batch followed by gemm_outer, in one pass
+  void gemm_outer_scaled(const Matrix<value_type>& alphas, const CVecRef<AR>& xx, const VecRef<AL>& yy,
+                         const std::vector<double>& yscale) {
+    if (alphas.rows() > xx.size() || alphas.cols() > yy.size() || alphas.cols() > yscale.size())
+      throw std::out_of_range("gemm_outer_scaled: dimensions of alphas do not match xx, yy, yscale");
+    const size_t nx = alphas.rows(), ny = alphas.cols();
+    if (ny == 0)
+      return;
+    this->m_counter->gemm_outer++;
+    this->m_counter->scal += int(ny);
+    std::vector<const double*> px(nx);
+    std::vector<double*> py(ny);
+    const AL& first = yy[0].get();
+    for (size_t i = 0; i < nx; ++i) {
+      first.require_compatible(xx[i].get(), "gemm_outer_scaled");
+      px[i] = xx[i].get().data();
+    }
+    for (size_t j = 0; j < ny; ++j) {
+      first.require_compatible(yy[j].get(), "gemm_outer_scaled");
+      py[j] = yy[j].get().data();
+    }
+    check(itsolv_gemm_outer_scaled_f64(first.context(), alphas.data().data(), int(nx), int(ny), px.data(), py.data(),
+                                       first.local_size(), yscale.data()),
+          "ArrayHandlerCUDA::gemm_outer_scaled");
+  }
   //! yy[j] = sum_i alphas(i,j) xx[i]: the targets are written, not read (fill + gemm_outer of the reference in one pass)
   void gemm_outer_assign(const Matrix<value_type>& alphas, const CVecRef<AR>& xx, const VecRef<AL>& yy) {
     expand(alphas, xx, yy, true);

@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <iostream>
+#include <limits>
 #include <map>
 #include <numeric>
 #include <stdexcept>
@@ -435,12 +436,29 @@ protected:
       subspace_solver.solve(xspace, solutions.rows());
     }
     auto wresidual = its::wrap(residuals.begin(), residuals.begin() + this->working_set().size());
-    normalise_set(wresidual);
-
     const auto dims = xspace.dimensions();
     const size_t nP = dims.nP, nQ = dims.nQ, nD = dims.nD, nX = dims.nX;
     size_t nN = wresidual.size();
     const size_t nN0 = nN; // columns of G keep their positions when vectors are dropped below
+    // normalise(): the factors 1/|r_i|. With a P space they are applied now; otherwise the vectors stay as they are until
+    // the projection below multiplies them in on the fly, and the overlaps are scaled on the host in the meantime.
+    std::vector<double> factor(nN, 1.0);
+    {
+      const auto d = m_written_norms.size() == nN ? m_written_norms : m_dense->self_dots(its::cwrap(wresidual));
+      m_written_norms.clear();
+      for (size_t i = 0; i < nN; ++i) {
+        const double norm = std::sqrt(std::abs(d[i]));
+        if (norm > 1.0e-14)
+          factor[i] = 1. / norm;
+        else
+          logger.msg("parameter's length is too small for normalisation, dot = " + its::Logger::scientific(norm),
+                     its::Logger::Warn);
+      }
+    }
+    if (nP > 0) {
+      m_dense->scal_batch(factor, wresidual);
+      factor.assign(nN, 1.0);
+    }
     const auto pparams = xspace.cparamsp();
     const auto qparams = xspace.cparamsq(), dparams = xspace.cparamsd();
     CVecRef<R> xdense(qparams.begin(), qparams.end());
@@ -448,7 +466,10 @@ protected:
     // overlap of the new vectors with themselves and with Q, D in one launch; with P through the sparse handler
     CVecRef<R> cols = its::cwrap(wresidual);
     cols.insert(cols.end(), xdense.begin(), xdense.end());
-    const auto G = m_dense->gemm_inner(its::cwrap(wresidual), cols); // nN x (nN + nQ + nD)
+    auto G = m_dense->gemm_inner(its::cwrap(wresidual), cols); // nN x (nN + nQ + nD)
+    for (size_t i = 0; i < nN; ++i)
+      for (size_t j = 0; j < G.cols(); ++j)
+        G(i, j) = G(i, j) * factor[i] * (j < nN ? factor[j] : 1.0);
     Matrix<double> GP({nN, nP});
     if (nP > 0)
       GP = handlers.rp().gemm_inner(its::cwrap(wresidual), pparams);
@@ -479,8 +500,13 @@ protected:
     }
     its::util::delete_parameters(redundant, wresidual);
     nN = wresidual.size();
+    std::vector<double> kept_factor(nN);
+    for (size_t j = 0; j < nN; ++j)
+      kept_factor[j] = factor[kept[j]];
 
-    // projection against P, Q, D: sequential coefficients by forward substitution, applied in one expansion
+    // projection against P, Q, D: sequential coefficients by forward substitution, applied in one expansion that also
+    // multiplies the normalisation factor in
+    bool scaled = nP > 0;
     if (nN > 0 && nX > 0) {
       Matrix<double> c({nX, nN});
       for (size_t j = 0; j < nN; ++j)
@@ -505,26 +531,68 @@ protected:
           for (size_t i = 0; i < nD; ++i)
             cd(nQ + i, j) = c(dims.oD + i, j);
         }
-        m_dense->gemm_outer(cd, xdense, wresidual);
+        if (scaled)
+          m_dense->gemm_outer(cd, xdense, wresidual);
+        else
+          m_dense->gemm_outer_scaled(cd, xdense, wresidual, kept_factor);
+        scaled = true;
       }
     }
-    // R-R modified Gram-Schmidt: per pivot one Gram row (norm and overlaps with the later vectors) and one fused update
+    if (!scaled && nN > 0)
+      m_dense->scal_batch(kept_factor, wresidual);
+    // R-R modified Gram-Schmidt: one pass per pivot, which scales the pivot, updates the later vectors and returns the
+    // norm and overlaps of the next pivot together with <r_i, r_i> of the finished one
     std::vector<int> null_params;
+    std::vector<double> final_dot(nN, -1.0); // <r_i, r_i> after the step, where known
+    std::vector<double> row;                  // {<r_i, r_i>, <r_i, r_j> for j > i} of the current pivot
     for (size_t i = 0; i < nN; ++i) {
-      CVecRef<R> later(wresidual.begin() + i, wresidual.end());
-      const auto row = m_dense->gemm_inner(CVecRef<R>{std::cref(wresidual[i].get())}, later); // 1 x (nN - i)
-      const double norm = std::sqrt(std::abs(row(0, 0)));
+      VecRef<R> later(wresidual.begin() + i + 1, wresidual.end());
+      if (row.size() != nN - i) {
+        const auto g = m_dense->gemm_inner(CVecRef<R>{std::cref(wresidual[i].get())},
+                                           CVecRef<R>(wresidual.begin() + i, wresidual.end())); // 1 x (nN - i)
+        row.assign(g.data().begin(), g.data().end());
+      }
+      const double norm = std::sqrt(std::abs(row[0]));
       if (norm > this->propose_rspace_norm_thresh) {
         std::vector<double> o(nN - i - 1);
         for (size_t j = 0; j < o.size(); ++j)
-          o[j] = row(0, j + 1) / norm; // <r_i / |r_i|, r_j>
-        m_dense->mgs_step(1. / norm, wresidual[i].get(), o, VecRef<R>(wresidual.begin() + i + 1, wresidual.end()));
+          o[j] = row[j + 1] / norm; // <r_i / |r_i|, r_j>
+        if (later.size() <= ArrayHandlerCUDA::max_mgs_step_dots) {
+          const auto dots = m_dense->mgs_step_dots(1. / norm, wresidual[i].get(), o, later);
+          final_dot[i] = dots[0];
+          row.assign(dots.begin() + 1, dots.end());
+        } else {
+          m_dense->mgs_step(1. / norm, wresidual[i].get(), o, later);
+          row.clear();
+        }
       } else {
         null_params.push_back(int(i));
+        row.clear();
       }
     }
+    {
+      auto sorted = null_params;
+      std::sort(sorted.begin(), sorted.end(), std::greater<int>());
+      for (auto i : sorted)
+        final_dot.erase(final_dot.begin() + i);
+    }
     its::util::delete_parameters(null_params, wresidual);
-    normalise_set(wresidual);
+    // closing normalise(): every survivor was scaled by 1/|r_i| in its own step, so its length is 1 to rounding and the
+    // factor 1/sqrt(<r_i, r_i>) differs from 1 by an ulp or two; the pass is made only for a vector that needs more
+    {
+      std::vector<double> alpha(wresidual.size(), 1.0);
+      bool needed = false;
+      for (size_t i = 0; i < wresidual.size(); ++i) {
+        const double d = final_dot[i] >= 0 ? final_dot[i]
+                                           : m_dense->self_dots(CVecRef<R>{std::cref(wresidual[i].get())})[0];
+        const double norm = std::sqrt(std::abs(d));
+        if (norm > 1.0e-14)
+          alpha[i] = 1. / norm;
+        needed = needed || std::abs(alpha[i] - 1.0) > 8 * std::numeric_limits<double>::epsilon();
+      }
+      if (needed)
+        m_dense->scal_batch(alpha, wresidual);
+    }
     auto new_working_set = det::get_new_working_set(this->working_set(), its::cwrap(residuals), its::cwrap(wresidual));
     for (size_t i = 0; i < wresidual.size(); ++i) {
       if (m_in_fused_solve) // the residual buffers are scratch until the next action() fills them: no copy needed

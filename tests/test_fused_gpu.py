@@ -80,6 +80,34 @@ def test_davidson_residual_kernel_equals_the_unfused_sequence(ctx, oracle, n, k,
     assert np.array_equal(host(q), Q) and np.array_equal(host(a), A), "inputs must not be touched"
 
 
+@pytest.mark.parametrize("n,m", [(1, 0), (2, 1), (33, 2), (1000, 3), (4097, 4), (50001, 7), (20001, 16)])
+def test_mgs_step_dots_equals_step_then_dots(ctx, oracle, n, m):
+    """itsolv_mgs_step_dots_f64: vectors bit for bit as scal + axpys; the returned products to 1e-12 of |x||y|"""
+    rng = np.random.default_rng(n + m)
+    R = rng.standard_normal((m + 1, n))
+    ov = rng.standard_normal(m)
+    rs = dev_rows(R)
+    dots = ctx.mgs_step_dots(0.731, rs[0], ov, rs[1:])
+    pivot = oracle.c.scal(0.731, R[0].copy())
+    want = np.stack([pivot] + [oracle.c.axpy(-ov[j], pivot.copy(), R[j + 1].copy()) for j in range(m)])
+    assert np.array_equal(host(rs), want)
+    norms = np.linalg.norm(want, axis=1)
+    assert abs(dots[0] - oracle.c.dot(want[0], want[0])) <= 1e-12 * norms[0] ** 2
+    for t in range(m):
+        assert abs(dots[1 + t] - oracle.c.dot(want[1], want[1 + t])) <= 1e-12 * norms[1] * norms[1 + t]
+
+
+@pytest.mark.parametrize("n,k,m", [(1, 1, 1), (33, 3, 2), (1000, 5, 4), (50001, 12, 7), (4097, 20, 16), (3001, 4, 19)])
+def test_gemm_outer_scaled_equals_scal_then_gemm_outer(ctx, oracle, n, k, m):
+    rng = np.random.default_rng(7 * n + k + m)
+    X, Y = rng.standard_normal((k, n)), rng.standard_normal((m, n))
+    alpha, scale = rng.standard_normal((k, m)), rng.standard_normal(m)
+    xs, ys = dev_rows(X), dev_rows(Y)
+    ctx.gemm_outer_scaled(alpha, xs, ys, scale)
+    scaled = np.stack([oracle.c.scal(scale[j], Y[j].copy()) for j in range(m)])
+    assert np.array_equal(host(ys), oracle.c.gemm_outer(alpha, X, scaled, fma=True))
+
+
 def test_davidson_residual_rejects_aliased_outputs(ctx):
     q = [torch.ones(64, dtype=torch.float64, device="cuda") for _ in range(2)]
     a = [torch.ones(64, dtype=torch.float64, device="cuda") for _ in range(2)]
