@@ -91,6 +91,8 @@ struct itsolv_ctx {
   int opt_go_cols = 0;    // gemm_outer columns per thread (0 = auto)
   int opt_go_ctas = 0;    // gemm_outer CTAs per SM
   int opt_blas1_ctas = 0; // CTAs per SM for streaming kernels
+  int opt_ds_ring = 0;    // davidson_residual: <0 never use the cp.async ring kernel
+  int opt_stream_ring = 0; // gemm_outer / mgs_step_dots: <0 never use the cp.async ring kernels
   int opt_p2p_allreduce = 0; // <0: use ncclAllReduce even when the peer buffers are mapped
 
   std::vector<std::pair<const void*, size_t>> smem_optin; // kernel -> largest dynamic shared memory size opted in

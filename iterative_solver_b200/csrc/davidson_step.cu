@@ -179,13 +179,38 @@ __device__ __forceinline__ void ds_rows(const DsParams& p, const double* __restr
   }
 }
 
+//! CTA fold of the running sums, per-CTA partials laid out [<r,r> of the m roots | <out_r,out_r> of the m roots], finish
+template <int MJ, class Norms>
+__device__ __forceinline__ void ds_finish(const DsParams& p, const Norms& nrm) {
+  __shared__ double s_part[kDsThreads / 32][2 * MJ];
+  __shared__ int s_is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int b = 0; b < 2 * MJ; ++b) {
+    double v = nrm.get(b);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+      v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0)
+      s_part[warp][b] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * p.m) {
+    const int half = threadIdx.x / p.m, j = threadIdx.x % p.m;
+    double sum = 0.0;
+#pragma unroll
+    for (int w = 0; w < kDsThreads / 32; ++w)
+      sum += s_part[w][half * MJ + j];
+    p.fin.partials[size_t(blockIdx.x) * (2 * p.m) + threadIdx.x] = sum;
+  }
+  gi_finalize(p.fin, 2 * p.m, &s_is_last);
+}
+
 template <int MJ, bool VEC>
 __global__ void __launch_bounds__(kDsThreads, MJ <= 2 ? 3 : 2)
     davidson_residual_kernel(const __grid_constant__ DsParams p) {
   extern __shared__ __align__(16) double sc[]; // k x ld coefficients [, 2 MJ x blockDim.x running sums]
   constexpr bool kSmemNorms = MJ > 8;
-  __shared__ double s_part[kDsThreads / 32][2 * MJ];
-  __shared__ int s_is_last;
   for (int e = threadIdx.x; e < p.k * p.ld; e += blockDim.x)
     sc[e] = p.coef[e];
   DsNorms<MJ, kSmemNorms> nrm;
@@ -203,33 +228,150 @@ __global__ void __launch_bounds__(kDsThreads, MJ <= 2 ? 3 : 2)
     for (size_t r = tid; r < p.n; r += nthreads)
       ds_rows<MJ, double>(p, sc, r, nrm);
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int b = 0; b < 2 * MJ; ++b) {
-    double v = nrm.get(b);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
-      v += __shfl_down_sync(0xffffffffu, v, off);
-    if (lane == 0)
-      s_part[warp][b] = v;
-  }
+  ds_finish<MJ>(p, nrm);
+}
+
+// ---- the same pass with a thread-private cp.async ring --------------------------------------------------------------
+// The kernel above keeps 2U loads per thread in flight only while it waits for them; during the arithmetic, the divisions
+// and the stores of a row nothing is outstanding, and with the register budget of 16 warps per SM the average falls short
+// of the ~45 KB per SM that HBM3e needs (measured 4.6 TB/s at k = 4..16). Here every thread copies the operands of its
+// NEXT S-1 trips (U subspace vectors and their actions, plus the diagonal with the first trip of a row) into its own
+// slots of a shared-memory ring with cp.async (LDGSTS, 16 bytes each, no registers, no barriers: slots are private) and
+// computes the current trip out of shared memory, so (S-1) 2U 16-byte loads per thread stay outstanding throughout.
+constexpr int kRingU = 2; // subspace vectors (and as many actions) per trip
+constexpr int kRingS = 4; // ring depth: S-1 trips are in flight while one is consumed
+constexpr int kRingSlots = 2 * kRingU + 1;
+static size_t ds_ring_bytes() { return size_t(kRingS) * kRingSlots * kDsThreads * sizeof(double2); }
+
+__device__ __forceinline__ void ds_cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void ds_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void ds_cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int MJ>
+__global__ void __launch_bounds__(kDsThreads, 2) davidson_residual_ring_kernel(const __grid_constant__ DsParams p) {
+  extern __shared__ __align__(16) double sc[]; // k x ld coefficients, then the ring [S][2U+1][blockDim.x] of double2
+  constexpr int U = kRingU, S = kRingS;
+  for (int e = threadIdx.x; e < p.k * p.ld; e += blockDim.x)
+    sc[e] = p.coef[e];
+  double2* ring = reinterpret_cast<double2*>(sc + ((p.k * p.ld + 1) & ~1)) + threadIdx.x;
+  DsNorms<MJ, false> nrm;
+  nrm.init(nullptr);
   __syncthreads();
-  // per-CTA sums, laid out [<r,r> of the m roots | <out_r,out_r> of the m roots]
-  if (threadIdx.x < 2 * p.m) {
-    const int half = threadIdx.x / p.m, j = threadIdx.x % p.m;
-    double sum = 0.0;
+  const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = size_t(gridDim.x) * blockDim.x;
+  const size_t npairs = p.n / 2;
+  const int nchunks = (p.k + U - 1) / U;
+  const size_t my_rows = tid < npairs ? (npairs - tid + nthreads - 1) / nthreads : 0;
+  const size_t trips = my_rows * size_t(nchunks);
+  // cursor of the copies
+  size_t it = 0, ir = tid;
+  int ic = 0, is = 0;
+  auto issue = [&]() {
+    if (it < trips) {
+      double2* st = ring + size_t(is) * (kRingSlots * kDsThreads);
+      const int i0 = ic * U;
 #pragma unroll
-    for (int w = 0; w < kDsThreads / 32; ++w)
-      sum += s_part[w][half * MJ + j];
-    p.fin.partials[size_t(blockIdx.x) * (2 * p.m) + threadIdx.x] = sum;
+      for (int u = 0; u < U; ++u)
+        if (i0 + u < p.k) {
+          ds_cp_async16(st + u * kDsThreads, reinterpret_cast<const double2*>(p.q[i0 + u]) + ir);
+          ds_cp_async16(st + (U + u) * kDsThreads, reinterpret_cast<const double2*>(p.a[i0 + u]) + ir);
+        }
+      if (ic == 0 && p.diag)
+        ds_cp_async16(st + 2 * U * kDsThreads, reinterpret_cast<const double2*>(p.diag) + ir);
+      if (++ic == nchunks) {
+        ic = 0;
+        ir += nthreads;
+      }
+      is = is + 1 == S ? 0 : is + 1;
+      ++it;
+    }
+    ds_cp_async_commit();
+  };
+#pragma unroll
+  for (int d = 0; d < S - 1; ++d)
+    issue();
+  using Ops = DsOps<double2>;
+  double2 ax[MJ], ar[MJ];
+  double2 dg = Ops::zero();
+  size_t cr = tid;
+  int cc = 0, cs = 0;
+  for (size_t t = 0; t < trips; ++t) {
+    issue();
+    ds_cp_async_wait<S - 1>();
+    const double2* st = ring + size_t(cs) * (kRingSlots * kDsThreads);
+    if (cc == 0) {
+#pragma unroll
+      for (int b = 0; b < MJ; ++b) {
+        ax[b] = Ops::zero();
+        ar[b] = Ops::zero();
+      }
+      if (p.diag)
+        dg = st[2 * U * kDsThreads];
+    }
+    const int i0 = cc * U;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i0 + u < p.k) {
+        const double2 qv = st[u * kDsThreads], av = st[(U + u) * kDsThreads];
+        const double* cu = sc + size_t(i0 + u) * p.ld;
+#pragma unroll
+        for (int b = 0; b < MJ; ++b) {
+          const double c = cu[b];
+          Ops::fma_to(ax[b], c, qv);
+          Ops::fma_to(ar[b], c, av);
+        }
+      }
+    if (cc == nchunks - 1) {
+#pragma unroll
+      for (int b = 0; b < MJ; ++b) {
+        if (b < p.m) {
+          if (p.write_x)
+            reinterpret_cast<double2*>(p.out_x[b])[cr] = ax[b];
+          double2 res = Ops::residual(ar[b], -p.lambda[b], ax[b]);
+          nrm.add(b, res);
+          if (p.diag) {
+            res = Ops::precondition(res, dg, p.shift[b]);
+            nrm.add(MJ + b, res);
+          }
+          reinterpret_cast<double2*>(p.out_r[b])[cr] = res;
+        }
+      }
+      cr += nthreads;
+      cc = 0;
+    } else {
+      ++cc;
+    }
+    cs = cs + 1 == S ? 0 : cs + 1;
   }
-  gi_finalize(p.fin, 2 * p.m, &s_is_last);
+  ds_cp_async_wait<0>();
+  if ((p.n & 1) && tid == 0)
+    ds_rows<MJ, double>(p, sc, p.n - 1, nrm);
+  ds_finish<MJ>(p, nrm);
 }
 
 using DsKernel = void (*)(const DsParams);
 template <int MJ>
 static DsKernel ds_pick_vec(bool vec) {
   return vec ? davidson_residual_kernel<MJ, true> : davidson_residual_kernel<MJ, false>;
+}
+static DsKernel ds_pick_ring(int mj) {
+  switch (mj) {
+  case 1:
+    return davidson_residual_ring_kernel<1>;
+  case 2:
+    return davidson_residual_ring_kernel<2>;
+  case 4:
+    return davidson_residual_ring_kernel<4>;
+  case 8:
+    return davidson_residual_ring_kernel<8>;
+  }
+  return nullptr;
 }
 static DsKernel ds_pick(int mj, bool vec) {
   switch (mj) {
@@ -321,12 +463,15 @@ int itsolv_davidson_residual_f64(itsolv_ctx* ctx, const double* coef, int k, int
       p.coef = reinterpret_cast<const double*>(d);
       if (mj == 16)
         vec = false; // 16 roots: one row per thread keeps the 32 running sums in registers at two CTAs per SM
-      DsKernel kernel = ds_pick(mj, vec);
+      const bool ring = vec && mj <= 8 && ctx->opt_ds_ring >= 0 &&
+                        ((cbytes + 15) & ~size_t(15)) + ds_ring_bytes() <= size_t(ctx->max_smem_optin) / 2 - 1024;
+      DsKernel kernel = ring ? ds_pick_ring(mj) : ds_pick(mj, vec);
       ITSOLV_REQUIRE(kernel != nullptr, "davidson_residual: root tile not instantiated");
-      const size_t smem = cbytes + (mj > 8 ? size_t(2 * mj) * kDsThreads * sizeof(double) : 0);
+      const size_t smem = ring ? ((cbytes + 15) & ~size_t(15)) + ds_ring_bytes()
+                               : cbytes + (mj > 8 ? size_t(2 * mj) * kDsThreads * sizeof(double) : 0);
       if (ensure_dynamic_smem(ctx, reinterpret_cast<const void*>(kernel), smem))
         return 1;
-      const int per_sm = mj <= 2 ? 3 : 2;
+      const int per_sm = ring ? 2 : (mj <= 2 ? 3 : 2);
       const size_t units = vec ? n / 2 : n;
       const int grid = int(std::max<size_t>(
           1, std::min<size_t>((units + kDsThreads - 1) / kDsThreads, size_t(ctx->num_sms) * per_sm)));

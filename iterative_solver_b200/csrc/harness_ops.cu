@@ -89,21 +89,55 @@ __device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
                : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_elem(double* dst, const double* src) { cp_async8(dst, src); }
+__device__ __forceinline__ void cp_async_elem(long long* dst, const long long* src) { cp_async8(dst, src); }
+__device__ __forceinline__ void cp_async_elem(int* dst, const int* src) { cp_async4(dst, src); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+/*!
+ * Asynchronous copy of g[lo, hi) into shared memory by the whole CTA, in 16-byte pieces where the global address allows
+ * and single elements at the two ends. The element g[i] lands at s[i - base(lo)], where base(lo) <= lo is the index of
+ * the 16-byte aligned element at or below lo (so that global and shared addresses are aligned alike); `s` must be
+ * 16-byte aligned and have 16/sizeof(T) - 1 elements of slack. Returns base(lo).
+ */
+template <class T>
+__device__ __forceinline__ long long stage_range(T* s, const T* __restrict__ g, long long lo, long long hi, int t) {
+  constexpr int PER = 16 / int(sizeof(T));
+  const long long off = (long long)((reinterpret_cast<uintptr_t>(g) / sizeof(T)) % PER); // (i + off) % PER == 0: aligned
+  const long long base = lo - ((lo + off) % PER + PER) % PER;
+  const long long alo = lo + ((PER - (lo + off) % PER) % PER + PER) % PER; // first aligned index >= lo
+  const long long ahi = hi - ((hi + off) % PER + PER) % PER;               // last aligned index <= hi
+  if (alo >= ahi) {
+    for (long long i = lo + t; i < hi; i += kCsrRows)
+      cp_async_elem(&s[i - base], &g[i]);
+    return base;
+  }
+  if (t < alo - lo)
+    cp_async_elem(&s[lo + t - base], &g[lo + t]);
+  if (t < hi - ahi)
+    cp_async_elem(&s[ahi + t - base], &g[ahi + t]);
+  for (long long i = alo + (long long)PER * t; i < ahi; i += (long long)PER * kCsrRows)
+    cp_async16(&s[i - base], &g[i]);
+  return base;
+}
+
 static size_t csr_smem_bytes(int w, int b) {
-  const int win = kCsrRows + 2 * b;
-  return size_t(kCsrChunk) * 12 + size_t(w) * win * 8 + size_t(kCsrRows + 2) * 8;
+  const int win = kCsrRows + 2 * b + 2;
+  return size_t(kCsrChunk + 4) * 12 + size_t(w) * win * 8 + size_t(kCsrRows + 4) * 8;
 }
 
 template <int W>
 __global__ void __launch_bounds__(kCsrRows) csr_apply_multi_kernel(const __grid_constant__ CsrMultiParams p) {
   extern __shared__ __align__(16) unsigned char csr_smem[];
-  const int win = kCsrRows + 2 * p.b;
-  double* s_val = reinterpret_cast<double*>(csr_smem);
-  double* s_x = s_val + kCsrChunk;                                  // [W][win]
-  long long* s_rp = reinterpret_cast<long long*>(s_x + W * win);    // [kCsrRows + 1]
-  int* s_col = reinterpret_cast<int*>(s_rp + kCsrRows + 2);         // [kCsrChunk]
+  const int win = kCsrRows + 2 * p.b + 2;                             // per-vector stride of the x windows (even)
+  double* s_val = reinterpret_cast<double*>(csr_smem);                // [kCsrChunk + 4]
+  double* s_x = s_val + kCsrChunk + 4;                                // [W][win]
+  long long* s_rp = reinterpret_cast<long long*>(s_x + W * win);      // [kCsrRows + 4]
+  int* s_col = reinterpret_cast<int*>(s_rp + kCsrRows + 4);           // [kCsrChunk + 4]
   const int t = threadIdx.x;
   const long long nblocks = (p.n + kCsrRows - 1) / kCsrRows;
   long long blk = blockIdx.x;
@@ -117,20 +151,24 @@ __global__ void __launch_bounds__(kCsrRows) csr_apply_multi_kernel(const __grid_
     const long long r0 = blk * kCsrRows;
     const int nrows = int(r0 + kCsrRows < p.n ? kCsrRows : p.n - r0);
     // row pointers of the block and the x window [r0 - b, r0 + nrows + b) of every vector
-    cp_async8(&s_rp[t], &p.row_ptr[r0 + (t < nrows ? t : nrows)]);
-    if (t == 0)
-      cp_async8(&s_rp[nrows], &p.row_ptr[r0 + nrows]);
-    for (int i = t; i < nrows + 2 * p.b; i += kCsrRows) {
-      const long long l = r0 - p.b + i; // local row of the shard
+    const long long rp_base = stage_range(s_rp, p.row_ptr, r0, r0 + nrows + 1, t);
+    const long long l0 = r0 - p.b > 0 ? r0 - p.b : 0;                              // rows of the window held locally
+    const long long l1 = r0 + nrows + p.b < p.n ? r0 + nrows + p.b : p.n;
+    // window position of local row l is l - xbase[k]; rows below the shard's first row need room in front of row 0
+    const int front = r0 < p.b ? int((p.b - r0 + 1) & ~1LL) : 0;
+    long long xbase[W];
 #pragma unroll
-      for (int k = 0; k < W; ++k) {
-        if (k < p.w) {
-          if (l >= 0 && l < p.n)
-            cp_async8(&s_x[k * win + i], &p.x[k][l]);
-          else if (l < 0)
-            s_x[k * win + i] = p.x_lo[k] ? p.x_lo[k][p.b + l] : 0.0;
-          else
-            s_x[k * win + i] = p.x_hi[k] ? p.x_hi[k][l - p.n] : 0.0;
+    for (int k = 0; k < W; ++k) {
+      xbase[k] = 0;
+      if (k < p.w) {
+        xbase[k] = stage_range(s_x + k * win + front, p.x[k], l0, l1, t) - front;
+        // halo rows outside the shard (beyond the global ends they are never referenced: zero)
+        for (int i = t; i < p.b; i += kCsrRows) {
+          const long long below = r0 - p.b + i, above = r0 + nrows + i;
+          if (below < 0)
+            s_x[k * win + (below - xbase[k])] = p.x_lo[k] ? p.x_lo[k][p.b + below] : 0.0;
+          if (above >= p.n)
+            s_x[k * win + (above - xbase[k])] = p.x_hi[k] ? p.x_hi[k][above - p.n] : 0.0;
         }
       }
     }
@@ -146,34 +184,30 @@ __global__ void __launch_bounds__(kCsrRows) csr_apply_multi_kernel(const __grid_
 #pragma unroll
     for (int k = 0; k < W; ++k)
       acc[k] = 0.0;
-    const long long wlo = p.off + r0 - p.b; // global column of s_x[.][0]
-    for (long long c0 = e0; c0 < e1 || c0 == e0; c0 += kCsrChunk) {
+    for (long long c0 = e0;; c0 += kCsrChunk) {
       const long long c1 = c0 + kCsrChunk < e1 ? c0 + kCsrChunk : e1;
       if (c0 > e0)
         __syncthreads(); // the previous round's entries have been consumed
-      for (long long e = c0 + t; e < c1; e += kCsrRows) {
-        cp_async8(&s_val[e - c0], &p.val[e]);
-        cp_async4(&s_col[e - c0], &p.col[e]);
-      }
+      const long long vbase = stage_range(s_val, p.val, c0, c1, t);
+      const long long cbase = stage_range(s_col, p.col, c0, c1, t);
       cp_async_wait_all();
       __syncthreads();
       if (t < nrows) {
-        const long long my0 = s_rp[t], my1 = s_rp[t + 1];
+        const long long my0 = s_rp[r0 + t - rp_base], my1 = s_rp[r0 + t + 1 - rp_base];
         const long long lo = my0 > c0 ? my0 : c0, hi = my1 < c1 ? my1 : c1;
         for (long long e = lo; e < hi; ++e) {
-          const double a = s_val[e - c0];
-          const long long c = s_col[e - c0];
-          const long long wi = c - wlo;
-          if (wi >= 0 && wi < nrows + 2 * p.b) {
+          const double a = s_val[e - vbase];
+          const long long l = (long long)s_col[e - cbase] - p.off; // local row of the column
+          if (l >= r0 - p.b && l < r0 + nrows + p.b) {
 #pragma unroll
             for (int k = 0; k < W; ++k)
               if (k < p.w)
-                acc[k] = __dadd_rn(acc[k], __dmul_rn(a, s_x[k * win + int(wi)]));
+                acc[k] = __dadd_rn(acc[k], __dmul_rn(a, s_x[k * win + (l - xbase[k])]));
           } else {
 #pragma unroll
             for (int k = 0; k < W; ++k)
               if (k < p.w)
-                acc[k] = __dadd_rn(acc[k], __dmul_rn(a, x_at(c, p.off, p.n, p.b, p.x[k], p.x_lo[k], p.x_hi[k])));
+                acc[k] = __dadd_rn(acc[k], __dmul_rn(a, x_at(l + p.off, p.off, p.n, p.b, p.x[k], p.x_lo[k], p.x_hi[k])));
           }
         }
       }

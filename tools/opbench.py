@@ -50,7 +50,7 @@ def main():
     results = []
 
     def run(name, bytes_per_call, fn):
-        if args.only and args.only not in name:
+        if args.only and not any(pat in name for pat in args.only.split(",")):
             return
         fn()  # warm-up (also sets function attributes)
         fn()
@@ -133,6 +133,35 @@ def run_all(ctx, lib, args, n, nvec, take, run, _ptr_array, _dbl):
         if (k + m) > nvec:
             continue
         run(f"gemm_outer[{k}x{m}]", 8 * n * (k + 2 * m), go(k, m))
+
+    # ---- kernels of the fused driver path
+    def ds(k, m):
+        coef = np.random.default_rng(1).standard_normal((k, m)) * 1e-2
+        lam = np.arange(1, m + 1) + 0.5
+
+        def f():
+            ctx.davidson_residual(coef, take(k), take(k), lam, take(m), diag=diag)
+        return f
+
+    for k, m in [(4, 4), (8, 4), (16, 4), (24, 8), (24, 16), (40, 16)]:
+        if 2 * k + m > nvec:
+            continue
+        run(f"davidson_residual[{k}x{m}]", 8 * n * (2 * k + m + 1), ds(k, m))
+    for m in (0, 1, 3, 7, 15):
+        run(f"mgs_step_dots[1+{m}]", 16 * n * (m + 1),
+            lambda m=m: (lambda v: ctx.mgs_step_dots(1.0000001, v[0], [1e-9] * m, v[1:]))(take(m + 1)))
+    for k, m in [(4, 4), (12, 4), (24, 16)]:
+        alpha = np.random.default_rng(2).standard_normal((k, m)) * 1e-3
+        run(f"gemm_outer_scaled[{k}x{m}]", 8 * n * (k + 2 * m),
+            lambda k=k, m=m, alpha=alpha: ctx.gemm_outer_scaled(alpha, take(k), take(m), [1.0000001] * m))
+    # stored CSR operator, banded with 9 entries per row, all vectors of a working set in one pass over the matrix
+    from iterative_solver_b200 import harness as H
+    row_ptr, col, val, _ = H.banded_csr_host(n, 4, 1e-3)
+    d_rp, d_col, d_val = torch.from_numpy(row_ptr).cuda(), torch.from_numpy(col).cuda(), torch.from_numpy(val).cuda()
+    nnz = int(row_ptr[-1])
+    for w in (1, 4, 8):
+        run(f"spmv_csr[w={w}]", 12 * nnz + 8 * (n + 1) + 16 * n * w,
+            lambda w=w: ctx.csr_apply_multi(d_rp.data_ptr(), d_col.data_ptr(), d_val, take(w), take(w), n, 0, 4))
 
 
 if __name__ == "__main__":
