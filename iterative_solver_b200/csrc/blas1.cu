@@ -128,15 +128,15 @@ __global__ void __launch_bounds__(kThreads, 4) precondition_kernel(const __grid_
           double2* rk = reinterpret_cast<double2*>(prm.r[k]);
           double2 v = rk[p];
           const double s = prm.shift[k];
-          v.x = __ddiv_rn(v.x, __dadd_rn(__dsub_rn(d.x, s), 1e-15));
-          v.y = __ddiv_rn(v.y, __dadd_rn(__dsub_rn(d.y, s), 1e-15));
+          v.x = div_rn(v.x, __dadd_rn(__dsub_rn(d.x, s), 1e-15));
+          v.y = div_rn(v.y, __dadd_rn(__dsub_rn(d.y, s), 1e-15));
           rk[p] = v;
         }
       },
       [&](size_t i) {
         const double d = diag[i];
         for (int k = 0; k < w; ++k)
-          prm.r[k][i] = __ddiv_rn(prm.r[k][i], __dadd_rn(__dsub_rn(d, prm.shift[k]), 1e-15));
+          prm.r[k][i] = div_rn(prm.r[k][i], __dadd_rn(__dsub_rn(d, prm.shift[k]), 1e-15));
       });
 }
 

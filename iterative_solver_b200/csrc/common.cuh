@@ -142,4 +142,19 @@ bool comm_peers(itsolv_ctx* ctx, GiPeers* peers);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+#ifdef __CUDACC__
+/*!
+ * IEEE round-to-nearest quotient, bit for bit what `/` gives on the host. __ddiv_rn's inline sequence (reciprocal
+ * estimate + Newton steps + remainder correction, ~15 instructions) leaves every numerator below 2^-120 - zero
+ * included - to a generic routine of ~60 instructions. Residual vectors are full of exact zeros wherever the operator has
+ * not coupled a row to the starting vectors yet, so 0 / x (x finite or infinite, not zero, not NaN) is answered here:
+ * a zero with the sign of the quotient.
+ */
+__device__ __forceinline__ double div_rn(double num, double den) {
+  if (num == 0.0 && den != 0.0 && den == den)
+    return __hiloint2double((__double2hiint(num) ^ __double2hiint(den)) & 0x80000000, 0);
+  return __ddiv_rn(num, den);
+}
+#endif
+
 } // namespace itsolv

@@ -64,8 +64,8 @@ struct DsOps<double2> {
     acc = fma(r.y, r.y, acc);
   }
   static __device__ __forceinline__ double2 precondition(const double2& r, const double2& d, double shift) {
-    return make_double2(__ddiv_rn(r.x, __dadd_rn(__dsub_rn(d.x, shift), 1e-15)),
-                        __ddiv_rn(r.y, __dadd_rn(__dsub_rn(d.y, shift), 1e-15)));
+    return make_double2(div_rn(r.x, __dadd_rn(__dsub_rn(d.x, shift), 1e-15)),
+                        div_rn(r.y, __dadd_rn(__dsub_rn(d.y, shift), 1e-15)));
   }
 };
 template <>
@@ -77,7 +77,7 @@ struct DsOps<double> {
   }
   static __device__ __forceinline__ void square_to(double& acc, const double& r) { acc = fma(r, r, acc); }
   static __device__ __forceinline__ double precondition(const double& r, const double& d, double shift) {
-    return __ddiv_rn(r, __dadd_rn(__dsub_rn(d, shift), 1e-15));
+    return div_rn(r, __dadd_rn(__dsub_rn(d, shift), 1e-15));
   }
 };
 

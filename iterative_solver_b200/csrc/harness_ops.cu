@@ -99,30 +99,26 @@ __device__ __forceinline__ void cp_async_elem(int* dst, const int* src) { cp_asy
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 /*!
- * Asynchronous copy of g[lo, hi) into shared memory by the whole CTA, in 16-byte pieces where the global address allows
- * and single elements at the two ends. The element g[i] lands at s[i - base(lo)], where base(lo) <= lo is the index of
- * the 16-byte aligned element at or below lo (so that global and shared addresses are aligned alike); `s` must be
- * 16-byte aligned and have 16/sizeof(T) - 1 elements of slack. Returns base(lo).
+ * Asynchronous copy of g0[0, count) into shared memory by the whole CTA, in 16-byte pieces where the global address
+ * allows and single elements at the two ends. Element j lands at s[j + mis], where mis (returned) is the misalignment of
+ * g0 in elements, so that global and shared addresses are aligned alike; `s` must be 16-byte aligned with
+ * 16/sizeof(T) - 1 elements of slack. 32-bit index arithmetic throughout.
  */
 template <class T>
-__device__ __forceinline__ long long stage_range(T* s, const T* __restrict__ g, long long lo, long long hi, int t) {
+__device__ __forceinline__ int stage_range(T* s, const T* __restrict__ g0, int count, int t) {
   constexpr int PER = 16 / int(sizeof(T));
-  const long long off = (long long)((reinterpret_cast<uintptr_t>(g) / sizeof(T)) % PER); // (i + off) % PER == 0: aligned
-  const long long base = lo - ((lo + off) % PER + PER) % PER;
-  const long long alo = lo + ((PER - (lo + off) % PER) % PER + PER) % PER; // first aligned index >= lo
-  const long long ahi = hi - ((hi + off) % PER + PER) % PER;               // last aligned index <= hi
-  if (alo >= ahi) {
-    for (long long i = lo + t; i < hi; i += kCsrRows)
-      cp_async_elem(&s[i - base], &g[i]);
-    return base;
-  }
-  if (t < alo - lo)
-    cp_async_elem(&s[lo + t - base], &g[lo + t]);
-  if (t < hi - ahi)
-    cp_async_elem(&s[ahi + t - base], &g[ahi + t]);
-  for (long long i = alo + (long long)PER * t; i < ahi; i += (long long)PER * kCsrRows)
-    cp_async16(&s[i - base], &g[i]);
-  return base;
+  const int mis = int((reinterpret_cast<uintptr_t>(g0) / sizeof(T)) & (PER - 1));
+  const int head = min((PER - mis) & (PER - 1), count);
+  const int body = (count - head) & ~(PER - 1);
+  T* sd = s + mis;
+  if (t < head)
+    cp_async_elem(sd + t, g0 + t);
+  for (int j = head + PER * t; j < head + body; j += PER * kCsrRows)
+    cp_async16(sd + j, g0 + j);
+  const int tail = head + body;
+  if (t < count - tail)
+    cp_async_elem(sd + tail + t, g0 + tail + t);
+  return mis;
 }
 
 static size_t csr_smem_bytes(int w, int b) {
@@ -133,7 +129,8 @@ static size_t csr_smem_bytes(int w, int b) {
 template <int W>
 __global__ void __launch_bounds__(kCsrRows) csr_apply_multi_kernel(const __grid_constant__ CsrMultiParams p) {
   extern __shared__ __align__(16) unsigned char csr_smem[];
-  const int win = kCsrRows + 2 * p.b + 2;                             // per-vector stride of the x windows (even)
+  const int b = p.b;
+  const int win = kCsrRows + 2 * b + 2;                               // per-vector stride of the x windows (even)
   double* s_val = reinterpret_cast<double*>(csr_smem);                // [kCsrChunk + 4]
   double* s_x = s_val + kCsrChunk + 4;                                // [W][win]
   long long* s_rp = reinterpret_cast<long long*>(s_x + W * win);      // [kCsrRows + 4]
@@ -150,27 +147,22 @@ __global__ void __launch_bounds__(kCsrRows) csr_apply_multi_kernel(const __grid_
   for (; blk < nblocks; blk += gridDim.x) {
     const long long r0 = blk * kCsrRows;
     const int nrows = int(r0 + kCsrRows < p.n ? kCsrRows : p.n - r0);
-    // row pointers of the block and the x window [r0 - b, r0 + nrows + b) of every vector
-    const long long rp_base = stage_range(s_rp, p.row_ptr, r0, r0 + nrows + 1, t);
-    const long long l0 = r0 - p.b > 0 ? r0 - p.b : 0;                              // rows of the window held locally
-    const long long l1 = r0 + nrows + p.b < p.n ? r0 + nrows + p.b : p.n;
-    // window position of local row l is l - xbase[k]; rows below the shard's first row need room in front of row 0
-    const int front = r0 < p.b ? int((p.b - r0 + 1) & ~1LL) : 0;
-    long long xbase[W];
+    const int rp_mis = stage_range(s_rp, p.row_ptr + r0, nrows + 1, t);
+    // x window: local rows [r0 - b, r0 + nrows + b); `below`/`above` of the b rows on either side lie inside the shard
+    const int below = int(r0 < b ? r0 : b);
+    const int above = int(p.n - (r0 + nrows) < b ? p.n - (r0 + nrows) : b);
+    const int front = (b - below + 1) & ~1; // room for the rows below the shard (first block only), kept even
+    int xpos[W];                            // window position of local row l in vector k: (l - (r0 - b)) + xpos[k]
 #pragma unroll
     for (int k = 0; k < W; ++k) {
-      xbase[k] = 0;
-      if (k < p.w) {
-        xbase[k] = stage_range(s_x + k * win + front, p.x[k], l0, l1, t) - front;
-        // halo rows outside the shard (beyond the global ends they are never referenced: zero)
-        for (int i = t; i < p.b; i += kCsrRows) {
-          const long long below = r0 - p.b + i, above = r0 + nrows + i;
-          if (below < 0)
-            s_x[k * win + (below - xbase[k])] = p.x_lo[k] ? p.x_lo[k][p.b + below] : 0.0;
-          if (above >= p.n)
-            s_x[k * win + (above - xbase[k])] = p.x_hi[k] ? p.x_hi[k][above - p.n] : 0.0;
-        }
-      }
+      double* sx = s_x + k * win;
+      const int mis = stage_range(sx + front, p.x[k] + (r0 - below), below + nrows + above, t);
+      xpos[k] = front + mis - (b - below);
+      // rows outside the shard: halo vectors, or zero beyond the global ends (never referenced)
+      if (t < b - below)
+        sx[xpos[k] + t] = p.x_lo[k] ? p.x_lo[k][(r0 - b + t) + b] : 0.0;
+      if (t < b - above)
+        sx[xpos[k] + b + nrows + above + t] = p.x_hi[k] ? p.x_hi[k][(r0 + nrows + above + t) - p.n] : 0.0;
     }
     // the next block's entry range, requested now and used after this block's arithmetic
     long long ne0 = 0, ne1 = 0;
@@ -184,41 +176,42 @@ __global__ void __launch_bounds__(kCsrRows) csr_apply_multi_kernel(const __grid_
 #pragma unroll
     for (int k = 0; k < W; ++k)
       acc[k] = 0.0;
+    const int cshift = int(p.off + r0 - b); // global column of window position 0 (columns are 32-bit)
+    const unsigned wn = unsigned(nrows + 2 * b);
     for (long long c0 = e0;; c0 += kCsrChunk) {
-      const long long c1 = c0 + kCsrChunk < e1 ? c0 + kCsrChunk : e1;
+      const int cnt = int(e1 - c0 < kCsrChunk ? e1 - c0 : kCsrChunk);
       if (c0 > e0)
         __syncthreads(); // the previous round's entries have been consumed
-      const long long vbase = stage_range(s_val, p.val, c0, c1, t);
-      const long long cbase = stage_range(s_col, p.col, c0, c1, t);
+      const double* __restrict__ sv = s_val + stage_range(s_val, p.val + c0, cnt, t);
+      const int* __restrict__ sc = s_col + stage_range(s_col, p.col + c0, cnt, t);
       cp_async_wait_all();
       __syncthreads();
       if (t < nrows) {
-        const long long my0 = s_rp[r0 + t - rp_base], my1 = s_rp[r0 + t + 1 - rp_base];
-        const long long lo = my0 > c0 ? my0 : c0, hi = my1 < c1 ? my1 : c1;
-        for (long long e = lo; e < hi; ++e) {
-          const double a = s_val[e - vbase];
-          const long long l = (long long)s_col[e - cbase] - p.off; // local row of the column
-          if (l >= r0 - p.b && l < r0 + nrows + p.b) {
+        const long long my0 = s_rp[t + rp_mis] - c0, my1 = s_rp[t + 1 + rp_mis] - c0;
+        const int lo = int(my0 > 0 ? my0 : 0), hi = int(my1 < cnt ? my1 : cnt);
+#pragma unroll 3
+        for (int e = lo; e < hi; ++e) {
+          const double a = sv[e];
+          const int wi = sc[e] - cshift;
+          if (unsigned(wi) < wn) {
 #pragma unroll
             for (int k = 0; k < W; ++k)
-              if (k < p.w)
-                acc[k] = __dadd_rn(acc[k], __dmul_rn(a, s_x[k * win + (l - xbase[k])]));
+              acc[k] = __dadd_rn(acc[k], __dmul_rn(a, s_x[k * win + xpos[k] + wi]));
           } else {
+            const long long c = (long long)sc[e];
 #pragma unroll
             for (int k = 0; k < W; ++k)
-              if (k < p.w)
-                acc[k] = __dadd_rn(acc[k], __dmul_rn(a, x_at(l + p.off, p.off, p.n, p.b, p.x[k], p.x_lo[k], p.x_hi[k])));
+              acc[k] = __dadd_rn(acc[k], __dmul_rn(a, x_at(c, p.off, p.n, b, p.x[k], p.x_lo[k], p.x_hi[k])));
           }
         }
       }
-      if (c1 >= e1)
+      if (c0 + cnt >= e1)
         break;
     }
     if (t < nrows) {
 #pragma unroll
       for (int k = 0; k < W; ++k)
-        if (k < p.w)
-          p.y[k][r0 + t] = acc[k];
+        p.y[k][r0 + t] = acc[k];
     }
     __syncthreads(); // shared memory is refilled by the next trip
     e0 = ne0;
@@ -374,14 +367,14 @@ int itsolv_csr_apply_multi_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_of
     p.n = (long long)n;
     p.b = b;
     p.w = cnt;
-    const int wt = cnt <= 1 ? 1 : (cnt <= 2 ? 2 : (cnt <= 4 ? 4 : 8));
+    const int wt = cnt <= 1 ? 1 : (cnt <= 2 ? 2 : (cnt <= 4 ? 4 : 8)); // the unstaged kernel predicates on p.w
     if (b <= kCsrMaxHalfBand) {
       using Kernel = void (*)(const CsrMultiParams);
-      const Kernel kernel = wt == 1   ? csr_apply_multi_kernel<1>
-                            : wt == 2 ? csr_apply_multi_kernel<2>
-                            : wt == 4 ? csr_apply_multi_kernel<4>
-                                      : csr_apply_multi_kernel<8>;
-      const size_t smem = csr_smem_bytes(wt, b);
+      static const Kernel kernels[8] = {csr_apply_multi_kernel<1>, csr_apply_multi_kernel<2>, csr_apply_multi_kernel<3>,
+                                        csr_apply_multi_kernel<4>, csr_apply_multi_kernel<5>, csr_apply_multi_kernel<6>,
+                                        csr_apply_multi_kernel<7>, csr_apply_multi_kernel<8>};
+      const Kernel kernel = kernels[cnt - 1]; // the vector count is a template argument: no predication in the row loop
+      const size_t smem = csr_smem_bytes(cnt, b);
       if (ensure_dynamic_smem(ctx, reinterpret_cast<const void*>(kernel), smem))
         return 1;
       const int per_sm = std::max(1, std::min(8, int(size_t(ctx->max_smem_optin) / (smem + 1024))));

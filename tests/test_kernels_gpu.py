@@ -196,6 +196,36 @@ def test_precondition_bit_exact(ctx, oracle, w, n):
     assert np.array_equal(dR.cpu().numpy(), oracle.c.precondition(R, shift, diag))
 
 
+def same_bits_or_both_nan(got, want):
+    nan = np.isnan(want)
+    return np.array_equal(np.isnan(got), nan) and np.array_equal(got[~nan].view(np.uint64), want[~nan].view(np.uint64))
+
+
+def test_precondition_special_values(ctx, oracle):
+    """the quotient follows IEEE division in the corners too: signed zeros (the kernels answer zero numerators
+    without the generic division), subnormal and tiny numerators, zero / infinite / NaN denominators"""
+    special = np.array([0.0, -0.0, 5e-324, -5e-324, 1e-310, 1e-200, -1e-200, 1e-37, 7.5e-37, 1.0, -1.0, 1e300, np.inf,
+                        -np.inf, np.nan])
+    dens = np.array([1.0, -1.0, 3.0, -3.0, 0.0, 1e-300, -1e300, np.inf, -np.inf, np.nan, 1e-15, 0.5])
+    num, den = [a.ravel() for a in np.meshgrid(special, dens)]
+    shift = np.array([0.0, 2.0])
+    diag = np.where(np.isfinite(den), den - 1e-15, den)  # (diag - 0) + 1e-15 reproduces most of the denominators
+    R = np.stack([num, num])
+    with np.errstate(all="ignore"):
+        want = oracle.c.precondition(R, shift, diag)
+    rs = dev_rows(R)
+    ctx.precondition(rs, dev(diag), shift)
+    assert same_bits_or_both_nan(host(rs), want)
+    # the same corners through the fused residual kernel: r = 1 * a - lambda * 0, then the preconditioner
+    q, a = [dev(np.zeros_like(num))], [dev(num)]
+    out = [dev(np.zeros_like(num)) for _ in range(2)]
+    ctx.davidson_residual(np.ones((1, 2)), q, a, shift, out, diag=dev(diag))
+    with np.errstate(all="ignore"):
+        res = np.stack([num + (-s) * np.zeros_like(num) for s in shift])
+        want = np.stack([oracle.c.precondition(res[j:j + 1], shift[j:j + 1], diag)[0] for j in range(2)])
+    assert same_bits_or_both_nan(host(out), want)
+
+
 @pytest.mark.parametrize("n,nsel", [(1, 1), (10, 3), (1000, 4), (1000, 500), (100003, 16), (4096, 4096)])
 @pytest.mark.parametrize("mode", ["min", "max", "absmax", "absmin", "maxdot"])
 def test_select(ctx, oracle, n, nsel, mode):

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--opt", action="append", default=[])
     ap.add_argument("--only", default="")
+    ap.add_argument("--pool", type=int, default=0, help="vectors in the rotating input pool (default 160 at n <= 1e7)")
     ap.add_argument("--json", default="")
     ap.add_argument("--sweep", action="append", default=[], help="NAME=v1,v2,...: rerun the selected ops for each value")
     args = ap.parse_args()
@@ -35,7 +36,7 @@ def main():
         ctx.set_option(k, int(v))
     n = args.n
     g = torch.Generator(device="cuda").manual_seed(0)
-    nvec = 160 if n <= 10_000_000 else 40
+    nvec = args.pool if args.pool > 0 else (160 if n <= 10_000_000 else 40)
     pool = [torch.randn(n, dtype=torch.float64, device="cuda", generator=g) for _ in range(nvec)]
     torch.cuda.synchronize()
     cursor = [0]
@@ -122,8 +123,9 @@ def run_all(ctx, lib, args, n, nvec, take, run, _ptr_array, _dbl):
     run("axpy", 24 * n, lambda: ctx.axpy(1e-9, *take(2)))
     run("dot", 16 * n, lambda: ctx.dot(*take(2)))
     run("dot(x,x)", 8 * n, lambda: (lambda v: ctx.dot(v, v))(take(1)[0]))
-    diag = torch.arange(1, n + 1, dtype=torch.float64, device="cuda")
-    run("precondition[w=4]", 8 * n * 9, lambda: ctx.precondition(take(4), diag, [0.1, 0.2, 0.3, 0.4]))
+    # denominators close to 1 so that the vectors, which are rewritten in place, keep their magnitude over the repetitions
+    diag = 1.0 + 1e-3 * torch.rand(n, dtype=torch.float64, device="cuda")
+    run("precondition[w=4]", 8 * n * 9, lambda: ctx.precondition(take(4), diag, [1e-4, 2e-4, 3e-4, 4e-4]))
     for k, m in [(4, 1), (1, 4), (4, 4), (4, 8), (4, 12), (4, 16), (4, 20), (8, 8), (16, 16), (16, 24), (16, 40), (16, 64),
                  (8, 100), (16, 128), (32, 32), (64, 64), (128, 128)]:
         if (k + m) > nvec:
@@ -137,10 +139,11 @@ def run_all(ctx, lib, args, n, nvec, take, run, _ptr_array, _dbl):
     # ---- kernels of the fused driver path
     def ds(k, m):
         coef = np.random.default_rng(1).standard_normal((k, m)) * 1e-2
-        lam = np.arange(1, m + 1) + 0.5
+        lam = 1e-4 * np.arange(1, m + 1)
+        outs = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(m)]  # not fed back into the pool
 
         def f():
-            ctx.davidson_residual(coef, take(k), take(k), lam, take(m), diag=diag)
+            ctx.davidson_residual(coef, take(k), take(k), lam, outs, diag=diag)
         return f
 
     for k, m in [(4, 4), (8, 4), (16, 4), (24, 8), (24, 16), (40, 16)]:
