@@ -463,7 +463,9 @@ int itsolv_davidson_residual_f64(itsolv_ctx* ctx, const double* coef, int k, int
       p.coef = reinterpret_cast<const double*>(d);
       if (mj == 16)
         vec = false; // 16 roots: one row per thread keeps the 32 running sums in registers at two CTAs per SM
-      const bool ring = vec && mj <= 8 && ctx->opt_ds_ring >= 0 &&
+      // measured (profiles/opbench): the ring wins while the epilogue (divisions, stores) is a large part of a row's work,
+      // the register kernel once the subspace has more than ~10 vector pairs
+      const bool ring = vec && mj <= 8 && ctx->opt_ds_ring >= 0 && (k <= 10 || ctx->opt_ds_ring > 0) &&
                         ((cbytes + 15) & ~size_t(15)) + ds_ring_bytes() <= size_t(ctx->max_smem_optin) / 2 - 1024;
       DsKernel kernel = ring ? ds_pick_ring(mj) : ds_pick(mj, vec);
       ITSOLV_REQUIRE(kernel != nullptr, "davidson_residual: root tile not instantiated");

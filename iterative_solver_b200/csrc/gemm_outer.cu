@@ -67,7 +67,7 @@ __device__ __forceinline__ void load_alpha_row(const double* __restrict__ arow, 
 }
 
 //! one thread, one row group `r` (index in units of RV), all column chunks
-template <int MJ, class RV>
+template <int MJ, class RV, bool SCALED>
 __device__ __forceinline__ void expand_rows(const GoParams& p, const double* __restrict__ sa, size_t r) {
   using Ops = RowOps<RV>;
   for (int jc = 0; jc < p.m; jc += MJ) {
@@ -79,7 +79,7 @@ __device__ __forceinline__ void expand_rows(const GoParams& p, const double* __r
       else
         acc[b] = Ops::zero();
     }
-    if (p.scaled) {
+    if constexpr (SCALED) { // compile-time: a run-time branch here would separate the loads of y from those of x
       double sv[MJ];
       load_alpha_row<MJ>(sa + size_t(p.k) * p.ld + jc, sv);
 #pragma unroll
@@ -116,7 +116,7 @@ __device__ __forceinline__ void expand_rows(const GoParams& p, const double* __r
   }
 }
 
-template <int MJ, bool VEC>
+template <int MJ, bool VEC, bool SCALED>
 __global__ void __launch_bounds__(kGoThreads, 2) gemm_outer_kernel(const __grid_constant__ GoParams p) {
   extern __shared__ __align__(16) double sa[]; // k (+1 when scaled) x ld, zero padded columns
   for (int e = threadIdx.x; e < (p.k + p.scaled) * p.ld; e += blockDim.x) {
@@ -129,32 +129,34 @@ __global__ void __launch_bounds__(kGoThreads, 2) gemm_outer_kernel(const __grid_
   if (VEC) {
     const size_t npairs = p.n / 2;
     for (size_t r = tid; r < npairs; r += nthreads)
-      expand_rows<MJ, double2>(p, sa, r);
+      expand_rows<MJ, double2, SCALED>(p, sa, r);
     if ((p.n & 1) && tid == 0)
-      expand_rows<MJ, double>(p, sa, p.n - 1);
+      expand_rows<MJ, double, SCALED>(p, sa, p.n - 1);
   } else {
     for (size_t r = tid; r < p.n; r += nthreads)
-      expand_rows<MJ, double>(p, sa, r);
+      expand_rows<MJ, double, SCALED>(p, sa, r);
   }
 }
 
 using GoKernel = void (*)(const GoParams);
 template <int MJ>
-static GoKernel go_pick_vec(bool vec) {
-  return vec ? gemm_outer_kernel<MJ, true> : gemm_outer_kernel<MJ, false>;
+static GoKernel go_pick_vec(bool vec, bool scaled) {
+  if (scaled)
+    return vec ? gemm_outer_kernel<MJ, true, true> : gemm_outer_kernel<MJ, false, true>;
+  return vec ? gemm_outer_kernel<MJ, true, false> : gemm_outer_kernel<MJ, false, false>;
 }
-static GoKernel go_pick(int mj, bool vec) {
+static GoKernel go_pick(int mj, bool vec, bool scaled) {
   switch (mj) {
   case 1:
-    return go_pick_vec<1>(vec);
+    return go_pick_vec<1>(vec, scaled);
   case 2:
-    return go_pick_vec<2>(vec);
+    return go_pick_vec<2>(vec, scaled);
   case 4:
-    return go_pick_vec<4>(vec);
+    return go_pick_vec<4>(vec, scaled);
   case 8:
-    return go_pick_vec<8>(vec);
+    return go_pick_vec<8>(vec, scaled);
   case 16:
-    return go_pick_vec<16>(vec);
+    return go_pick_vec<16>(vec, scaled);
   }
   return nullptr;
 }
@@ -266,7 +268,7 @@ static int gemm_outer_impl(itsolv_ctx* ctx, const double* alpha, int k, int m, c
       if (ctx->opt_go_cols > 0)
         mj = ctx->opt_go_cols;
       p.ld = ((mb + mj - 1) / mj) * mj;
-      GoKernel kernel = go_pick(mj, vec);
+      GoKernel kernel = go_pick(mj, vec, scaled);
       ITSOLV_REQUIRE(kernel != nullptr, "gemm_outer: column tile not instantiated");
       const size_t smem = size_t(kb + p.scaled) * p.ld * sizeof(double);
       if (ensure_dynamic_smem(ctx, reinterpret_cast<const void*>(kernel), smem))

@@ -71,8 +71,55 @@ def main():
     y = H.harness_banded_apply(ctx, X[2].copy(), 4, 1e-3, explicit_csr=True)
     assert np.array_equal(y[lo:hi], cpu.banded_apply(X[2].copy(), 4, 1e-3)[lo:hi])
 
-    # complete solves on sharded vectors against the reference's golden results
+    # kernels of the fused driver path on row shards: vectors bit for bit (no communication), the sums they return
+    # all-reduced inside the kernel tail (or by NCCL) and identical on every rank
+    def shard(a):
+        return [torch.from_numpy(np.ascontiguousarray(a[i, lo:hi])).cuda() for i in range(a.shape[0])]
+
+    Q, A = rng.standard_normal((5, n)), rng.standard_normal((5, n))
+    coef, lam = rng.standard_normal((5, 3)), np.array([1.25, 2.5, 3.75])
+    diag = np.arange(1, n + 1, dtype=np.float64)
+    out = [torch.empty(hi - lo, dtype=torch.float64, device="cuda") for _ in range(3)]
+    n2, n2w = ctx.davidson_residual(coef, shard(Q), shard(A), lam, out, diag=shard(diag[None])[0])
+    wx = cpu.gemm_outer(coef, Q, np.zeros((3, n)), fma=True)
+    wr = cpu.gemm_outer(coef, A, np.zeros((3, n)), fma=True)
+    wr = np.stack([cpu.axpy(-lam[j], wx[j], wr[j]) for j in range(3)])
+    wp = cpu.precondition(wr, lam, diag)
+    assert np.array_equal(np.stack([t.cpu().numpy() for t in out]), wp[:, lo:hi])
+    for j in range(3):
+        assert abs(n2[j] - cpu.dot(wr[j], wr[j])) <= 1e-12 * n2[j]
+        assert abs(n2w[j] - cpu.dot(wp[j], wp[j])) <= 1e-12 * n2w[j]
+    both = torch.from_numpy(np.concatenate([n2, n2w])).cuda()
+    alln = [torch.zeros_like(both) for _ in range(world)]
+    dist.all_gather(alln, both)
+    assert all(torch.equal(alln[0], g) for g in alln)
+    R = rng.standard_normal((4, n))
+    rs = shard(R)
+    ov = rng.standard_normal(3)
+    dots = ctx.mgs_step_dots(0.77, rs[0], ov, rs[1:])
+    piv = cpu.scal(0.77, R[0].copy())
+    wR = np.stack([piv] + [cpu.axpy(-ov[j], piv.copy(), R[j + 1].copy()) for j in range(3)])
+    assert np.array_equal(np.stack([t.cpu().numpy() for t in rs]), wR[:, lo:hi])
+    nr = np.linalg.norm(wR, axis=1)
+    assert abs(dots[0] - cpu.dot(wR[0], wR[0])) <= 1e-12 * nr[0] ** 2
+    for t_ in range(3):
+        assert abs(dots[1 + t_] - cpu.dot(wR[1], wR[1 + t_])) <= 1e-12 * nr[1] * nr[1 + t_]
+
+    # the fused driver path on sharded vectors: same golden results of the reference
     golden = json.load(open(os.path.join(ROOT, "tests", "golden", "solve_golden.json")))
+    fused_report = {}
+    for name in sorted(k for k, v in golden.items() if v["spec"]["kind"] == N.KIND_DAVIDSON and v["spec"]["n"] >= 1000):
+        want = golden[name]
+        res, sol = H.solve(ctx, H.make_spec(fused=1, **want["spec"]), want_solutions=True)
+        assert res.iterations == want["iterations"] and res.converged == want["converged"], name
+        ev = np.array([res.eigenvalues[i] for i in range(res.nroots)])
+        assert np.abs(ev / np.array(want["eigenvalues"]) - 1).max() <= 1e-10, name
+        chk = ctx.allreduce_host(np.array([np.sum(s_) for s_ in sol]))
+        for c, w in zip(chk, want["solution_checksums"]):
+            assert abs(c - w) <= 1e-6 * max(1.0, abs(w)), name
+        fused_report[name] = res.iterations
+
+    # complete solves on sharded vectors against the reference's golden results
     report = {}
     for name in ("banded_davidson_n100000_r4", "banded_davidson_n30000_r6_qcap8", "banded_davidson_n30000_r4_p20",
                  "banded_lineq_n50000_r1", "banded_diis_n50000", "banded_davidson_n30000_r16"):
@@ -93,7 +140,7 @@ def main():
             assert abs(c - w) <= 1e-6 * max(1.0, abs(w)), name
         report[name] = res.iterations
     dist.barrier()
-    print(f"rank {rank}/{world} ok {report}", flush=True)
+    print(f"rank {rank}/{world} ok {report} fused {fused_report}", flush=True)
     ctx.close()
     dist.destroy_process_group()
 

@@ -216,13 +216,17 @@ def test_precondition_special_values(ctx, oracle):
     rs = dev_rows(R)
     ctx.precondition(rs, dev(diag), shift)
     assert same_bits_or_both_nan(host(rs), want)
-    # the same corners through the fused residual kernel: r = 1 * a - lambda * 0, then the preconditioner
-    q, a = [dev(np.zeros_like(num))], [dev(num)]
-    out = [dev(np.zeros_like(num)) for _ in range(2)]
+    # the same corners through the fused residual kernel (x = 1 * 0, r = 1 * num - shift * x, then the preconditioner),
+    # expected values from the oracle's sequence of the separate steps
+    zero = np.zeros_like(num)
+    q, a = [dev(zero)], [dev(num)]
+    out = [dev(zero) for _ in range(2)]
     ctx.davidson_residual(np.ones((1, 2)), q, a, shift, out, diag=dev(diag))
     with np.errstate(all="ignore"):
-        res = np.stack([num + (-s) * np.zeros_like(num) for s in shift])
-        want = np.stack([oracle.c.precondition(res[j:j + 1], shift[j:j + 1], diag)[0] for j in range(2)])
+        x = oracle.c.gemm_outer(np.ones((1, 2)), zero[None], np.zeros((2, num.size)), fma=True)
+        r = oracle.c.gemm_outer(np.ones((1, 2)), num[None], np.zeros((2, num.size)), fma=True)
+        r = np.stack([oracle.c.axpy(-shift[j], x[j], r[j]) for j in range(2)])
+        want = oracle.c.precondition(r, shift, diag)
     assert same_bits_or_both_nan(host(out), want)
 
 
