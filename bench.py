@@ -47,7 +47,7 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
+def ncu_traffic(family):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel family, from the newest committed
     ncu capture of this same command (profiles/ncu_dram_bench_rNN.json, written by tools/summarize_profiles.py)"""
     import glob
@@ -56,7 +56,10 @@ def ncu_traffic():
         return None, None
     with open(files[-1]) as f:
         d = json.load(f)
-    return d["gemm_inner_family"]["dram_bytes_per_launch"], os.path.relpath(files[-1], ROOT)
+    fam = d.get("families", {}).get(family)
+    if fam is None or not fam.get("launches"):
+        return None, None
+    return fam["dram_bytes_per_launch"], os.path.relpath(files[-1], ROOT)
 
 
 class ClockSampler:
@@ -201,7 +204,8 @@ def main():
     lib.itsolv_comm_barrier(ctx.handle)
     torch.cuda.synchronize()
     iterations, launches = 0, 0
-    agg = dict(bytes=0.0, secs=0.0, bgi=0.0, sgi=0.0, bgo=0.0, sgo=0.0, bb1=0.0, sb1=0.0, action=0.0)
+    agg = dict(bytes=0.0, secs=0.0, bgi=0.0, sgi=0.0, bgo=0.0, sgo=0.0, bb1=0.0, sb1=0.0, brs=0.0, srs=0.0, action=0.0,
+               cgi=0, cgo=0, cb1=0, crs=0)
     with ClockSampler(local_rank) as clocks:
         ctx.timer_start()
         for _ in range(args.steps):
@@ -216,7 +220,12 @@ def main():
             agg["sgo"] += res.seconds_gemm_outer
             agg["bb1"] += res.bytes_blas1
             agg["sb1"] += res.seconds_blas1
-            agg["ngi"] = agg.get("ngi", 0) + res.n_dot + res.n_gemm_inner
+            agg["brs"] += res.bytes_residual
+            agg["srs"] += res.seconds_residual
+            agg["cgi"] += res.calls_gemm_inner
+            agg["cgo"] += res.calls_gemm_outer
+            agg["cb1"] += res.calls_blas1
+            agg["crs"] += res.calls_residual
         ms = ctx.timer_stop()
         lib.itsolv_comm_barrier(ctx.handle)
         torch.cuda.synchronize()
@@ -242,9 +251,9 @@ def main():
                  "iterations_per_solve": o_iter / o_steps,
                  "eigenvalues_agree_to": max(abs(r_o.eigenvalues[i] / eig[i] - 1) for i in range(args.roots))}
     ms_max = float(ctx.allreduce_host(np.array([ms]), op_max=True)[0])
-    sums = ctx.allreduce_host(np.array([agg["bytes"], agg["bgi"], agg["bgo"], agg["bb1"], float(launches)]))
-    gi_launches = float(agg.get("ngi", 0)) * world
-    maxs = ctx.allreduce_host(np.array([agg["secs"], agg["sgi"], agg["sgo"], agg["sb1"]]), op_max=True)
+    sums = ctx.allreduce_host(np.array([agg["bytes"], agg["bgi"], agg["bgo"], agg["bb1"], float(launches), agg["brs"],
+                                        float(agg["cgi"]), float(agg["cgo"]), float(agg["cb1"]), float(agg["crs"])]))
+    maxs = ctx.allreduce_host(np.array([agg["secs"], agg["sgi"], agg["sgo"], agg["sb1"], agg["srs"]]), op_max=True)
     value = world * iterations / (ms_max * 1e-3)  # shard-iterations per second: every rank iterates over its 1e7-row shard
     problem.close()
 
@@ -304,8 +313,22 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        gi_gbs = agg_gbs(sums[1] / world, maxs[1])
-        traffic, traffic_src = ncu_traffic()
+        # kernel families of the subspace path (itsolv_counters): algorithmic bytes, event time and calls of each, summed
+        # over the timed region; the roofline object describes the one with the largest share of the device time
+        families = {
+            "gemm_inner": dict(kernel="gemm_inner_kernel / gemm_inner_direct_kernel (Gram blocks, dot)",
+                               bytes=sums[1], secs=maxs[1], calls=sums[6]),
+            "gemm_outer": dict(kernel="gemm_outer_kernel (subspace -> full space expansion, projection)",
+                               bytes=sums[2], secs=maxs[2], calls=sums[7]),
+            "blas1": dict(kernel="streaming kernels (mgs_step_dots, axpy/scal/copy/fill, preconditioner)",
+                          bytes=sums[3], secs=maxs[3], calls=sums[8]),
+            "residual": dict(kernel="davidson_residual_kernel (solution + residual + norms + preconditioner in one pass)",
+                             bytes=sums[5], secs=maxs[4], calls=sums[9]),
+        }
+        dominant = max(families, key=lambda k: families[k]["secs"])
+        dom = families[dominant]
+        dom_gbs = agg_gbs(dom["bytes"] / world, dom["secs"])
+        traffic, traffic_src = ncu_traffic(dominant)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, args.min_warmup),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -317,11 +340,15 @@ def main():
                        "l2": "inputs larger than L2 (each vector 80 MB, ~40 live vectors)",
                        "value_unit_note": "iterations/s x number of 1e7-row shards (weak scaling)"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(sums[4]),
-            "roofline": {"bound": "hbm", "kernel": "gemm_inner_kernel (gemm_inner and its 1x1 case dot)",
-                         "achieved": gi_gbs, "peak": peak, "unit": "GB/s", "frac": gi_gbs / peak if peak else None,
+            "roofline": {"bound": "hbm", "kernel": dom["kernel"], "family": dominant,
+                         "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak if peak else None,
                          "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
-                         "algorithmic_bytes_per_launch": sums[1] / max(gi_launches, 1.0),
-                         "launch_share_of_handler_time": maxs[1] / maxs[0] if maxs[0] else None},
+                         "algorithmic_bytes_per_launch": dom["bytes"] / max(dom["calls"], 1.0),
+                         "launch_share_of_handler_time": dom["secs"] / maxs[0] if maxs[0] else None,
+                         "families": {k: {"gbs": agg_gbs(v["bytes"] / world, v["secs"]),
+                                          "frac": agg_gbs(v["bytes"] / world, v["secs"]) / peak if peak else None,
+                                          "share_of_handler_time": v["secs"] / maxs[0] if maxs[0] else None,
+                                          "launches": int(v["calls"])} for k, v in families.items()}},
             "cpu_baseline": cpu,
             "subspace_update": {"gbs_per_gpu": agg_gbs(sums[0] / world, maxs[0]),
                                 "frac_of_measured_hbm": agg_gbs(sums[0] / world, maxs[0]) / peak,

@@ -53,7 +53,9 @@ typedef struct itsolv_counters {
   double device_seconds; /* only while profiling */
   double bytes_gemm_inner, seconds_gemm_inner; /* gemm_inner_kernel launches: gemm_inner and dot (its 1 x 1 case) */
   double bytes_gemm_outer, seconds_gemm_outer; /* gemm_outer_kernel launches */
-  double bytes_blas1, seconds_blas1;           /* streaming kernels: axpy, scal, copy, fill, preconditioner */
+  double bytes_blas1, seconds_blas1;           /* streaming kernels: axpy, scal, copy, fill, preconditioner, mgs steps */
+  double bytes_residual, seconds_residual;     /* davidson_residual_kernel launches (fused driver path) */
+  int64_t calls_gemm_inner, calls_gemm_outer, calls_blas1, calls_residual; /* accounted calls (~ launches) per family */
 } itsolv_counters;
 void itsolv_ctx_counters(itsolv_ctx* ctx, itsolv_counters* out);
 void itsolv_ctx_reset_counters(itsolv_ctx* ctx);

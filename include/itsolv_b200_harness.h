@@ -66,6 +66,8 @@ typedef struct itsolv_solve_result {
   int64_t kernel_launches;
   double device_ms_solve; /* solve() bracketed by CUDA events on the context's stream (0 for the oracle) */
   double bytes_gemm_inner, seconds_gemm_inner, bytes_gemm_outer, seconds_gemm_outer, bytes_blas1, seconds_blas1;
+  double bytes_residual, seconds_residual; /* the fused solution/residual/preconditioner kernel */
+  int64_t calls_gemm_inner, calls_gemm_outer, calls_blas1, calls_residual;
 } itsolv_solve_result;
 
 /* One trace record = one handler call that returned numbers to the host. op: 'd' dot, 'g' gemm_inner. */

@@ -24,7 +24,8 @@ class Counters(C.Structure):
         "n_dot", "n_axpy", "n_scal", "n_copy", "n_fill", "n_gemm_inner", "n_gemm_outer", "n_precondition", "n_select",
         "n_sparse")] + [(n, C.c_double) for n in (
             "bytes", "device_seconds", "bytes_gemm_inner", "seconds_gemm_inner", "bytes_gemm_outer",
-            "seconds_gemm_outer", "bytes_blas1", "seconds_blas1")]
+            "seconds_gemm_outer", "bytes_blas1", "seconds_blas1", "bytes_residual", "seconds_residual")] + [
+                (n, C.c_int64) for n in ("calls_gemm_inner", "calls_gemm_outer", "calls_blas1", "calls_residual")]
 
 
 class SolveSpec(C.Structure):
@@ -47,7 +48,9 @@ class SolveResult(C.Structure):
                 ("handler_bytes", C.c_double), ("handler_device_seconds", C.c_double), ("kernel_launches", C.c_int64),
                 ("device_ms_solve", C.c_double), ("bytes_gemm_inner", C.c_double), ("seconds_gemm_inner", C.c_double),
                 ("bytes_gemm_outer", C.c_double), ("seconds_gemm_outer", C.c_double), ("bytes_blas1", C.c_double),
-                ("seconds_blas1", C.c_double)]
+                ("seconds_blas1", C.c_double), ("bytes_residual", C.c_double), ("seconds_residual", C.c_double),
+                ("calls_gemm_inner", C.c_int64), ("calls_gemm_outer", C.c_int64), ("calls_blas1", C.c_int64),
+                ("calls_residual", C.c_int64)]
 
 
 class TraceEntry(C.Structure):

@@ -35,7 +35,7 @@ void set_error(const std::string& msg);
 
 struct Comm; // NCCL communicator wrapper (comm.cu)
 
-enum OpClass { OP_BLAS1 = 0, OP_GEMM_INNER = 1, OP_GEMM_OUTER = 2, OP_OTHER = 3 };
+enum OpClass { OP_BLAS1 = 0, OP_GEMM_INNER = 1, OP_GEMM_OUTER = 2, OP_OTHER = 3, OP_RESIDUAL = 4 };
 
 struct CallScope;
 

@@ -20,12 +20,19 @@ CallScope::CallScope(itsolv_ctx* c, int cls_, double bytes) : ctx(c), cls(cls_) 
   switch (cls) {
   case OP_GEMM_INNER:
     ctx->counters.bytes_gemm_inner += bytes;
+    ctx->counters.calls_gemm_inner++;
     break;
   case OP_GEMM_OUTER:
     ctx->counters.bytes_gemm_outer += bytes;
+    ctx->counters.calls_gemm_outer++;
     break;
   case OP_BLAS1:
     ctx->counters.bytes_blas1 += bytes;
+    ctx->counters.calls_blas1++;
+    break;
+  case OP_RESIDUAL:
+    ctx->counters.bytes_residual += bytes;
+    ctx->counters.calls_residual++;
     break;
   default:
     break;
@@ -90,6 +97,8 @@ void drain_pending(itsolv_ctx* ctx) {
         ctx->counters.seconds_gemm_outer += s;
       else if (p.cls == OP_BLAS1)
         ctx->counters.seconds_blas1 += s;
+      else if (p.cls == OP_RESIDUAL)
+        ctx->counters.seconds_residual += s;
     }
     ctx->event_pool.push_back(p.start);
     ctx->event_pool.push_back(p.stop);

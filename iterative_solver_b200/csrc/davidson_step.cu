@@ -239,9 +239,14 @@ __global__ void __launch_bounds__(kDsThreads, MJ <= 2 ? 3 : 2)
 // slots of a shared-memory ring with cp.async (LDGSTS, 16 bytes each, no registers, no barriers: slots are private) and
 // computes the current trip out of shared memory, so (S-1) 2U 16-byte loads per thread stay outstanding throughout.
 constexpr int kRingU = 2; // subspace vectors (and as many actions) per trip
-constexpr int kRingS = 4; // ring depth: S-1 trips are in flight while one is consumed
 constexpr int kRingSlots = 2 * kRingU + 1;
-static size_t ds_ring_bytes() { return size_t(kRingS) * kRingSlots * kDsThreads * sizeof(double2); }
+//! ring depth: S-1 trips are in flight while one is consumed. With 8 roots the running sums of squares move to shared
+//! memory (the 32 sums of the expansions need the registers) and the ring gives up one stage for them.
+__host__ __device__ constexpr int ring_depth(int mj) { return mj >= 8 ? 3 : 4; }
+static size_t ds_ring_bytes(int mj) {
+  return size_t(ring_depth(mj)) * kRingSlots * kDsThreads * sizeof(double2) +
+         (mj >= 8 ? size_t(2 * mj) * kDsThreads * sizeof(double) : 0);
+}
 
 __device__ __forceinline__ void ds_cp_async16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
@@ -255,13 +260,15 @@ __device__ __forceinline__ void ds_cp_async_wait() {
 
 template <int MJ>
 __global__ void __launch_bounds__(kDsThreads, 2) davidson_residual_ring_kernel(const __grid_constant__ DsParams p) {
-  extern __shared__ __align__(16) double sc[]; // k x ld coefficients, then the ring [S][2U+1][blockDim.x] of double2
-  constexpr int U = kRingU, S = kRingS;
+  // k x ld coefficients, then the ring [S][2U+1][blockDim.x] of double2 [, then 2 MJ x blockDim.x running sums]
+  extern __shared__ __align__(16) double sc[];
+  constexpr int U = kRingU, S = ring_depth(MJ);
   for (int e = threadIdx.x; e < p.k * p.ld; e += blockDim.x)
     sc[e] = p.coef[e];
-  double2* ring = reinterpret_cast<double2*>(sc + ((p.k * p.ld + 1) & ~1)) + threadIdx.x;
-  DsNorms<MJ, false> nrm;
-  nrm.init(nullptr);
+  double2* ring_base = reinterpret_cast<double2*>(sc + ((p.k * p.ld + 1) & ~1));
+  double2* ring = ring_base + threadIdx.x;
+  DsNorms<MJ, (MJ >= 8)> nrm;
+  nrm.init(reinterpret_cast<double*>(ring_base + size_t(S) * kRingSlots * kDsThreads));
   __syncthreads();
   const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = size_t(gridDim.x) * blockDim.x;
@@ -418,7 +425,7 @@ int itsolv_davidson_residual_f64(itsolv_ctx* ctx, const double* coef, int k, int
   for (int j0 = 0; j0 < m; j0 += kDsMaxRoots) {
     const int mb = std::min(kDsMaxRoots, m - j0);
     const double bytes = 8.0 * double(n) * (2.0 * k + mb * (out_x ? 2.0 : 1.0) + (diag ? 1.0 : 0.0));
-    CallScope scope(ctx, OP_GEMM_OUTER, bytes);
+    CallScope scope(ctx, OP_RESIDUAL, bytes);
     bool direct = false;
     if (n == 0) { // an empty shard still takes part in the all-reduce
       ITSOLV_CUDA(cudaMemsetAsync(ctx->d_result, 0, size_t(2 * mb) * sizeof(double), ctx->stream));
@@ -465,11 +472,11 @@ int itsolv_davidson_residual_f64(itsolv_ctx* ctx, const double* coef, int k, int
         vec = false; // 16 roots: one row per thread keeps the 32 running sums in registers at two CTAs per SM
       // measured (profiles/opbench): the ring wins while the epilogue (divisions, stores) is a large part of a row's work,
       // the register kernel once the subspace has more than ~10 vector pairs
-      const bool ring = vec && mj <= 8 && ctx->opt_ds_ring >= 0 && (k <= 10 || ctx->opt_ds_ring > 0) &&
-                        ((cbytes + 15) & ~size_t(15)) + ds_ring_bytes() <= size_t(ctx->max_smem_optin) / 2 - 1024;
+      const bool ring = vec && mj <= 8 && ctx->opt_ds_ring >= 0 && (k <= 10 || mj == 8 || ctx->opt_ds_ring > 0) &&
+                        ((cbytes + 15) & ~size_t(15)) + ds_ring_bytes(mj) <= size_t(ctx->max_smem_optin) / 2 - 1024;
       DsKernel kernel = ring ? ds_pick_ring(mj) : ds_pick(mj, vec);
       ITSOLV_REQUIRE(kernel != nullptr, "davidson_residual: root tile not instantiated");
-      const size_t smem = ring ? ((cbytes + 15) & ~size_t(15)) + ds_ring_bytes()
+      const size_t smem = ring ? ((cbytes + 15) & ~size_t(15)) + ds_ring_bytes(mj)
                                : cbytes + (mj > 8 ? size_t(2 * mj) * kDsThreads * sizeof(double) : 0);
       if (ensure_dynamic_smem(ctx, reinterpret_cast<const void*>(kernel), smem))
         return 1;

@@ -295,6 +295,12 @@ void fill_counters(itsolv_ctx* ctx, itsolv_solve_result* result) {
   result->seconds_gemm_outer = c.seconds_gemm_outer;
   result->bytes_blas1 = c.bytes_blas1;
   result->seconds_blas1 = c.seconds_blas1;
+  result->bytes_residual = c.bytes_residual;
+  result->seconds_residual = c.seconds_residual;
+  result->calls_gemm_inner = c.calls_gemm_inner;
+  result->calls_gemm_outer = c.calls_gemm_outer;
+  result->calls_blas1 = c.calls_blas1;
+  result->calls_residual = c.calls_residual;
 }
 
 template <class F>

@@ -328,9 +328,9 @@ protected:
     this->m_subspace_solver->solve(*this->m_xspace, this->n_roots());
     const auto nsol = this->m_subspace_solver->size();
     const auto dims = this->m_xspace->dimensions();
-    if (dims.nP != 0 || nsol == 0 || nsol > parameters.size() || this->m_normalise_solution || dims.nQ + dims.nD == 0) {
-      // several batches of roots, a P space or normalised solutions: the general routine (it solves the same subspace
-      // problem again, which is cheap next to these cases' vector work)
+    if (dims.nP != 0 || nsol == 0 || this->m_normalise_solution || dims.nQ + dims.nD == 0) {
+      // a P space or normalised solutions: the general routine (it solves the same subspace problem again, which is
+      // cheap next to these cases' vector work)
       const auto nwork = this->solve_and_generate_working_set(parameters, actions);
       its::read_handler_counts(this->m_stats, this->m_handlers);
       this->m_end_iteration_needed = true;
@@ -338,29 +338,47 @@ protected:
     }
     auto& xs = *this->m_xspace;
     const auto& sol = this->m_subspace_solver->solutions();
-    std::vector<int> roots(nsol);
-    std::iota(roots.begin(), roots.end(), 0);
-    Matrix<double> c({dims.nQ + dims.nD, nsol});
-    std::vector<double> lambda(nsol);
     const auto eigvals = this->eigenvalues();
-    for (size_t i = 0; i < nsol; ++i) {
-      lambda[i] = eigvals.at(i);
-      for (size_t j = 0; j < dims.nQ; ++j)
-        c(j, i) = sol(i, dims.oQ + j);
-      for (size_t j = 0; j < dims.nD; ++j)
-        c(dims.nQ + j, i) = sol(i, dims.oD + j);
-    }
     auto stack = [](CVecRef<R> a, const CVecRef<R>& b) {
       a.insert(a.end(), b.begin(), b.end());
       return a;
     };
-    const auto norms = m_dense->davidson_residual(c, stack(xs.cparamsq(), xs.cparamsd()), stack(xs.cactionsq(), xs.cactionsd()),
-                                                  lambda, diagonals, VecRef<R>{},
-                                                  VecRef<R>(actions.begin(), actions.begin() + nsol));
-    std::vector<double> errors(nsol);
-    for (size_t i = 0; i < nsol; ++i)
-      errors[i] = std::sqrt(std::abs(norms.residual[i]));
-    this->m_subspace_solver->set_error(roots, errors);
+    const auto xpar = stack(xs.cparamsq(), xs.cparamsd()), xact = stack(xs.cactionsq(), xs.cactionsd());
+    // fewer buffers than roots: the roots are treated in batches and the residuals of a finished batch are parked, as the
+    // reference parks solutions and residuals (IterativeSolverTemplate.h:527-541); parking hands over the allocation
+    const auto batches = its::detail::parameter_batches(nsol, parameters.size());
+    std::vector<R> parked;
+    std::vector<double> written(nsol);
+    std::vector<int> last_roots;
+    for (const auto& batch : batches) {
+      const size_t start = batch.first, nb = batch.second - batch.first;
+      std::vector<int> roots(nb);
+      std::iota(roots.begin(), roots.end(), int(start));
+      Matrix<double> c({dims.nQ + dims.nD, nb});
+      std::vector<double> lambda(nb);
+      for (size_t i = 0; i < nb; ++i) {
+        lambda[i] = eigvals.at(start + i);
+        for (size_t j = 0; j < dims.nQ; ++j)
+          c(j, i) = sol(start + i, dims.oQ + j);
+        for (size_t j = 0; j < dims.nD; ++j)
+          c(dims.nQ + j, i) = sol(start + i, dims.oD + j);
+      }
+      const auto norms = m_dense->davidson_residual(c, xpar, xact, lambda, diagonals, VecRef<R>{},
+                                                    VecRef<R>(actions.begin(), actions.begin() + nb));
+      std::vector<double> errors(nb);
+      for (size_t i = 0; i < nb; ++i) {
+        errors[i] = std::sqrt(std::abs(norms.residual[i]));
+        written[start + i] = norms.written[i];
+      }
+      if (batches.size() > 1) {
+        ArrayHandlerCUDA::TakeOnCopy take(*m_dense);
+        for (size_t i = 0; i < nb; ++i)
+          parked.emplace_back(this->m_handlers->qr().copy(actions[i]));
+        this->m_stats->q_creations += 2 * nb; // the reference parks two vectors per root
+      }
+      this->m_subspace_solver->set_error(roots, errors);
+      last_roots = roots;
+    }
     this->set_value_errors();
     this->m_errors = this->m_subspace_solver->errors();
     this->m_working_set =
@@ -369,15 +387,19 @@ protected:
     m_written_norms.clear();
     for (size_t i = 0; i < this->m_working_set.size(); ++i) {
       const size_t root = this->m_working_set[i];
-      if (root < i)
-        throw std::logic_error("incorrect ordering of roots");
-      if (root > i)
-        this->m_handlers->rr().copy(actions[i], actions[root]);
-      m_written_norms.push_back(norms.written[root]);
+      if (batches.size() > 1) {
+        actions[i].get().swap(parked.at(root));
+      } else {
+        if (root < i)
+          throw std::logic_error("incorrect ordering of roots");
+        if (root > i)
+          this->m_handlers->rr().copy(actions[i], actions[root]);
+      }
+      m_written_norms.push_back(written[root]);
     }
     preconditioned = diagonals != nullptr;
     if (this->m_working_set.empty()) // converged: leave solutions and residuals in the caller's vectors as the reference does
-      solution(roots, parameters, actions);
+      solution(last_roots, parameters, actions);
     its::read_handler_counts(this->m_stats, this->m_handlers);
     this->m_end_iteration_needed = true;
     return int(this->m_working_set.size());

@@ -36,7 +36,7 @@ def test_host_library_exports_every_declared_symbol():
 def test_struct_layouts_match_the_header():
     import ctypes as C
     assert C.sizeof(N.SolveSpec) == 80
-    assert C.sizeof(N.SolveResult) == 16 + 2 * 64 * 8 + 3 * 8 + 4 * 8 + 7 * 8 + 2 * 8 + 8 + 7 * 8
+    assert C.sizeof(N.SolveResult) == 16 + 2 * 64 * 8 + 3 * 8 + 4 * 8 + 7 * 8 + 2 * 8 + 8 + 7 * 8 + 2 * 8 + 4 * 8
 
 
 def test_no_cpu_fallback_without_a_device():

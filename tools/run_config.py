@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--buffers", type=int, default=0)
     ap.add_argument("--max-iter", type=int, default=0)
     ap.add_argument("--threshold", type=float, default=0.0)
+    ap.add_argument("--unfused", action="store_true", help="the reference's solver class call for call (default: fused driver)")
     ap.add_argument("--cold", action="store_true", help="report the first solve (includes first-touch allocation of the pool)")
     args = ap.parse_args()
     rank, world, local = D.env_rank_world()
@@ -56,6 +57,8 @@ def main():
         kw["max_iter"] = args.max_iter
     if args.threshold:
         kw["convergence_threshold"] = args.threshold
+    if kw["kind"] == N.KIND_DAVIDSON and not args.unfused:
+        kw["fused"] = 1
     spec = H.make_spec(**kw)
     ctx.set_profiling(True)
     ctx.mem_usage(reset_peak=True)
@@ -81,6 +84,10 @@ def main():
         "gemm_inner_gbs": res.bytes_gemm_inner / res.seconds_gemm_inner / 1e9 if res.seconds_gemm_inner else None,
         "gemm_outer_gbs": res.bytes_gemm_outer / res.seconds_gemm_outer / 1e9 if res.seconds_gemm_outer else None,
         "streaming_gbs": res.bytes_blas1 / res.seconds_blas1 / 1e9 if res.seconds_blas1 else None,
+        "residual_gbs": res.bytes_residual / res.seconds_residual / 1e9 if res.seconds_residual else None,
+        "seconds_by_family": {"gemm_inner": res.seconds_gemm_inner, "gemm_outer": res.seconds_gemm_outer,
+                              "blas1": res.seconds_blas1, "residual": res.seconds_residual},
+        "seconds_action": res.seconds_action,
         "peak_vectors": peak / (8.0 * max(nloc, 1)), "peak_gb_per_gpu": peak / 1e9,
         "launches": int(res.kernel_launches),
         "calls": {"dot": int(res.n_dot), "gemm_inner": int(res.n_gemm_inner), "gemm_outer": int(res.n_gemm_outer),

@@ -15,6 +15,16 @@ SRC = os.path.join(ROOT, "gpurun_out")
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
 
 
+# kernel families as bench.py accounts them (itsolv_counters): name prefixes of the kernels of each
+FAMILIES = {
+    "gemm_inner": ("gemm_inner",),
+    "gemm_outer": ("gemm_outer",),
+    "residual": ("davidson_residual",),
+    "blas1": ("axpy", "scal", "copy", "fill", "precondition", "mgs_step", "shift"),
+    "harness_spmv": ("csr_apply", "banded_apply"),
+}
+
+
 def load(path):
     with open(path) as f:
         lines = [l for l in f if l.startswith('"')]
@@ -85,16 +95,28 @@ def main():
         ours = launches[len(launches) // 2:]  # the second (timed) solve of `bench.py --steps 1 --warmup 1`
         agg, total = table(ours, os.path.join(OUT, f"ncu_dram_bench_{TAG}.csv"), with_dram=True)
         fam = {"n": 0, "us": 0.0, "bytes": 0.0}
+        families = {k: {"launches": 0, "us": 0.0, "bytes": 0.0} for k in FAMILIES}
         for (name, _, _), a in agg.items():
             if name.startswith("gemm_inner"):
                 fam["n"] += a["n"]
                 fam["us"] += a["us"]
                 fam["bytes"] += a["rd"] + a["wr"]
+            for k, prefixes in FAMILIES.items():
+                if name.startswith(prefixes):
+                    families[k]["launches"] += a["n"]
+                    families[k]["us"] += a["us"]
+                    families[k]["bytes"] += a["rd"] + a["wr"]
+        for k, v in families.items():
+            v["share_of_kernel_time"] = v["us"] / total
+            v["dram_bytes_per_launch"] = v["bytes"] / max(v["launches"], 1)
+            v["avg_us"] = v["us"] / max(v["launches"], 1)
+            v["dram_GBps"] = v["bytes"] / v["us"] / 1e3 if v["us"] else 0.0
         with open(os.path.join(OUT, f"ncu_dram_bench_{TAG}.json"), "w") as f:
             json.dump({"command": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
                                   "--clock-control none python bench.py --steps 1 --warmup 1 --min-warmup 1 --no-e2e "
                                   "--no-cpu-baseline (second solve)",
                        "kernel_time_us_one_solve": total, "launches_one_solve": sum(a["n"] for a in agg.values()),
+                       "families": families,
                        "gemm_inner_family": {"launches": fam["n"], "share_of_kernel_time": fam["us"] / total,
                                              "dram_bytes_per_launch": fam["bytes"] / max(fam["n"], 1),
                                              "avg_us": fam["us"] / max(fam["n"], 1)}}, f, indent=1)
