@@ -264,8 +264,11 @@ struct DeviceBackend {
   void synchronize() { check(itsolv_ctx_synchronize(ctx), "synchronize"); }
   std::unique_ptr<its::LinearEigensystemDavidson<R, R, PMap>>
   make_davidson(const std::shared_ptr<itsolv_b200::HandlersCUDA>& handlers, const itsolv_solve_spec& spec) {
-    if (spec.fused)
-      return std::make_unique<itsolv_b200::LinearEigensystemDavidsonFused>(handlers);
+    if (spec.fused) { // 1: fused solve(); 2: the reference's solve() loop over the batched add_vector / end_iteration
+      auto solver = std::make_unique<itsolv_b200::LinearEigensystemDavidsonFused>(handlers);
+      solver->set_fuse_solve(spec.fused != 2);
+      return solver;
+    }
     return std::make_unique<its::LinearEigensystemDavidson<R, R, PMap>>(handlers);
   }
   void timer_start() { check(itsolv_ctx_timer_start(ctx, 0), "timer"); }

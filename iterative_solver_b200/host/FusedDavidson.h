@@ -30,6 +30,7 @@
 #include <map>
 #include <numeric>
 #include <stdexcept>
+#include <tuple>
 #include <memory>
 #include <vector>
 
@@ -129,6 +130,72 @@ public:
     this->qspace.update(params, actions, nd.qq, nd.qx, nd.xq, dims, this->data);
     this->update_dimensions();
   }
+
+  /*!
+   * New D space (reference itsolv/subspace/XSpace.h:174-187 with update_dspace_overlap_data / _action_data, :85-134):
+   * the reference forms S_dd with nD(nD+1)/2 dots and five more blocks with separate contractions; here the D
+   * parameters are contracted with {D, Q parameters, D, Q actions, right-hand sides} in ONE Gram launch and the
+   * remaining block <q_i, A d_j> in a second.
+   */
+  void update_dspace(VecRef<R>& params, VecRef<R>& actions) override {
+    using its::subspace::EqnData;
+    namespace xsp = its::subspace::xspace;
+    this->dspace.update(params, actions);
+    this->update_dimensions();
+    const auto dim = this->m_dim;
+    for (auto e : {EqnData::H, EqnData::S})
+      this->data[e].resize({dim.nX, dim.nX});
+    auto& handlers = *this->m_handlers;
+    const auto pparams = this->cparamsp();
+    const auto qparams = this->cparamsq(), qactions = this->cactionsq(), dparams = this->cparamsd(),
+               dactions = this->cactionsd();
+    const size_t nP = dim.nP, nQ = dim.nQ, nD = dim.nD, nRHS = this->m_rhs.size(), nPQ = nP + nQ;
+    xsp::NewData ov(nD, nPQ, nRHS), act(nD, nPQ, 0);
+    if (nD > 0) {
+      CVecRef<R> cols(dparams.begin(), dparams.end());
+      cols.insert(cols.end(), qparams.begin(), qparams.end());
+      cols.insert(cols.end(), dactions.begin(), dactions.end());
+      cols.insert(cols.end(), qactions.begin(), qactions.end());
+      for (const auto& r : this->m_rhs)
+        cols.emplace_back(std::cref(r));
+      const auto G = handlers.qq().gemm_inner(dparams, cols);
+      for (size_t i = 0; i < nD; ++i) {
+        for (size_t j = 0; j <= i; ++j) // util::overlap of one set mirrors the lower triangle
+          ov.qq[EqnData::S](i, j) = ov.qq[EqnData::S](j, i) = G(i, j);
+        for (size_t j = 0; j < nQ; ++j) {
+          ov.qx[EqnData::S](i, nP + j) = G(i, nD + j);
+          act.qx[EqnData::H](i, nP + j) = G(i, 2 * nD + nQ + j);
+        }
+        for (size_t j = 0; j < nD; ++j)
+          act.qq[EqnData::H](i, j) = G(i, nD + nQ + j);
+        for (size_t j = 0; j < nRHS; ++j)
+          ov.qq[EqnData::rhs](i, j) = G(i, 2 * nD + 2 * nQ + j);
+      }
+      if (nQ > 0) {
+        const auto Gqd = handlers.qq().gemm_inner(qparams, dactions);
+        for (size_t i = 0; i < nQ; ++i)
+          for (size_t j = 0; j < nD; ++j)
+            act.xq[EqnData::H](nP + i, j) = Gqd(i, j);
+      }
+      if (nP > 0) { // sparse P vectors through the dense x sparse handler (rows: dense)
+        const auto Sdp = handlers.qp().gemm_inner(dparams, pparams);
+        const auto Hdp = handlers.qp().gemm_inner(dactions, pparams);
+        for (size_t i = 0; i < nD; ++i)
+          for (size_t j = 0; j < nP; ++j) {
+            ov.qx[EqnData::S](i, j) = Sdp(i, j);
+            act.xq[EqnData::H](j, i) = Hdp(i, j);
+            act.qx[EqnData::H](i, j) = Hdp(i, j);
+          }
+      }
+      for (size_t i = 0; i < nD; ++i)
+        for (size_t j = 0; j < nPQ; ++j)
+          ov.xq[EqnData::S](j, i) = ov.qx[EqnData::S](i, j);
+    }
+    xsp::copy_dspace_eqn_data(ov, this->data, EqnData::S, dim);
+    xsp::copy_dspace_eqn_data(act, this->data, EqnData::H, dim);
+    this->data[EqnData::rhs].resize({dim.nX, dim.nRHS});
+    this->data[EqnData::rhs].slice({dim.oD, 0}, {dim.oD + dim.nD, dim.nRHS}) = ov.qq[EqnData::rhs].slice();
+  }
 };
 
 class LinearEigensystemDavidsonFused
@@ -151,6 +218,8 @@ public:
   }
 
   using Base::solve;
+  //! false: solve() is the reference's own loop and only add_vector / solution / end_iteration are batched
+  void set_fuse_solve(bool on) { m_fuse_solve = on; }
   /*!
    * The reference's one-call driver (IterativeSolverTemplate.h:322-408), statement for statement, with three changes that
    * do not alter what is computed:
@@ -169,6 +238,8 @@ public:
       throw std::runtime_error("Empty container passed to IterativeSolver::solve()");
     if (parameters.size() != actions.size())
       throw std::runtime_error("Inconsistent container sizes in IterativeSolver::solve()");
+    if (!m_fuse_solve)
+      return Base::solve(parameters, actions, problem, generate_initial_guess);
     struct InSolve {
       bool& flag;
       explicit InSolve(bool& f) : flag(f) { flag = true; }
@@ -415,6 +486,63 @@ protected:
                         VecRef<R>(actions.begin(), actions.begin() + roots.size()));
   }
 
+  /*!
+   * New D vectors from the Q vectors that leave the Q space and the old D vectors (reference
+   * itsolv/propose_rspace.h:350-403). The host part - projected solutions, their overlaps, null-space removal - is the
+   * reference's own functions; the vectors, which the reference builds with nD (nQd + nD) axpy pairs on zeroed copies
+   * (3 vector passes each), come from two expansions that write their targets without reading them, one Gram launch for
+   * the norms and one scaling launch.
+   */
+  std::tuple<std::vector<R>, std::vector<R>> construct_dspace_fused(const Matrix<double>& solutions,
+                                                                   const std::vector<int>& q_delete) {
+    namespace dsp = its::detail::dspace;
+    auto& xspace = *this->m_xspace;
+    auto& logger = *this->m_logger;
+    const auto dims = xspace.dimensions();
+    const auto overlap = xspace.data.at(its::subspace::EqnData::S);
+    const auto norm_thresh = this->propose_rspace_norm_thresh;
+    const auto svd_thresh = this->propose_rspace_svd_thresh;
+    auto solutions_proj = dsp::construct_projected_solution(solutions, dims, q_delete, logger);
+    auto overlap_proj = dsp::construct_projected_solutions_overlap(solutions_proj, overlap, dims, q_delete, logger);
+    dsp::remove_null_norm_and_normalise(solutions_proj, overlap_proj, norm_thresh, logger);
+    solutions_proj = dsp::remove_null_projected_solutions(solutions_proj, overlap_proj, svd_thresh, logger);
+    overlap_proj = dsp::construct_projected_solutions_overlap(solutions_proj, overlap, dims, q_delete, logger);
+    dsp::remove_null_norm_and_normalise(solutions_proj, overlap_proj, norm_thresh, logger);
+    const size_t nD = solutions_proj.rows(), nQd = q_delete.size();
+    const auto qparams = xspace.cparamsq(), qactions = xspace.cactionsq();
+    const auto dparams = xspace.cparamsd(), dactions = xspace.cactionsd();
+    std::vector<R> dparams_new, dactions_new;
+    if (nD == 0 || (qparams.empty() && dparams.empty()))
+      return std::make_tuple(std::move(dparams_new), std::move(dactions_new));
+    const R& shape = !qparams.empty() ? qparams.front().get() : dparams.front().get();
+    for (size_t i = 0; i < nD; ++i) {
+      dparams_new.emplace_back(shape.size(), shape.context());
+      dactions_new.emplace_back(shape.size(), shape.context());
+    }
+    CVecRef<R> xpar, xact;
+    for (auto j : q_delete) {
+      xpar.emplace_back(qparams.at(j));
+      xact.emplace_back(qactions.at(j));
+    }
+    xpar.insert(xpar.end(), dparams.begin(), dparams.end());
+    xact.insert(xact.end(), dactions.begin(), dactions.end());
+    Matrix<double> c({nQd + dims.nD, nD});
+    for (size_t i = 0; i < nD; ++i)
+      for (size_t j = 0; j < nQd + dims.nD; ++j)
+        c(j, i) = solutions_proj(i, j);
+    m_dense->gemm_outer_assign(c, xpar, its::wrap(dparams_new));
+    m_dense->gemm_outer_assign(c, xact, its::wrap(dactions_new));
+    const auto d = m_dense->self_dots(its::cwrap(dparams_new));
+    std::vector<double> alpha(2 * nD);
+    VecRef<R> both = its::wrap(dparams_new);
+    for (auto& a : dactions_new)
+      both.emplace_back(a);
+    for (size_t i = 0; i < nD; ++i)
+      alpha[i] = alpha[nD + i] = 1. / std::sqrt(std::abs(d[i]));
+    m_dense->scal_batch(alpha, both);
+    return std::make_tuple(std::move(dparams_new), std::move(dactions_new));
+  }
+
   //! ||p|| -> 1 for every vector of the set: one Gram launch for the norms, one launch for the scaling
   void normalise_set(const VecRef<R>& params, double thresh = 1.0e-14) {
     if (params.empty())
@@ -447,8 +575,7 @@ protected:
     // Q-space limit -> D space: rare, left to the reference's routines (they go through the same handlers)
     auto q_delete = det::limit_qspace_size(xspace.dimensions(), this->m_max_size_qspace, solutions, logger);
     if (!q_delete.empty()) {
-      auto [dparams, dactions] = det::construct_dspace(solutions, xspace, q_delete, this->propose_rspace_norm_thresh,
-                                                       this->propose_rspace_svd_thresh, handlers.qq(), logger);
+      auto [dparams, dactions] = construct_dspace_fused(solutions, q_delete);
       std::sort(begin(q_delete), end(q_delete), std::greater<int>());
       for (auto iq : q_delete)
         xspace.eraseq(iq);
@@ -627,6 +754,7 @@ protected:
 
   ArrayHandlerCUDA* m_dense = nullptr;
   bool m_in_fused_solve = false;
+  bool m_fuse_solve = true;
   std::vector<double> m_written_norms; //!< <r,r> of the working set's preconditioned residuals, from the residual kernel
 };
 

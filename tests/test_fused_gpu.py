@@ -140,3 +140,26 @@ def test_fused_path_needs_far_fewer_calls(ctx):
     assert fused.handler_bytes < 0.7 * plain.handler_bytes
     for i in range(4):
         assert abs(fused.eigenvalues[i] / plain.eigenvalues[i] - 1) <= 1e-12
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n=30000, nroots=16, max_size_qspace=8, nbuffers=8),   # BASELINE.json configs[3] in small: D space + root batches
+    dict(n=30000, nroots=16, max_size_qspace=8),
+    dict(n=20011, nroots=6, max_size_qspace=6, nbuffers=3),
+    dict(n=20011, nroots=8, max_size_qspace=4, reset_D=3),
+    dict(n=20011, nroots=5, max_size_qspace=5, nbuffers=2, hermitian=0),
+], ids=lambda kw: "_".join(f"{k}{v}" for k, v in kw.items()))
+def test_fused_solve_matches_the_reference_run_here(ctx, oracle, kw):
+    """memory-capped configurations (Q-space limit -> D space, fewer buffers than roots, D-space resets): the fused
+    driver against the reference's own templates run in this process on the same operator"""
+    if oracle.ref is None:
+        pytest.skip("oracle/_ref is not built")
+    kw = dict(kw)
+    kw.setdefault("hermitian", 1)
+    want, _ = oracle.ref.solve(H.make_spec(kind=N.KIND_DAVIDSON, **kw))
+    got, _ = H.solve(ctx, H.make_spec(kind=N.KIND_DAVIDSON, fused=1, **kw))
+    assert got.iterations == want.iterations and got.converged == want.converged
+    assert [got.r_creations, got.q_creations, got.p_creations, got.d_creations] == \
+           [want.r_creations, want.q_creations, want.p_creations, want.d_creations]
+    for i in range(kw["nroots"]):
+        assert abs(got.eigenvalues[i] / want.eigenvalues[i] - 1) <= 1e-10
