@@ -73,6 +73,7 @@ struct itsolv_ctx {
   std::vector<cudaEvent_t> stage_events;
   // select scratch
   unsigned long long* d_select = nullptr;
+  unsigned long long* d_select_cand = nullptr; // candidates of the radix select: [key | global index | value] x capacity
 
   itsolv::Comm* comm = nullptr;
 

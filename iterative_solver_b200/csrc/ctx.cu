@@ -273,6 +273,7 @@ void itsolv_ctx_destroy(itsolv_ctx* ctx) {
   cudaFreeHost(ctx->h_stage);
   cudaFree(ctx->d_stage);
   cudaFree(ctx->d_select);
+  cudaFree(ctx->d_select_cand);
   if (ctx->own_stream)
     cudaStreamDestroy(ctx->stream);
   delete ctx;

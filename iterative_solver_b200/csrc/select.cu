@@ -3,8 +3,11 @@
 // array/DistrArray.cpp:191-224). The reference keeps the n largest (key, index) PAIRS under lexicographic order,
 // key = v or |v| (max) / -v or -|v| (min), so among equal keys the higher index wins. That rule is reproduced exactly
 // by a most-significant-digit radix select over the 128-bit composite (order-preserving image of key, global index):
-// 8 histogram passes over the key bytes + the index bytes that can be non-zero, all on the device with no host round
-// trip, then one compaction pass. Runs once or twice per solve (initial guess, P-space choice), HBM-bound, 8n bytes/pass.
+// histogram passes over the key bytes + the index bytes that can be non-zero, each finished by its last CTA (which picks
+// the boundary bin), all on the device with no host round trip. Only the two leading key bytes and one gather pass read
+// the vector; the gather pass moves the boundary bucket (at most 2^20 elements, else the vector keeps being read) into
+// a candidate buffer on which the remaining passes and the final compaction run. Runs once or twice per solve (initial
+// guess, P-space choice): 3 passes of 8n bytes.
 #include <algorithm>
 #include <cstring>
 #include <utility>
@@ -15,7 +18,9 @@
 namespace itsolv {
 
 // layout of ctx->d_select (unsigned long long words)
-enum { SEL_KEY = 0, SEL_IDX = 1, SEL_REMAINING = 2, SEL_COUNT = 3, SEL_HIST = 16 };
+enum { SEL_KEY = 0, SEL_IDX = 1, SEL_REMAINING = 2, SEL_COUNT = 3, SEL_NCAND = 4, SEL_TICKET = 5, SEL_HIST = 16 };
+
+constexpr unsigned long long kSelCandCapacity = 1ull << 20; // candidates kept after the two leading key bytes
 
 struct SelParams {
   const double* x;
@@ -23,6 +28,10 @@ struct SelParams {
   size_t n;
   unsigned long long offset; // global index of x[0]
   int max, ignore_sign;
+  // candidates gathered after the first two passes (key image, global index, value); used while their number fits
+  const unsigned long long* cand_key;
+  const unsigned long long* cand_idx;
+  const double* cand_val;
 };
 
 __device__ __forceinline__ double sel_value(const SelParams& p, size_t i) {
@@ -57,54 +66,110 @@ __device__ __forceinline__ bool sel_digit(unsigned long long u, unsigned long lo
   return true;
 }
 
+/*!
+ * Histogram of digit `d` over the elements that agree with the digits fixed so far; the last CTA to finish then picks
+ * the bin that holds the boundary element (walk from the top bin until `remaining` elements are covered), fixes the digit
+ * and clears the histogram for the next pass. From digit 2 on the pass runs over the gathered candidates when they fit.
+ */
 __global__ void __launch_bounds__(256) select_hist_kernel(const __grid_constant__ SelParams p, int d,
                                                           unsigned long long* __restrict__ state) {
   __shared__ unsigned int hist[256];
+  __shared__ unsigned long long suffix[257];
+  __shared__ int s_last;
   hist[threadIdx.x] = 0;
   __syncthreads();
   const unsigned long long kpre = state[SEL_KEY], ipre = state[SEL_IDX];
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n; i += size_t(gridDim.x) * blockDim.x) {
-    const unsigned long long u = sel_key(p, sel_value(p, i));
+  const unsigned long long ncand = state[SEL_NCAND];
+  const bool from_candidates = d >= 2 && ncand <= kSelCandCapacity;
+  const size_t count = from_candidates ? size_t(ncand) : p.n;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x) {
+    const unsigned long long u = from_candidates ? p.cand_key[i] : sel_key(p, sel_value(p, i));
+    const unsigned long long gi = from_candidates ? p.cand_idx[i] : p.offset + i;
     unsigned digit;
-    if (sel_digit(u, p.offset + i, d, kpre, ipre, digit))
+    if (sel_digit(u, gi, d, kpre, ipre, digit))
       atomicAdd(&hist[digit], 1u);
   }
   __syncthreads();
   if (hist[threadIdx.x])
     atomicAdd(&state[SEL_HIST + threadIdx.x], (unsigned long long)hist[threadIdx.x]);
-}
-
-//! choose the bin that holds the boundary element: walk bins from the top until `remaining` elements are covered
-__global__ void select_pick_kernel(int d, unsigned long long* __restrict__ state) {
-  if (threadIdx.x != 0 || blockIdx.x != 0)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0)
+    s_last = atomicAdd(&state[SEL_TICKET], 1ull) == gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  if (!s_last)
     return;
-  unsigned long long remaining = state[SEL_REMAINING];
-  int chosen = 0;
-  for (int bin = 255; bin >= 0; --bin) {
-    const unsigned long long c = state[SEL_HIST + bin];
-    if (c >= remaining) {
-      chosen = bin;
-      break;
-    }
-    remaining -= c;
+  __threadfence();
+  // inclusive suffix sums: suffix[b] = number of elements in bins >= b
+  const int t = threadIdx.x;
+  const unsigned long long remaining = state[SEL_REMAINING]; // read by all before the barriers below, written after them
+  suffix[t] = __ldcg(&state[SEL_HIST + t]);
+  if (t == 0)
+    suffix[256] = 0;
+  __syncthreads();
+  for (int step = 1; step < 256; step <<= 1) {
+    const unsigned long long add = t + step < 256 ? suffix[t + step] : 0;
+    __syncthreads();
+    suffix[t] += add;
+    __syncthreads();
   }
-  state[SEL_REMAINING] = remaining;
-  if (d < 8)
-    state[SEL_KEY] |= (unsigned long long)chosen << (56 - 8 * d);
-  else
-    state[SEL_IDX] |= (unsigned long long)chosen << (56 - 8 * (d - 8));
-  for (int bin = 0; bin < 256; ++bin)
-    state[SEL_HIST + bin] = 0;
+  if (suffix[t] >= remaining && suffix[t + 1] < remaining) {
+    state[SEL_REMAINING] = remaining - suffix[t + 1];
+    if (d < 8)
+      state[SEL_KEY] = kpre | ((unsigned long long)t << (56 - 8 * d));
+    else
+      state[SEL_IDX] = ipre | ((unsigned long long)t << (56 - 8 * (d - 8)));
+  }
+  state[SEL_HIST + t] = 0;
+  if (t == 0)
+    state[SEL_TICKET] = 0;
 }
 
+/*!
+ * After the two leading key bytes are fixed: elements above the boundary prefix are selected for certain and go straight
+ * to the output; elements with the boundary prefix become the candidates of the remaining passes.
+ */
+__global__ void __launch_bounds__(256)
+    select_gather_kernel(const __grid_constant__ SelParams p, unsigned long long* __restrict__ state,
+                         unsigned long long* __restrict__ cand_key, unsigned long long* __restrict__ cand_idx,
+                         double* __restrict__ cand_val, long long* __restrict__ out_idx, double* __restrict__ out_val,
+                         unsigned long long capacity) {
+  const unsigned long long prefix = state[SEL_KEY] >> 48;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n; i += size_t(gridDim.x) * blockDim.x) {
+    const double value = sel_value(p, i);
+    const unsigned long long u = sel_key(p, value);
+    const unsigned long long top = u >> 48;
+    if (top > prefix) {
+      const unsigned long long pos = atomicAdd(&state[SEL_COUNT], 1ull);
+      if (pos < capacity) {
+        out_idx[pos] = (long long)(p.offset + i);
+        out_val[pos] = value;
+      }
+    } else if (top == prefix) {
+      const unsigned long long pos = atomicAdd(&state[SEL_NCAND], 1ull);
+      if (pos < kSelCandCapacity) {
+        cand_key[pos] = u;
+        cand_idx[pos] = p.offset + i;
+        cand_val[pos] = value;
+      }
+    }
+  }
+}
+
+//! elements with the boundary prefix that lie at or above the boundary (key, index) pair
 __global__ void __launch_bounds__(256)
     select_compact_kernel(const __grid_constant__ SelParams p, unsigned long long* __restrict__ state,
                           long long* __restrict__ out_idx, double* __restrict__ out_val, unsigned long long capacity) {
   const unsigned long long kthr = state[SEL_KEY], ithr = state[SEL_IDX];
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n; i += size_t(gridDim.x) * blockDim.x) {
-    const double value = sel_value(p, i);
-    const unsigned long long u = sel_key(p, value);
-    const unsigned long long gi = p.offset + i;
+  const unsigned long long ncand = state[SEL_NCAND];
+  const bool from_candidates = ncand <= kSelCandCapacity;
+  const size_t count = from_candidates ? size_t(ncand) : p.n;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x) {
+    const double value = from_candidates ? p.cand_val[i] : sel_value(p, i);
+    const unsigned long long u = from_candidates ? p.cand_key[i] : sel_key(p, value);
+    const unsigned long long gi = from_candidates ? p.cand_idx[i] : p.offset + i;
+    if ((u >> 48) != (kthr >> 48))
+      continue; // above the prefix: already in the output; below: not selected
     if (u > kthr || (u == kthr && gi >= ithr)) {
       const unsigned long long pos = atomicAdd(&state[SEL_COUNT], 1ull);
       if (pos < capacity) {
@@ -166,10 +231,16 @@ int itsolv_select_f64(itsolv_ctx* ctx, const double* x, const double* y, size_t 
   double* d_val = reinterpret_cast<double*>(dmine + nsel * 8);
   ITSOLV_CUDA(cudaMemsetAsync(dmine, 0xFF, nsel * 8, ctx->stream)); // idx = -1: empty candidate
   if (nloc > 0) {
-    SelParams p{x, y, n, (unsigned long long)global_offset, (max || y) ? 1 : 0, ignore_sign};
+    if (!ctx->d_select_cand)
+      ITSOLV_CUDA(cudaMalloc(&ctx->d_select_cand, kSelCandCapacity * 3 * sizeof(unsigned long long)));
+    unsigned long long* cand_key = ctx->d_select_cand;
+    unsigned long long* cand_idx = cand_key + kSelCandCapacity;
+    double* cand_val = reinterpret_cast<double*>(cand_idx + kSelCandCapacity);
+    SelParams p{x, y, n, (unsigned long long)global_offset, (max || y) ? 1 : 0, ignore_sign, cand_key, cand_idx, cand_val};
     unsigned long long init[SEL_HIST + 256];
     std::memset(init, 0, sizeof(init));
     init[SEL_REMAINING] = nloc;
+    init[SEL_NCAND] = ~0ull; // no candidates gathered yet
     ITSOLV_CUDA(cudaMemcpyAsync(ctx->d_select, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     const int grid = int(std::min<size_t>((n + 255) / 256, size_t(ctx->num_sms) * 8));
     // index bytes above the largest global index are zero for every element: skip those passes
@@ -180,11 +251,17 @@ int itsolv_select_f64(itsolv_ctx* ctx, const double* x, const double* y, size_t 
     for (int dgt = 0; dgt < 16; ++dgt) {
       if (dgt >= 8 && dgt - 8 < 8 - idx_bytes)
         continue;
-      select_hist_kernel<<<grid, 256, 0, ctx->stream>>>(p, dgt, ctx->d_select);
-      select_pick_kernel<<<1, 32, 0, ctx->stream>>>(dgt, ctx->d_select);
-      ctx->counters.launches += 2;
+      if (dgt == 2) { // two key bytes are fixed: certain elements to the output, the boundary bucket to the candidates
+        ITSOLV_CUDA(cudaMemsetAsync(ctx->d_select + SEL_NCAND, 0, sizeof(unsigned long long), ctx->stream));
+        select_gather_kernel<<<grid, 256, 0, ctx->stream>>>(p, ctx->d_select, cand_key, cand_idx, cand_val, d_idx, d_val,
+                                                            nloc);
+        ctx->counters.launches += 1;
+      }
+      // the passes over the candidates are short: a grid of one CTA per SM is plenty
+      select_hist_kernel<<<dgt < 2 ? grid : std::min(grid, ctx->num_sms), 256, 0, ctx->stream>>>(p, dgt, ctx->d_select);
+      ctx->counters.launches += 1;
     }
-    select_compact_kernel<<<grid, 256, 0, ctx->stream>>>(p, ctx->d_select, d_idx, d_val, nloc);
+    select_compact_kernel<<<std::min(grid, ctx->num_sms), 256, 0, ctx->stream>>>(p, ctx->d_select, d_idx, d_val, nloc);
     ctx->counters.launches += 1;
     ITSOLV_CUDA(cudaGetLastError());
   }

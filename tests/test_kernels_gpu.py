@@ -196,6 +196,18 @@ def test_precondition_bit_exact(ctx, oracle, w, n):
     assert np.array_equal(dR.cpu().numpy(), oracle.c.precondition(R, shift, diag))
 
 
+@pytest.mark.parametrize("mode", ["min", "max"])
+def test_select_when_the_boundary_bucket_exceeds_the_candidate_buffer(ctx, oracle, mode):
+    """1.3e6 values that share sign, exponent and the four leading mantissa bits: more candidates after the two leading
+    key bytes than the candidate buffer (2^20) holds, so the later passes keep reading the vector; many exact ties"""
+    rng = np.random.default_rng(3)
+    x = 1.0 + np.round(0.05 * rng.random(1_300_000), 4)
+    kw = {"max": True} if mode == "max" else {}
+    idx, val = ctx.select(dev(x), 9, **kw)
+    want_idx, want_val = oracle.c.select(x, 9, **kw)
+    assert np.array_equal(idx, want_idx) and np.array_equal(val, want_val)
+
+
 def same_bits_or_both_nan(got, want):
     nan = np.isnan(want)
     return np.array_equal(np.isnan(got), nan) and np.array_equal(got[~nan].view(np.uint64), want[~nan].view(np.uint64))
