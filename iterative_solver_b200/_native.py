@@ -174,6 +174,41 @@ HARNESS_API = {
 }
 
 
+# declarations of include/itsolv_b200_solver.h (flat C interface of the solvers over device buffers)
+c_size_p = C.POINTER(C.c_size_t)
+APPLY_ON_P = C.CFUNCTYPE(None, c_double_p, C.c_void_p, C.c_size_t, c_size_p)
+SOLVER_API = {
+    "ItsolvB200LinearEigensystemInitialize": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, c_size_p, c_size_p,
+                                                        C.c_double, C.c_double, C.c_int, C.c_int, C.c_char_p]),
+    "ItsolvB200LinearEquationsInitialize": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, c_size_p, c_size_p,
+                                                      C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                                      C.c_char_p]),
+    "ItsolvB200NonLinearEquationsInitialize": (C.c_int, [C.c_void_p, C.c_size_t, c_size_p, c_size_p, C.c_double,
+                                                         C.c_int, C.c_char_p]),
+    "ItsolvB200Finalize": (C.c_int, []),
+    "ItsolvB200AddVector": (C.c_long, [C.c_size_t, C.c_void_p, C.c_void_p]),
+    "ItsolvB200Solution": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]),
+    "ItsolvB200EndIteration": (C.c_long, [C.c_size_t, C.c_void_p, C.c_void_p]),
+    "ItsolvB200EndIterationNeeded": (C.c_int, []),
+    "ItsolvB200AddP": (C.c_long, [C.c_size_t, C.c_size_t, c_size_p, c_size_p, c_double_p, c_double_p, C.c_void_p,
+                                  C.c_void_p, APPLY_ON_P]),
+    "ItsolvB200Errors": (C.c_int, [c_double_p]),
+    "ItsolvB200Eigenvalues": (C.c_int, [c_double_p]),
+    "ItsolvB200WorkingSetEigenvalues": (C.c_int, [c_double_p]),
+    "ItsolvB200WorkingSet": (C.c_long, [C.POINTER(C.c_int)]),
+    "ItsolvB200NonLinear": (C.c_int, []),
+    "ItsolvB200HasEigenvalues": (C.c_int, []),
+    "ItsolvB200SetDiagonals": (C.c_int, [C.c_void_p]),
+    "ItsolvB200Diagonals": (C.c_int, [C.c_void_p]),
+    "ItsolvB200PreconditionDefault": (C.c_int, [C.c_size_t, C.c_void_p]),
+    "ItsolvB200Verbosity": (C.c_int, []),
+    "ItsolvB200MaxIter": (C.c_int, []),
+    "ItsolvB200SetMaxIter": (C.c_int, [C.c_int]),
+    "ItsolvB200Iterations": (C.c_long, []),
+    "ItsolvB200LastError": (C.c_char_p, []),
+}
+
+
 def _bind(lib: C.CDLL, table: dict) -> None:
     for name, (restype, argtypes) in table.items():
         fn = getattr(lib, name)  # AttributeError = the library does not export what the header declares
@@ -208,5 +243,6 @@ def host() -> C.CDLL:
             raise ImportError(f"{path} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
         lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
         _bind(lib, HARNESS_API)
+        _bind(lib, SOLVER_API)
         _host = lib
     return _host

@@ -87,7 +87,8 @@ def build_host(force: bool = False) -> str:
         "options.cpp", "itsolv/Logger.cpp", "itsolv/util.cpp", "itsolv/Options.cpp",
         "itsolv/LinearEigensystemDavidsonOptions.cpp", "itsolv/LinearEquationsDavidsonOptions.cpp",
         "itsolv/NonLinearEquationsDIISOptions.cpp")]
-    own_cpp = [os.path.join(PKG, "host", "helper_lapack.cpp"), os.path.join(PKG, "harness", "solver_capi.cpp")]
+    own_cpp = [os.path.join(PKG, "host", "helper_lapack.cpp"), os.path.join(PKG, "harness", "solver_capi.cpp"),
+               os.path.join(PKG, "harness", "solver_flat_capi.cpp")]
     headers = (glob.glob(os.path.join(PKG, "host", "*.h")) + glob.glob(os.path.join(PKG, "harness", "*.h")) +
                glob.glob(os.path.join(ROOT, "include", "*.h")))
     flags = ["-std=c++17", "-O2", "-DNDEBUG", "-fPIC", "-ffp-contract=off", "-w",

@@ -48,6 +48,26 @@ public:
     check(itsolv_alloc(m_ctx, m_local, &m_data), "DistrArrayCUDA: allocation");
   }
 
+  /*!
+   * Non-owning view of caller-owned DEVICE memory as this rank's shard of a vector of global length `dimension`
+   * (`local_size()` doubles at `data`): what DistrArraySpan is for host buffers in the reference's C interface
+   * (reference array/DistrArraySpan.h:8-48, IterativeSolverCMPI.cpp:89-107). Copies of a view own their memory.
+   */
+  static DistrArrayCUDA view(size_t dimension, itsolv_ctx* ctx, double* data) {
+    DistrArrayCUDA v;
+    v.m_ctx = ctx;
+    v.m_dimension = dimension;
+    const int nranks = itsolv_comm_size(ctx), rank = itsolv_comm_rank(ctx);
+    std::vector<int64_t> borders(size_t(nranks) + 1);
+    itsolv_distribution(dimension, nranks, borders.data());
+    v.m_start = size_t(borders[rank]);
+    v.m_local = size_t(borders[rank + 1] - borders[rank]);
+    v.m_data = data;
+    v.m_owner = false;
+    return v;
+  }
+  bool owns() const { return m_owner; }
+
   DistrArrayCUDA(const DistrArrayCUDA& source)
       : m_ctx(source.m_ctx), m_dimension(source.m_dimension), m_start(source.m_start), m_local(source.m_local) {
     if (source.m_data) {
@@ -137,12 +157,15 @@ public:
     std::swap(m_start, o.m_start);
     std::swap(m_local, o.m_local);
     std::swap(m_data, o.m_data);
+    std::swap(m_owner, o.m_owner);
   }
 
   //! Hands this vector's contents to a new array without moving a byte: the new array owns the old allocation, this one
   //! continues with a fresh allocation of the same shape whose contents are unspecified. For callers that are about to
   //! overwrite this vector anyway (the fused driver path: R vectors entering the Q space).
   DistrArrayCUDA take_contents() {
+    if (!m_owner) // a view cannot give its memory away
+      return DistrArrayCUDA(*this);
     DistrArrayCUDA fresh(m_dimension, m_ctx);
     std::swap(m_data, fresh.m_data);
     itsolv_ctx_note_write(m_ctx);
@@ -171,9 +194,10 @@ private:
   }
 
   void release() noexcept {
-    if (m_data && m_ctx)
+    if (m_data && m_ctx && m_owner)
       itsolv_free(m_ctx, m_data);
     m_data = nullptr;
+    m_owner = true;
   }
 
   itsolv_ctx* m_ctx = nullptr;
@@ -181,6 +205,7 @@ private:
   size_t m_start = 0;
   size_t m_local = 0;
   double* m_data = nullptr;
+  bool m_owner = true;
 };
 
 } // namespace itsolv_b200

@@ -458,7 +458,9 @@ protected:
     m_written_norms.clear();
     for (size_t i = 0; i < this->m_working_set.size(); ++i) {
       const size_t root = this->m_working_set[i];
-      if (batches.size() > 1) {
+      if (batches.size() > 1 && !actions[i].get().owns()) {
+        this->m_handlers->rq().copy(actions[i], parked.at(root));
+      } else if (batches.size() > 1) {
         actions[i].get().swap(parked.at(root));
       } else {
         if (root < i)
@@ -744,7 +746,8 @@ protected:
     }
     auto new_working_set = det::get_new_working_set(this->working_set(), its::cwrap(residuals), its::cwrap(wresidual));
     for (size_t i = 0; i < wresidual.size(); ++i) {
-      if (m_in_fused_solve) // the residual buffers are scratch until the next action() fills them: no copy needed
+      // inside solve() the residual buffers are scratch until the next action() fills them: no copy needed
+      if (m_in_fused_solve && parameters.at(i).get().owns() && wresidual.at(i).get().owns())
         parameters.at(i).get().swap(wresidual.at(i).get());
       else
         handlers.rr().copy(parameters.at(i), wresidual.at(i));

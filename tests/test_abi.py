@@ -33,6 +33,21 @@ def test_host_library_exports_every_declared_symbol():
     assert sorted(N.HARNESS_API) == names
 
 
+def test_host_library_exports_the_flat_solver_interface():
+    lib = N.host()
+    text = open(os.path.join(ROOT, "include", "itsolv_b200_solver.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = sorted(set(re.findall(r"\b(ItsolvB200[A-Za-z]+)\s*\(", text)))
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), f"{name} is declared in include/itsolv_b200_solver.h but not exported"
+    assert sorted(N.SOLVER_API) == names
+    # no instance is active: calls fail with a message instead of crashing (the reference throws, IterativeSolverCMPI.cpp:283)
+    assert lib.ItsolvB200AddVector(1, None, None) == -1
+    assert b"not initialised" in lib.ItsolvB200LastError()
+    assert lib.ItsolvB200Finalize() != 0
+
+
 def test_struct_layouts_match_the_header():
     import ctypes as C
     assert C.sizeof(N.SolveSpec) == 80

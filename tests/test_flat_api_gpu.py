@@ -1,0 +1,139 @@
+"""The flat C interface of the solvers over DEVICE buffers (include/itsolv_b200_solver.h, the counterpart of the
+reference's src/molpro/linalg/IterativeSolverC.h): a caller that owns its vectors in GPU memory drives the solvers step
+by step - AddVector / PreconditionDefault / EndIteration / Solution - exactly as the reference's solve() does
+(itsolv/IterativeSolverTemplate.h:322-408), and must arrive at the reference's golden results."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from iterative_solver_b200 import _native as N
+
+pytestmark = pytest.mark.gpu
+HUGE = float(np.finfo(np.float64).max)
+B, EPS = 4, 1e-3
+
+with open(os.path.join(os.path.dirname(__file__), "golden", "solve_golden.json")) as f:
+    GOLDEN = json.load(f)
+
+
+def check(lib, rc):
+    assert rc == 0, lib.ItsolvB200LastError().decode()
+
+
+def apply_operator(ctx, x, y, n):
+    for k in range(x.shape[0]):
+        ctx.banded_apply(x[k], y[k], n, 0, B, EPS)
+
+
+def drive(lib, ctx, params, action, nwork, n, precondition=True):
+    """the loop of the reference's solve() over the flat interface"""
+    nbuf = params.shape[0]
+    for _ in range(100):
+        if nwork <= 0:
+            break
+        apply_operator(ctx, params[:nwork], action[:nwork], n)
+        nwork = lib.ItsolvB200AddVector(nbuf, params.data_ptr(), action.data_ptr())
+        assert nwork >= 0, lib.ItsolvB200LastError().decode()
+        while lib.ItsolvB200EndIterationNeeded() == 1:
+            if nwork > 0 and precondition:
+                check(lib, lib.ItsolvB200PreconditionDefault(nwork, action.data_ptr()))
+            nwork = lib.ItsolvB200EndIteration(nbuf, params.data_ptr(), action.data_ptr())
+            assert nwork >= 0, lib.ItsolvB200LastError().decode()
+    return nwork
+
+
+@pytest.mark.parametrize("name,options", [("banded_davidson_n100000_r4", b""), ("banded_davidson_n100000_r4", b"fused=0"),
+                                          ("banded_davidson_n30000_r6_qcap8", b"max_size_qspace=8")])
+def test_davidson_through_the_flat_interface(ctx, name, options):
+    want = GOLDEN[name]
+    n, nroots = want["spec"]["n"], want["spec"]["nroots"]
+    lib = N.host()
+    lo, hi = C.c_size_t(), C.c_size_t()
+    check(lib, lib.ItsolvB200LinearEigensystemInitialize(ctx.handle, n, nroots, C.byref(lo), C.byref(hi), 1e-8, HUGE, 1, 0,
+                                                        options))
+    try:
+        assert (lo.value, hi.value) == (0, n)
+        assert lib.ItsolvB200HasEigenvalues() == 1 and lib.ItsolvB200NonLinear() == 0
+        params = torch.zeros((nroots, n), dtype=torch.float64, device="cuda")
+        action = torch.zeros_like(params)
+        diag = torch.arange(1, n + 1, dtype=torch.float64, device="cuda")
+        check(lib, lib.ItsolvB200SetDiagonals(diag.data_ptr()))
+        back = torch.zeros_like(diag)
+        check(lib, lib.ItsolvB200Diagonals(back.data_ptr()))
+        assert torch.equal(back, diag)
+        for k in range(nroots):  # the default initial guess: unit vectors on the smallest diagonal elements
+            params[k, k] = 1.0
+        nwork = drive(lib, ctx, params, action, nroots, n)
+        assert nwork == 0
+        assert lib.ItsolvB200Iterations() == want["iterations"]
+        ev, err = np.zeros(nroots), np.zeros(nroots)
+        check(lib, lib.ItsolvB200Eigenvalues(ev.ctypes.data_as(N.c_double_p)))
+        check(lib, lib.ItsolvB200Errors(err.ctypes.data_as(N.c_double_p)))
+        assert np.abs(ev / np.array(want["eigenvalues"]) - 1).max() <= 1e-10
+        assert err.max() <= 1e-8
+        roots = (C.c_int * nroots)(*range(nroots))
+        check(lib, lib.ItsolvB200Solution(nroots, roots, params.data_ptr(), action.data_ptr()))
+        sol = params.cpu().numpy()
+        for s, chk in zip(sol, want["solution_checksums"]):
+            assert abs(np.sum(s) - chk) <= 1e-7 * max(1.0, np.abs(s).sum())
+        assert float(action.norm(dim=1).max()) <= 1e-8  # the residuals A x - lambda x of the solutions
+        y = torch.zeros_like(params)
+        apply_operator(ctx, params, y, n)
+        lam = torch.from_numpy(ev).cuda()[:, None]
+        assert float((y - lam * params).norm(dim=1).max()) <= 1e-7
+    finally:
+        check(lib, lib.ItsolvB200Finalize())
+
+
+def test_linear_equations_through_the_flat_interface(ctx):
+    want = GOLDEN["banded_lineq_n20000_r8"]
+    n, nroots = want["spec"]["n"], want["spec"]["nroots"]
+    lib = N.host()
+    kernels = N.kernels()
+    scratch = torch.zeros(n, dtype=torch.float64, device="cuda")
+    rhs = torch.zeros((nroots, n), dtype=torch.float64, device="cuda")
+    for k in range(nroots):  # the harness's right-hand sides: A applied to a generated vector
+        assert kernels.itsolv_banded_fill_f64(ctx.handle, 1, k, 0, n, scratch.data_ptr()) == 0
+        ctx.banded_apply(scratch, rhs[k], n, 0, B, EPS)
+    lo, hi = C.c_size_t(), C.c_size_t()
+    check(lib, lib.ItsolvB200LinearEquationsInitialize(ctx.handle, n, nroots, C.byref(lo), C.byref(hi), rhs.data_ptr(), 0.0,
+                                                      1e-8, HUGE, 1, 0, b""))
+    try:
+        params = rhs.clone()  # initial guess c = rhs (reference test_simplified.cpp:131-134)
+        action = torch.zeros_like(params)
+        diag = torch.arange(1, n + 1, dtype=torch.float64, device="cuda")
+        check(lib, lib.ItsolvB200SetDiagonals(diag.data_ptr()))
+        nwork = drive(lib, ctx, params, action, nroots, n)
+        assert nwork == 0
+        assert lib.ItsolvB200Iterations() == want["iterations"]
+        roots = (C.c_int * nroots)(*range(nroots))
+        check(lib, lib.ItsolvB200Solution(nroots, roots, params.data_ptr(), action.data_ptr()))
+        sol = params.cpu().numpy()
+        for s, chk in zip(sol, want["solution_checksums"]):
+            assert abs(np.sum(s) - chk) <= 1e-6 * max(1.0, abs(chk))
+        y = torch.zeros_like(params)
+        apply_operator(ctx, params, y, n)
+        assert float(((y - rhs).norm(dim=1) / rhs.norm(dim=1)).max()) <= 1e-7
+    finally:
+        check(lib, lib.ItsolvB200Finalize())
+
+
+def test_instances_nest_and_errors_are_reported(ctx):
+    lib = N.host()
+    lo, hi = C.c_size_t(), C.c_size_t()
+    assert lib.ItsolvB200LinearEigensystemInitialize(ctx.handle, 100, 2, C.byref(lo), C.byref(hi), 1e-8, HUGE, 1, 0,
+                                                    b"no_such_option=1") != 0
+    assert b"unknown option" in lib.ItsolvB200LastError()
+    check(lib, lib.ItsolvB200LinearEigensystemInitialize(ctx.handle, 100, 2, C.byref(lo), C.byref(hi), 1e-8, HUGE, 1, 0, b""))
+    check(lib, lib.ItsolvB200NonLinearEquationsInitialize(ctx.handle, 50, C.byref(lo), C.byref(hi), 1e-8, 0, b""))
+    assert lib.ItsolvB200NonLinear() == 1 and lib.ItsolvB200HasEigenvalues() == 0  # the top instance is the active one
+    lib.ItsolvB200SetMaxIter(17)
+    assert lib.ItsolvB200MaxIter() == 17
+    check(lib, lib.ItsolvB200Finalize())
+    assert lib.ItsolvB200NonLinear() == 0 and lib.ItsolvB200HasEigenvalues() == 1
+    assert lib.ItsolvB200AddVector(1, None, None) == -1  # null buffers
+    check(lib, lib.ItsolvB200Finalize())
