@@ -20,6 +20,15 @@ from iterative_solver_b200 import harness as H  # noqa: E402
 
 
 def main():
+    import time
+    t_start = time.time()
+    progress = os.environ.get("ITSOLV_WORKER_PROGRESS")  # optional: a file prefix for per-rank progress lines
+
+    def mark(what):
+        if progress:
+            with open(f"{progress}.rank{os.environ.get('RANK', '0')}", "a") as f:
+                f.write(f"{time.time() - t_start:8.2f} s  {what}\n")
+
     rank, world, local = D.env_rank_world()
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -35,6 +44,7 @@ def main():
     b = pkg.distribution(n, world)
     lo, hi = int(b[rank]), int(b[rank + 1])
 
+    mark("context and communicator up")
     # Gram block: per-rank partial sums + NCCL all-reduce
     G = H.handler_gemm_inner(ctx, X, Y)
     want = cpu.gemm_inner(X, Y)
@@ -71,6 +81,7 @@ def main():
     y = H.harness_banded_apply(ctx, X[2].copy(), 4, 1e-3, explicit_csr=True)
     assert np.array_equal(y[lo:hi], cpu.banded_apply(X[2].copy(), 4, 1e-3)[lo:hi])
 
+    mark("handler operations done")
     # kernels of the fused driver path on row shards: vectors bit for bit (no communication), the sums they return
     # all-reduced inside the kernel tail (or by NCCL) and identical on every rank
     def shard(a):
@@ -105,6 +116,7 @@ def main():
     for t_ in range(3):
         assert abs(dots[1 + t_] - cpu.dot(wR[1], wR[1 + t_])) <= 1e-12 * nr[1] * nr[1 + t_]
 
+    mark("fused kernels done")
     # the fused driver path on sharded vectors: same golden results of the reference
     golden = json.load(open(os.path.join(ROOT, "tests", "golden", "solve_golden.json")))
     fused_report = {}
@@ -118,6 +130,7 @@ def main():
         for c, w in zip(chk, want["solution_checksums"]):
             assert abs(c - w) <= 1e-6 * max(1.0, abs(w)), name
         fused_report[name] = res.iterations
+        mark("fused " + name)
 
     # complete solves on sharded vectors against the reference's golden results
     report = {}
@@ -139,6 +152,7 @@ def main():
         for c, w in zip(chk, want["solution_checksums"]):
             assert abs(c - w) <= 1e-6 * max(1.0, abs(w)), name
         report[name] = res.iterations
+        mark("unfused " + name)
     dist.barrier()
     print(f"rank {rank}/{world} ok {report} fused {fused_report}", flush=True)
     ctx.close()
