@@ -117,43 +117,55 @@ def main():
         assert abs(dots[1 + t_] - cpu.dot(wR[1], wR[1 + t_])) <= 1e-12 * nr[1] * nr[1 + t_]
 
     mark("fused kernels done")
+    # Complete solves. A failed comparison is recorded and the run goes on, so that all ranks keep making the same
+    # collective calls; the list is asserted empty at the end.
+    problems = []
+
+    def expect(cond, what):
+        if not cond:
+            problems.append(what)
+
+    def check_solutions(name, want, res, sol, head_tol):
+        if want["eigenvalues"]:
+            ev = np.array([res.eigenvalues[i] for i in range(res.nroots)])
+            expect(np.abs(ev / np.array(want["eigenvalues"]) - 1).max() <= 1e-10, f"{name}: eigenvalues")
+        if rank == 0:
+            for s_, head in zip(sol, want["solution_head"]):
+                dev_ = np.abs(s_[:8] - np.array(head)).max() / max(1.0, np.abs(np.array(head)).max())
+                expect(dev_ <= head_tol, f"{name}: solution head differs by {dev_:.2e}")
+        chk = ctx.allreduce_host(np.array([np.sum(s_) for s_ in sol]))
+        for c, w in zip(chk, want["solution_checksums"]):
+            expect(abs(c - w) <= 1e-6 * max(1.0, abs(w)), f"{name}: checksum {c} vs {w}")
+
     # the fused driver path on sharded vectors: same golden results of the reference
     golden = json.load(open(os.path.join(ROOT, "tests", "golden", "solve_golden.json")))
     fused_report = {}
     for name in sorted(k for k, v in golden.items() if v["spec"]["kind"] == N.KIND_DAVIDSON and v["spec"]["n"] >= 1000):
         want = golden[name]
         res, sol = H.solve(ctx, H.make_spec(fused=1, **want["spec"]), want_solutions=True)
-        assert res.iterations == want["iterations"] and res.converged == want["converged"], name
-        ev = np.array([res.eigenvalues[i] for i in range(res.nroots)])
-        assert np.abs(ev / np.array(want["eigenvalues"]) - 1).max() <= 1e-10, name
-        chk = ctx.allreduce_host(np.array([np.sum(s_) for s_ in sol]))
-        for c, w in zip(chk, want["solution_checksums"]):
-            assert abs(c - w) <= 1e-6 * max(1.0, abs(w)), name
+        expect(res.iterations == want["iterations"] and res.converged == want["converged"], f"fused {name}: iterations")
+        check_solutions("fused " + name, want, res, sol, 1e-7)
         fused_report[name] = res.iterations
         mark("fused " + name)
 
-    # complete solves on sharded vectors against the reference's golden results
+    # the reference's solver classes on sharded vectors against the reference's golden results, call for call.
+    # Eigenvectors are compared to 1e-7; solutions of the linear and non-linear equations to 1e-6: two runs that both meet
+    # the residual threshold 1e-8 agree only to that threshold times the conditioning, and the summation order of the
+    # inner products changes with the number of ranks.
     report = {}
     for name in ("banded_davidson_n100000_r4", "banded_davidson_n30000_r6_qcap8", "banded_davidson_n30000_r4_p20",
                  "banded_lineq_n50000_r1", "banded_diis_n50000", "banded_davidson_n30000_r16"):
         want = golden[name]
         spec = H.make_spec(trace=1, **want["spec"])
         res, sol = H.solve(ctx, spec, want_solutions=True)
-        assert res.iterations == want["iterations"] and res.converged == want["converged"], name
-        assert [[op, r, c] for op, r, c, _ in H.read_trace()] == want["trace_shapes"], name
-        if want["eigenvalues"]:
-            ev = np.array([res.eigenvalues[i] for i in range(res.nroots)])
-            assert np.abs(ev / np.array(want["eigenvalues"]) - 1).max() <= 1e-10, name
-        bb = pkg.distribution(want["spec"]["n"], world)
-        if rank == 0:
-            for s, head in zip(sol, want["solution_head"]):
-                assert np.abs(s[:8] - np.array(head)).max() <= 1e-7 * max(1.0, np.abs(np.array(head)).max())
-        chk = ctx.allreduce_host(np.array([np.sum(s) for s in sol]))
-        for c, w in zip(chk, want["solution_checksums"]):
-            assert abs(c - w) <= 1e-6 * max(1.0, abs(w)), name
+        expect(res.iterations == want["iterations"] and res.converged == want["converged"], f"{name}: iterations")
+        expect([[op, r, c] for op, r, c, _ in H.read_trace()] == want["trace_shapes"], f"{name}: call trace")
+        check_solutions(name, want, res, sol, 1e-7 if want["eigenvalues"] else 1e-6)
         report[name] = res.iterations
         mark("unfused " + name)
+    mark("problems: " + repr(problems))
     dist.barrier()
+    assert not problems, problems
     print(f"rank {rank}/{world} ok {report} fused {fused_report}", flush=True)
     ctx.close()
     dist.destroy_process_group()
