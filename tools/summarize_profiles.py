@@ -139,6 +139,33 @@ def main():
             w.writerow([hdr[i] + (f" [{units[i]}]" if units[i] else "") for i in idx])
             for r in rows[2:]:
                 w.writerow([short(r[i]) if hdr[i] == "Kernel Name" else r[i] for i in idx])
+    # raw page of a `ncu --set full` capture exported on the GPU box (`ncu -i … --page raw --csv`): one row per launch
+    for src_name, out_name in (("bench_full_raw.csv", f"ncu_full_bench_{TAG}.csv"),
+                               ("fused_raw.csv", f"ncu_full_fused_{TAG}.csv")):
+        p = os.path.join(SRC, src_name)
+        if not os.path.exists(p):
+            continue
+        rows = list(csv.reader(open(p)))
+        rows = [r for r in rows if len(r) > 10 and (r[0] == "ID" or r[0] == "" or r[0].isdigit())]
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum",
+                "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+                "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+                "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+                "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+                "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+                "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+                "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+                "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+                "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+                "smsp__inst_executed.sum"]
+        idx = [hdr.index(w) for w in want if w in hdr]
+        with open(os.path.join(OUT, out_name), "w", newline="") as f:
+            w = csv.writer(f)
+            w.writerow([hdr[i] + (f" [{units[i]}]" if units[i] else "") for i in idx])
+            for r in data:
+                w.writerow([short(r[i]) if hdr[i] == "Kernel Name" else r[i] for i in idx])
     for name in ("opbench_r01.json",):
         p = os.path.join(SRC, name)
         if os.path.exists(p):
