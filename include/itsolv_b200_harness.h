@@ -45,7 +45,9 @@ typedef struct itsolv_solve_spec {
   int32_t verbosity;            /* 0..3 as IterativeSolver::set_verbosity(int) */
   int32_t trace;                /* record every dot/gemm_inner result for parity checks */
   int32_t explicit_csr;         /* banded operator: 1 = stored CSR arrays, 0 = entries generated in the kernel */
-  int32_t fused;                /* Davidson on the CUDA backend: 1 = fused driver path (FusedDavidson.h); ignored by the oracle */
+  int32_t fused;                /* CUDA backend: 1 = fused driver path (Davidson: FusedDavidson.h, 2 = its batched pieces under
+                                   the reference's solve() loop; LinearEquations / DIIS: fused X space, FusedEquations.h);
+                                   0 = the reference's classes call for call; ignored by the oracle */
 } itsolv_solve_spec;
 
 typedef struct itsolv_solve_result {

@@ -58,7 +58,9 @@ inline double now_seconds() {
  *   ProblemT& problem();                              Problem<R> with make_rhs(k, R&), seconds_action, seconds_precond
  *   void synchronize();                               wait for outstanding device work (no-op on the host)
  *   void timer_start(); double timer_stop_ms();       device stopwatch around solve() (0 on the host)
- *   unique_ptr<LinearEigensystemDavidson<R,R,P>> make_davidson(handlers, spec);
+ *   unique_ptr<LinearEigensystemDavidson<R,R,P>> make_davidson(handlers, spec);   the reference's class or a subclass
+ *   unique_ptr<LinearEquationsDavidson<R,R,P>> make_lineq(handlers, spec);
+ *   unique_ptr<NonLinearEquationsDIIS<R,R,P>> make_diis(handlers, spec);
  */
 template <class Backend>
 int run_solve(const itsolv_solve_spec& spec, Backend& backend, itsolv_solve_result& res, double* solutions) {
@@ -146,7 +148,8 @@ int run_solve(const itsolv_solve_spec& spec, Backend& backend, itsolv_solve_resu
       res.eigenvalues[i] = ev[i];
     export_solutions(solver);
   } else if (spec.kind == ITSOLV_KIND_LINEQ) {
-    its::LinearEquationsDavidson<R, R, P> solver(handlers);
+    auto solver_ptr = backend.make_lineq(handlers, spec);
+    auto& solver = *solver_ptr;
     configure(solver);
     solver.set_hermiticity(spec.hermitian != 0);
     if (spec.reset_D > 0)
@@ -171,7 +174,8 @@ int run_solve(const itsolv_solve_spec& spec, Backend& backend, itsolv_solve_resu
     finish(solver, ok, t0);
     export_solutions(solver);
   } else if (spec.kind == ITSOLV_KIND_DIIS) {
-    its::NonLinearEquationsDIIS<R, R, P> solver(handlers);
+    auto solver_ptr = backend.make_diis(handlers, spec);
+    auto& solver = *solver_ptr;
     configure(solver);
     backend.synchronize();
     const double t0 = now_seconds();

@@ -19,6 +19,7 @@
 #include "ArrayHandlerCUDA.h"
 #include "DistrArrayCUDA.h"
 #include "FusedDavidson.h"
+#include "FusedEquations.h"
 
 namespace {
 using itsolv_b200::check;
@@ -270,6 +271,18 @@ struct DeviceBackend {
       return solver;
     }
     return std::make_unique<its::LinearEigensystemDavidson<R, R, PMap>>(handlers);
+  }
+  std::unique_ptr<its::LinearEquationsDavidson<R, R, PMap>>
+  make_lineq(const std::shared_ptr<itsolv_b200::HandlersCUDA>& handlers, const itsolv_solve_spec& spec) {
+    if (spec.fused)
+      return std::make_unique<itsolv_b200::LinearEquationsDavidsonFused>(handlers);
+    return std::make_unique<its::LinearEquationsDavidson<R, R, PMap>>(handlers);
+  }
+  std::unique_ptr<its::NonLinearEquationsDIIS<R, R, PMap>>
+  make_diis(const std::shared_ptr<itsolv_b200::HandlersCUDA>& handlers, const itsolv_solve_spec& spec) {
+    if (spec.fused)
+      return std::make_unique<itsolv_b200::NonLinearEquationsDIISFused>(handlers);
+    return std::make_unique<its::NonLinearEquationsDIIS<R, R, PMap>>(handlers);
   }
   void timer_start() { check(itsolv_ctx_timer_start(ctx, 0), "timer"); }
   double timer_stop_ms() {

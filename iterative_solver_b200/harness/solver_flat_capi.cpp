@@ -20,6 +20,7 @@
 #include "ArrayHandlerCUDA.h"
 #include "DistrArrayCUDA.h"
 #include "FusedDavidson.h"
+#include "FusedEquations.h"
 
 namespace {
 namespace its = molpro::linalg::itsolv;
@@ -180,9 +181,13 @@ int ItsolvB200LinearEquationsInitialize(itsolv_ctx* ctx, size_t n, size_t nroot,
                                         size_t* range_end, const double* rhs, double aughes, double thresh,
                                         double thresh_value, int hermitian, int verbosity, const char* options) {
   return guarded([&] {
-    const auto opt = parse_options(options, {"max_size_qspace", "reset_d", "reset_d_max_q_size", "max_iter"});
+    const auto opt = parse_options(options, {"max_size_qspace", "reset_d", "reset_d_max_q_size", "max_iter", "fused"});
     auto handlers = itsolv_b200::make_handlers();
-    auto solver = std::make_unique<its::LinearEquationsDavidson<R, R, P>>(handlers);
+    std::unique_ptr<its::LinearEquationsDavidson<R, R, P>> solver;
+    if (!opt.count("fused") || opt.at("fused") != 0)
+      solver = std::make_unique<itsolv_b200::LinearEquationsDavidsonFused>(handlers);
+    else
+      solver = std::make_unique<its::LinearEquationsDavidson<R, R, P>>(handlers);
     auto* s = solver.get();
     auto& in = push_instance(ctx, n, std::move(solver), handlers, range_begin, range_end);
     try {
@@ -209,9 +214,13 @@ int ItsolvB200LinearEquationsInitialize(itsolv_ctx* ctx, size_t n, size_t nroot,
 int ItsolvB200NonLinearEquationsInitialize(itsolv_ctx* ctx, size_t n, size_t* range_begin, size_t* range_end,
                                            double thresh, int verbosity, const char* options) {
   return guarded([&] {
-    const auto opt = parse_options(options, {"max_size_qspace", "max_iter"});
+    const auto opt = parse_options(options, {"max_size_qspace", "max_iter", "fused"});
     auto handlers = itsolv_b200::make_handlers();
-    auto solver = std::make_unique<its::NonLinearEquationsDIIS<R, R, P>>(handlers);
+    std::unique_ptr<its::NonLinearEquationsDIIS<R, R, P>> solver;
+    if (!opt.count("fused") || opt.at("fused") != 0)
+      solver = std::make_unique<itsolv_b200::NonLinearEquationsDIISFused>(handlers);
+    else
+      solver = std::make_unique<its::NonLinearEquationsDIIS<R, R, P>>(handlers);
     solver->set_convergence_threshold(thresh);
     solver->set_verbosity(verbosity);
     if (opt.count("max_size_qspace"))

@@ -205,6 +205,12 @@ struct HostBackend {
   auto make_davidson(const std::shared_ptr<its::ArrayHandlers<Vec, Vec, PMap>>& handlers, const itsolv_solve_spec&) {
     return std::make_unique<its::LinearEigensystemDavidson<Vec, Vec, PMap>>(handlers);
   }
+  auto make_lineq(const std::shared_ptr<its::ArrayHandlers<Vec, Vec, PMap>>& handlers, const itsolv_solve_spec&) {
+    return std::make_unique<its::LinearEquationsDavidson<Vec, Vec, PMap>>(handlers);
+  }
+  auto make_diis(const std::shared_ptr<its::ArrayHandlers<Vec, Vec, PMap>>& handlers, const itsolv_solve_spec&) {
+    return std::make_unique<its::NonLinearEquationsDIIS<Vec, Vec, PMap>>(handlers);
+  }
 };
 
 Vec to_vec(const double* p, size_t n) { return Vec(p, p + n); }

@@ -57,7 +57,7 @@ def main():
         kw["max_iter"] = args.max_iter
     if args.threshold:
         kw["convergence_threshold"] = args.threshold
-    if kw["kind"] == N.KIND_DAVIDSON and not args.unfused:
+    if not args.unfused:
         kw["fused"] = 1
     spec = H.make_spec(**kw)
     ctx.set_profiling(True)
