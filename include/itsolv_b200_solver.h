@@ -30,7 +30,8 @@ extern "C" {
 struct itsolv_ctx; /* include/itsolv_b200.h */
 
 /* options: blank- or comma-separated key=value pairs; understood: max_size_qspace, reset_D, reset_D_max_Q_size, max_iter,
- * fused (Davidson: 1 default, 0 = the reference's class call for call). Unknown keys are an error. */
+ * fused (eigensolver: 1 by default = the fused driver, 0 = the reference's class call for call; equation solvers: 0 by
+ * default, 1 = fused X space). Unknown keys are an error. */
 
 /* reference IterativeSolverC.h:6-9; n = global length of the vectors */
 int ItsolvB200LinearEigensystemInitialize(struct itsolv_ctx* ctx, size_t n, size_t nroot, size_t* range_begin,

@@ -184,7 +184,7 @@ int ItsolvB200LinearEquationsInitialize(itsolv_ctx* ctx, size_t n, size_t nroot,
     const auto opt = parse_options(options, {"max_size_qspace", "reset_d", "reset_d_max_q_size", "max_iter", "fused"});
     auto handlers = itsolv_b200::make_handlers();
     std::unique_ptr<its::LinearEquationsDavidson<R, R, P>> solver;
-    if (!opt.count("fused") || opt.at("fused") != 0)
+    if (opt.count("fused") && opt.at("fused") != 0)
       solver = std::make_unique<itsolv_b200::LinearEquationsDavidsonFused>(handlers);
     else
       solver = std::make_unique<its::LinearEquationsDavidson<R, R, P>>(handlers);
@@ -217,7 +217,7 @@ int ItsolvB200NonLinearEquationsInitialize(itsolv_ctx* ctx, size_t n, size_t* ra
     const auto opt = parse_options(options, {"max_size_qspace", "max_iter", "fused"});
     auto handlers = itsolv_b200::make_handlers();
     std::unique_ptr<its::NonLinearEquationsDIIS<R, R, P>> solver;
-    if (!opt.count("fused") || opt.at("fused") != 0)
+    if (opt.count("fused") && opt.at("fused") != 0)
       solver = std::make_unique<itsolv_b200::NonLinearEquationsDIISFused>(handlers);
     else
       solver = std::make_unique<its::NonLinearEquationsDIIS<R, R, P>>(handlers);

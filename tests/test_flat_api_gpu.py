@@ -89,7 +89,8 @@ def test_davidson_through_the_flat_interface(ctx, name, options):
         check(lib, lib.ItsolvB200Finalize())
 
 
-def test_linear_equations_through_the_flat_interface(ctx):
+@pytest.mark.parametrize("options", [b"", b"fused=1"])
+def test_linear_equations_through_the_flat_interface(ctx, options):
     want = GOLDEN["banded_lineq_n20000_r8"]
     n, nroots = want["spec"]["n"], want["spec"]["nroots"]
     lib = N.host()
@@ -101,7 +102,7 @@ def test_linear_equations_through_the_flat_interface(ctx):
         ctx.banded_apply(scratch, rhs[k], n, 0, B, EPS)
     lo, hi = C.c_size_t(), C.c_size_t()
     check(lib, lib.ItsolvB200LinearEquationsInitialize(ctx.handle, n, nroots, C.byref(lo), C.byref(hi), rhs.data_ptr(), 0.0,
-                                                      1e-8, HUGE, 1, 0, b""))
+                                                      1e-8, HUGE, 1, 0, options))
     try:
         params = rhs.clone()  # initial guess c = rhs (reference test_simplified.cpp:131-134)
         action = torch.zeros_like(params)

@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--max-iter", type=int, default=0)
     ap.add_argument("--threshold", type=float, default=0.0)
     ap.add_argument("--unfused", action="store_true", help="the reference's solver class call for call (default: fused driver)")
+    ap.add_argument("--fused-equations", action="store_true", help="LinearEquations / DIIS on the fused X space")
     ap.add_argument("--cold", action="store_true", help="report the first solve (includes first-touch allocation of the pool)")
     args = ap.parse_args()
     rank, world, local = D.env_rank_world()
@@ -57,7 +58,9 @@ def main():
         kw["max_iter"] = args.max_iter
     if args.threshold:
         kw["convergence_threshold"] = args.threshold
-    if not args.unfused:
+    # Davidson: the fused driver is the default. The equation solvers run the reference's classes unless --fused-equations
+    # asks for their fused X space (FusedEquations.h).
+    if (kw["kind"] == N.KIND_DAVIDSON and not args.unfused) or args.fused_equations:
         kw["fused"] = 1
     spec = H.make_spec(**kw)
     ctx.set_profiling(True)
