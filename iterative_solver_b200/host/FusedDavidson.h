@@ -362,6 +362,7 @@ public:
   size_t end_iteration(const VecRef<R>& parameters, const VecRef<R>& action) override {
     if (this->m_dspace_resetter.do_reset(this->m_stats->iterations, this->m_xspace->dimensions())) {
       this->m_resetting_in_progress = true;
+      m_written_norms.clear();
       this->m_working_set = this->m_dspace_resetter.run(
           parameters, *this->m_xspace, this->m_subspace_solver->solutions(), this->propose_rspace_norm_thresh,
           this->propose_rspace_svd_thresh, *this->m_handlers, *this->m_logger);
@@ -384,6 +385,7 @@ protected:
    */
   int add_vector_fused(const VecRef<R>& parameters, const VecRef<R>& actions, const R* diagonals, bool& preconditioned) {
     preconditioned = false;
+    m_written_norms.clear(); // valid only from the residual kernel of THIS call to the proposal step that follows it
     if (this->m_xspace->dimensions().nP != 0 && !this->m_apply_p)
       throw std::runtime_error(
           "Solver contains P space but no valid apply_p function. Make sure add_p was called correctly.");
