@@ -117,6 +117,15 @@ int itsolv_mgs_step_f64(itsolv_ctx* ctx, double inv_norm, double* ri, const doub
  * dots[0] = <ri', ri'>, dots[1+t] = <rj[0]', rj[t]'> for t in [0, m) (HOST, m+1 values, all-reduced over ranks); m <= 16 */
 int itsolv_mgs_step_dots_f64(itsolv_ctx* ctx, double inv_norm, double* ri, const double* ov, double* const* rj, int m,
                              size_t n, double* dots);
+/* The whole R-R modified Gram-Schmidt of w vectors (reference itsolv/propose_rspace.h:451-463) as ONE chain of launches
+ * without host round trips: a Gram row for the first pivot, then w steps as above, each of which takes its coefficients
+ * (1/|r_i|, -<r_i,r_j>/|r_i|) from device memory where the previous launch's tail has left them, computed with the host's
+ * arithmetic from the all-reduced sums. A pivot whose norm is <= thresh is left untouched, and so are the later
+ * vectors with respect to it. rows (HOST, w + w(w+1)/2 values): {<r_0,r_j> before the chain, j = 0..w-1}, then per step i
+ * {<r_i',r_i'>, <r_{i+1}',r_j'> for j = i+1..w-1}: everything the caller needs to repeat the decisions. w <= 17.
+ * itsolv_mgs_chain_supported: 1 when the chain can run (option MGS_CHAIN, sums delivered by the kernels themselves). */
+int itsolv_mgs_chain_supported(itsolv_ctx* ctx, int w, size_t n);
+int itsolv_mgs_chain_f64(itsolv_ctx* ctx, double* const* r, int w, size_t n, double thresh, double* rows);
 /* counter that every call which may write a vector advances (and DistrArrayCUDA::data() non-const): results cached
  * on the host side (ArrayHandlerCUDA's primed dots) are valid only while it stands still */
 unsigned long long itsolv_ctx_write_epoch(itsolv_ctx* ctx);

@@ -165,6 +165,14 @@ class Context:
                                                       _ptr_array(rjs), len(rjs), ri.numel(), _dbl(dots)))
         return dots
 
+    def mgs_chain(self, rs: Sequence, thresh: float = 1e-10) -> np.ndarray:
+        """R-R modified Gram-Schmidt of the vectors as one chain of launches (itsolv_mgs_chain_f64); returns the rows of
+        inner products described in include/itsolv_b200.h"""
+        w = len(rs)
+        rows = np.zeros(w + w * (w + 1) // 2)
+        self._check(self.lib.itsolv_mgs_chain_f64(self.handle, _ptr_array(rs), w, rs[0].numel(), thresh, _dbl(rows)))
+        return rows
+
     def dot(self, x, y) -> float:
         r = C.c_double()
         self._check(self.lib.itsolv_dot_f64(self.handle, _ptr(x), _ptr(y), x.numel(), C.byref(r)))

@@ -64,6 +64,11 @@ struct itsolv_ctx {
   unsigned long long* h_flag = nullptr; // pinned + mapped: sequence number of the last result delivered by a kernel
   unsigned long long flag_seq = 0;
   unsigned int* d_counter = nullptr;    // CTA arrival counter of the fused final reduction (self-resetting)
+  // requests picked up by the next fill_finalize() (chained Gram-Schmidt steps, mgs_fused.cu)
+  size_t result_offset = 0;             // the kernel delivers its sums at h_result + result_offset
+  double* chain_out = nullptr;          // see GiFinalize::chain_out
+  int chain_offset = 0, chain_count = 0;
+  double chain_thresh = 0.0;
   // staging for small host->device payloads (alphas, sparse maps, pointer tables): pinned ring + device ring
   char* h_stage = nullptr;
   char* d_stage = nullptr;
@@ -94,6 +99,7 @@ struct itsolv_ctx {
   int opt_blas1_ctas = 0; // CTAs per SM for streaming kernels
   int opt_ds_ring = 0;    // davidson_residual: <0 never use the cp.async ring kernel
   int opt_stream_ring = 0; // gemm_outer / mgs_step_dots: <0 never use the cp.async ring kernels
+  int opt_mgs_chain = 0;   // R-R Gram-Schmidt steps chained on the device: >0 on, 0 default (see mgs_fused.cu), <0 off
   int opt_p2p_allreduce = 0; // <0: use ncclAllReduce even when the peer buffers are mapped
 
   std::vector<std::pair<const void*, size_t>> smem_optin; // kernel -> largest dynamic shared memory size opted in

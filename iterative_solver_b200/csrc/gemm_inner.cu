@@ -249,16 +249,29 @@ void fill_finalize(itsolv_ctx* ctx, int grid_bound, int km, GiFinalize* f, bool*
   f->peers.nranks = 1;
   f->peers.rank = 0;
   f->peers.slot_doubles = 0;
+  f->dev_sums = nullptr;
+  f->chain_out = nullptr;
+  f->chain_offset = f->chain_count = 0;
+  f->chain_thresh = 0.0;
   *host_direct = false;
   const int nranks = itsolv_comm_size(ctx);
   if (f->fused && (nranks == 1 || comm_peers(ctx, &f->peers))) {
     // mapped pinned memory: the kernel delivers the result (all-reduced over peer memory when there are several ranks),
     // no NCCL launch, no copy, no stream synchronisation
-    f->out = ctx->h_result;
+    f->out = ctx->h_result + ctx->result_offset;
     f->flag = ctx->h_flag;
     f->seq = ++ctx->flag_seq;
     *host_direct = true;
+    if (ctx->chain_out) { // chained Gram-Schmidt step: the tail also prepares the next step's coefficients
+      f->chain_out = ctx->chain_out;
+      f->chain_offset = ctx->chain_offset;
+      f->chain_count = ctx->chain_count;
+      f->chain_thresh = ctx->chain_thresh;
+      f->dev_sums = ctx->d_result + 8192; // the upper half of the device result buffer
+    }
   }
+  ctx->chain_out = nullptr; // requests hold for one launch
+  ctx->result_offset = 0;
 }
 
 int launch_reduce_partials(itsolv_ctx* ctx, int grid, int km);
@@ -544,6 +557,8 @@ static int wait_host_flag(itsolv_ctx* ctx) {
 #endif
   }
 }
+
+int wait_host_result(itsolv_ctx* ctx) { return wait_host_flag(ctx); }
 
 //! all-reduce over ranks, copy to the pinned buffer, synchronise, hand to the caller
 int finish_result(itsolv_ctx* ctx, int count, double* out, bool host_direct) {

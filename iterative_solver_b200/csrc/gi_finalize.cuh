@@ -33,7 +33,26 @@ struct GiFinalize {
   unsigned long long seq;
   int fused;                // 0: a separate kernel reduces the partials
   GiPeers peers;            // peers.nranks <= 1: single rank
+  // Chained Gram-Schmidt steps (mgs_fused.cu): the finishing CTA turns the row {<r,r>, <r,r_j>...} that starts at
+  // sums[chain_offset] into the coefficients of the NEXT pivot step and leaves them in device memory, so that step can be
+  // launched without a host round trip: chain_out = {1/|r|, null flag, -<r,r_j>/|r| ...}; null (|r| <= thresh): {1, 1, 0...}
+  double* dev_sums;         // device copy of the km final sums (needed when chain_out is set)
+  double* chain_out;        // null: no chaining
+  int chain_offset, chain_count;
+  double chain_thresh;
 };
+
+//! coefficients of the next pivot step from its row of inner products, exactly the host's arithmetic
+//! (FusedDavidson.h, R-R modified Gram-Schmidt): norm = sqrt(|<r,r>|), o_j = <r,r_j> / norm
+__device__ __forceinline__ void gi_chain(const GiFinalize& f) {
+  const double* row = f.dev_sums + f.chain_offset;
+  const double norm = sqrt(fabs(row[0]));
+  const bool ok = norm > f.chain_thresh;
+  f.chain_out[0] = ok ? __ddiv_rn(1.0, norm) : 1.0;
+  f.chain_out[1] = ok ? 0.0 : 1.0;
+  for (int t = 1; t < f.chain_count; ++t)
+    f.chain_out[1 + t] = ok ? -__ddiv_rn(row[t], norm) : 0.0;
+}
 
 __device__ __forceinline__ unsigned long long ld_volatile_sys(const unsigned long long* p) {
   unsigned long long v;
@@ -46,7 +65,7 @@ __device__ __forceinline__ unsigned long long ld_volatile_sys(const unsigned lon
  * Returns false on timeout (a peer never arrived); the caller reports it through the host word.
  */
 __device__ __forceinline__ bool gi_peer_allreduce(const GiPeers& pr, const double* local, int km, unsigned long long seq,
-                                                  double* out) {
+                                                  double* out, double* dev_copy = nullptr) {
   const int tid = threadIdx.x;
   const int parity = int(seq & 1ull);
   const size_t slot = (size_t(parity) * pr.nranks + pr.rank) * pr.slot_doubles;
@@ -81,6 +100,8 @@ __device__ __forceinline__ bool gi_peer_allreduce(const GiPeers& pr, const doubl
     for (int r = 0; r < pr.nranks; ++r)
       sum += __ldcv(base + size_t(r) * pr.slot_doubles + e);
     out[e] = sum;
+    if (dev_copy)
+      dev_copy[e] = sum;
   }
   return true;
 }
@@ -106,16 +127,21 @@ __device__ __forceinline__ void gi_finalize(const GiFinalize& f, int km, int* s_
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1)
       sum += __shfl_down_sync(0xffffffffu, sum, off);
-    if (lane == 0)
+    if (lane == 0) {
       (f.peers.nranks > 1 ? f.local : f.out)[e] = sum;
+      if (f.chain_out && f.peers.nranks <= 1)
+        f.dev_sums[e] = sum;
+    }
   }
   __syncthreads();
   bool ok = true;
   if (f.peers.nranks > 1) {
-    ok = gi_peer_allreduce(f.peers, f.local, km, f.seq, f.out);
+    ok = gi_peer_allreduce(f.peers, f.local, km, f.seq, f.out, f.chain_out ? f.dev_sums : nullptr);
     __syncthreads();
   }
   if (tid == 0) {
+    if (f.chain_out)
+      gi_chain(f);
     *f.counter = 0u;
     if (f.flag) {
       __threadfence_system();

@@ -26,20 +26,34 @@ int finish_result(itsolv_ctx* ctx, int count, double* out, bool host_direct);   
 
 constexpr int kMfThreads = 256;
 constexpr int kMfMaxLater = 16; // later vectors per launch
+constexpr int kMgsChainDefault = 0; // option MGS_CHAIN is added to this: > 0 chains the steps on the device
 
 struct MfParams {
   double* ri;
   double* rj[kMfMaxLater];
   double neg_ov[kMfMaxLater];
   double inv_norm;
+  // chained steps: {1/|r_i|, null flag, -ov...} left in device memory by the previous launch's tail (GiFinalize::chain_out)
+  // replace inv_norm / neg_ov; with the null flag set nothing is stored (the reference skips a null pivot,
+  // propose_rspace.h:451-463) but the products of the untouched vectors are still returned
+  const double* chain_in;
   GiFinalize fin;
   size_t n;
   int m;
 };
 
+//! the coefficients of one step, in registers
+template <int M>
+struct MfCoef {
+  double inv_norm;
+  double neg_ov[M > 0 ? M : 1];
+  bool store;
+};
+
 //! U row groups of one thread: all loads first, then the arithmetic, then all stores
 template <int M, int U, class RV>
-__device__ __forceinline__ void mf_rows(const MfParams& p, const size_t (&r)[U], int nu, double (&dots)[M + 1]) {
+__device__ __forceinline__ void mf_rows(const MfParams& p, const MfCoef<M>& c, const size_t (&r)[U], int nu,
+                                        double (&dots)[M + 1]) {
   RV v[U], y[U][M > 0 ? M : 1];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
@@ -56,34 +70,36 @@ __device__ __forceinline__ void mf_rows(const MfParams& p, const size_t (&r)[U],
     if (u < nu) {
       if constexpr (sizeof(RV) == sizeof(double2)) {
         double2& a = reinterpret_cast<double2&>(v[u]);
-        a.x = __dmul_rn(a.x, p.inv_norm);
-        a.y = __dmul_rn(a.y, p.inv_norm);
+        a.x = __dmul_rn(a.x, c.inv_norm);
+        a.y = __dmul_rn(a.y, c.inv_norm);
         dots[0] = fma(a.x, a.x, dots[0]);
         dots[0] = fma(a.y, a.y, dots[0]);
 #pragma unroll
         for (int k = 0; k < M; ++k)
           if (k < p.m) {
             double2& b = reinterpret_cast<double2&>(y[u][k]);
-            b.x = __dadd_rn(b.x, __dmul_rn(p.neg_ov[k], a.x));
-            b.y = __dadd_rn(b.y, __dmul_rn(p.neg_ov[k], a.y));
+            b.x = __dadd_rn(b.x, __dmul_rn(c.neg_ov[k], a.x));
+            b.y = __dadd_rn(b.y, __dmul_rn(c.neg_ov[k], a.y));
             const double2& b0 = reinterpret_cast<const double2&>(y[u][0]);
             dots[1 + k] = fma(b0.x, b.x, dots[1 + k]);
             dots[1 + k] = fma(b0.y, b.y, dots[1 + k]);
           }
       } else {
         double& a = reinterpret_cast<double&>(v[u]);
-        a = __dmul_rn(a, p.inv_norm);
+        a = __dmul_rn(a, c.inv_norm);
         dots[0] = fma(a, a, dots[0]);
 #pragma unroll
         for (int k = 0; k < M; ++k)
           if (k < p.m) {
             double& b = reinterpret_cast<double&>(y[u][k]);
-            b = __dadd_rn(b, __dmul_rn(p.neg_ov[k], a));
+            b = __dadd_rn(b, __dmul_rn(c.neg_ov[k], a));
             dots[1 + k] = fma(reinterpret_cast<const double&>(y[u][0]), b, dots[1 + k]);
           }
       }
     }
   }
+  if (!c.store)
+    return;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     if (u < nu) {
@@ -105,6 +121,12 @@ __global__ void __launch_bounds__(kMfThreads, M <= 4 ? 4 : 2) mgs_step_dots_kern
 #pragma unroll
   for (int k = 0; k <= M; ++k)
     dots[k] = 0.0;
+  MfCoef<M> c;
+  c.inv_norm = p.chain_in ? p.chain_in[0] : p.inv_norm;
+  c.store = p.chain_in ? p.chain_in[1] == 0.0 : true;
+#pragma unroll
+  for (int k = 0; k < M; ++k)
+    c.neg_ov[k] = k < p.m ? (p.chain_in ? p.chain_in[2 + k] : p.neg_ov[k]) : 0.0;
   const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = size_t(gridDim.x) * blockDim.x;
   if (VEC) {
@@ -118,11 +140,11 @@ __global__ void __launch_bounds__(kMfThreads, M <= 4 ? 4 : 2) mgs_step_dots_kern
         if (r[u] < npairs)
           nu = u + 1;
       }
-      mf_rows<M, U, double2>(p, r, nu, dots);
+      mf_rows<M, U, double2>(p, c, r, nu, dots);
     }
     if ((p.n & 1) && tid == 0) {
       const size_t r[1] = {p.n - 1};
-      mf_rows<M, 1, double>(p, r, 1, dots);
+      mf_rows<M, 1, double>(p, c, r, 1, dots);
     }
   } else {
     for (size_t r0 = tid; r0 < p.n; r0 += U * nthreads) {
@@ -134,7 +156,7 @@ __global__ void __launch_bounds__(kMfThreads, M <= 4 ? 4 : 2) mgs_step_dots_kern
         if (r[u] < p.n)
           nu = u + 1;
       }
-      mf_rows<M, U, double>(p, r, nu, dots);
+      mf_rows<M, U, double>(p, c, r, nu, dots);
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -185,6 +207,64 @@ static MfKernel mf_pick(int mt, bool vec) {
 
 using namespace itsolv;
 
+namespace itsolv {
+
+int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const double* const* yy, int m, size_t n,
+                      bool* host_direct); // gemm_inner.cu
+int wait_host_result(itsolv_ctx* ctx);   // gemm_inner.cu: waits for the newest sequence word
+
+//! launch one step; the sums are delivered as fill_finalize() decides (no waiting here)
+static int mgs_step_launch(itsolv_ctx* ctx, double inv_norm, double* ri, const double* ov, double* const* rj, int m,
+                           size_t n, const double* chain_in, bool* direct) {
+  MfParams p;
+  bool vec = aligned16(ri);
+  for (int k = 0; k < kMfMaxLater; ++k) {
+    p.rj[k] = k < m ? rj[k] : nullptr;
+    p.neg_ov[k] = (k < m && ov) ? -ov[k] : 0.0;
+    if (k < m) {
+      ITSOLV_REQUIRE(rj[k] != ri, "mgs step: a target aliases the pivot vector");
+      for (int k2 = 0; k2 < k; ++k2)
+        ITSOLV_REQUIRE(rj[k] != rj[k2], "mgs step: the same target twice");
+      vec = vec && aligned16(rj[k]);
+    }
+  }
+  p.ri = ri;
+  p.inv_norm = inv_norm;
+  p.chain_in = chain_in;
+  p.n = n;
+  p.m = m;
+  int mt = 0;
+  if (m > 0) {
+    mt = 1;
+    while (mt < m)
+      mt *= 2;
+  }
+  MfKernel kernel = mf_pick(mt, vec);
+  ITSOLV_REQUIRE(kernel != nullptr, "mgs step: vector count not instantiated");
+  const int per_sm = mt <= 4 ? 4 : 2;
+  const int unroll = mt <= 1 ? 4 : (mt <= 4 ? 2 : 1);
+  const size_t units = vec ? n / 2 : n;
+  const size_t want = (units + size_t(kMfThreads) * unroll - 1) / (size_t(kMfThreads) * unroll);
+  const int grid = int(std::max<size_t>(1, std::min<size_t>(want, size_t(ctx->num_sms) * per_sm)));
+  const int km = m + 1;
+  if (ensure_partials(ctx, size_t(grid) * km))
+    return 1;
+  fill_finalize(ctx, ctx->num_sms * per_sm, km, &p.fin, direct);
+  mark_launch(ctx);
+  kernel<<<grid, kMfThreads, 0, ctx->stream>>>(p);
+  ITSOLV_CUDA(cudaGetLastError());
+  ctx->counters.launches += 1;
+  if (!p.fin.fused) {
+    if (launch_reduce_partials(ctx, grid, km))
+      return 1;
+    if (finish_with_peers(ctx, km, direct))
+      return 1;
+  }
+  return 0;
+}
+
+} // namespace itsolv
+
 extern "C" {
 
 int itsolv_mgs_step_dots_f64(itsolv_ctx* ctx, double inv_norm, double* ri, const double* ov, double* const* rj, int m,
@@ -202,52 +282,69 @@ int itsolv_mgs_step_dots_f64(itsolv_ctx* ctx, double inv_norm, double* ri, const
     ITSOLV_CUDA(cudaMemsetAsync(ctx->d_result, 0, size_t(km) * sizeof(double), ctx->stream));
     if (finish_with_peers(ctx, km, &direct))
       return 1;
-  } else {
-    MfParams p;
-    bool vec = aligned16(ri);
-    for (int k = 0; k < kMfMaxLater; ++k) {
-      p.rj[k] = k < m ? rj[k] : nullptr;
-      p.neg_ov[k] = k < m ? -ov[k] : 0.0;
-      if (k < m) {
-        ITSOLV_REQUIRE(rj[k] != ri, "itsolv_mgs_step_dots_f64: a target aliases the pivot vector");
-        for (int k2 = 0; k2 < k; ++k2)
-          ITSOLV_REQUIRE(rj[k] != rj[k2], "itsolv_mgs_step_dots_f64: the same target twice");
-        vec = vec && aligned16(rj[k]);
-      }
-    }
-    p.ri = ri;
-    p.inv_norm = inv_norm;
-    p.n = n;
-    p.m = m;
-    int mt = 0;
-    if (m > 0) {
-      mt = 1;
-      while (mt < m)
-        mt *= 2;
-    }
-    MfKernel kernel = mf_pick(mt, vec);
-    ITSOLV_REQUIRE(kernel != nullptr, "itsolv_mgs_step_dots_f64: vector count not instantiated");
-    const int per_sm = mt <= 4 ? 4 : 2;
-    const int unroll = mt <= 1 ? 4 : (mt <= 4 ? 2 : 1);
-    const size_t units = vec ? n / 2 : n;
-    const size_t want = (units + size_t(kMfThreads) * unroll - 1) / (size_t(kMfThreads) * unroll);
-    const int grid = int(std::max<size_t>(1, std::min<size_t>(want, size_t(ctx->num_sms) * per_sm)));
-    if (ensure_partials(ctx, size_t(grid) * km))
-      return 1;
-    fill_finalize(ctx, ctx->num_sms * per_sm, km, &p.fin, &direct);
-    mark_launch(ctx);
-    kernel<<<grid, kMfThreads, 0, ctx->stream>>>(p);
-    ITSOLV_CUDA(cudaGetLastError());
-    ctx->counters.launches += 1;
-    if (!p.fin.fused) {
-      if (launch_reduce_partials(ctx, grid, km))
-        return 1;
-      if (finish_with_peers(ctx, km, &direct))
-        return 1;
-    }
+  } else if (mgs_step_launch(ctx, inv_norm, ri, ov, rj, m, n, nullptr, &direct)) {
+    return 1;
   }
   scope.stop();
   return finish_result(ctx, km, dots, direct);
+}
+
+int itsolv_mgs_chain_supported(itsolv_ctx* ctx, int w, size_t n) {
+  if (ctx->opt_mgs_chain + kMgsChainDefault <= 0 || w < 1 || w > kMfMaxLater + 1 || n == 0)
+    return 0;
+  GiPeers peers;
+  // the sums must be delivered by the kernels themselves (single rank, or exchange buffers of all ranks mapped)
+  return (itsolv_comm_size(ctx) == 1 || comm_peers(ctx, &peers)) ? 1 : 0;
+}
+
+int itsolv_mgs_chain_f64(itsolv_ctx* ctx, double* const* r, int w, size_t n, double thresh, double* rows) {
+  ITSOLV_REQUIRE(itsolv_mgs_chain_supported(ctx, w, n), "itsolv_mgs_chain_f64: not available for this call");
+  ITSOLV_REQUIRE(r != nullptr && rows != nullptr, "itsolv_mgs_chain_f64: null argument");
+  for (int i = 0; i < w; ++i)
+    for (int j = 0; j < i; ++j)
+      ITSOLV_REQUIRE(r[i] != r[j], "itsolv_mgs_chain_f64: the same vector twice");
+  ctx->counters.n_scal += w;
+  ctx->counters.n_axpy += w * (w - 1) / 2;
+  ctx->counters.n_dot += w * (w + 1) / 2 + w;
+  // device scratch: coefficients of step i at chain + 32 i (upper part of the device result buffer)
+  double* chain = ctx->d_result + 12288;
+  size_t offset = 0; // of the next block of sums in the host result buffer
+  bool direct = false;
+  {
+    // the first pivot's norm and overlaps with all later vectors: one Gram row, its tail prepares step 0
+    CallScope scope(ctx, OP_GEMM_INNER, 8.0 * double(n) * w);
+    ctx->result_offset = offset;
+    ctx->chain_out = chain;
+    ctx->chain_offset = 0;
+    ctx->chain_count = w;
+    ctx->chain_thresh = thresh;
+    const double* x0 = r[0];
+    if (gemm_inner_device(ctx, &x0, 1, r, w, n, &direct))
+      return 1;
+    ITSOLV_REQUIRE(direct, "itsolv_mgs_chain_f64: the Gram row was not delivered by the kernel");
+    offset += size_t(w);
+  }
+  for (int i = 0; i < w; ++i) {
+    const int m = w - i - 1;
+    CallScope scope(ctx, OP_BLAS1, 16.0 * double(n) * (m + 1));
+    ctx->result_offset = offset;
+    if (m > 0) { // the sums of this step hold the next pivot's row from index 1 on
+      ctx->chain_out = chain + 32 * (i + 1);
+      ctx->chain_offset = 1;
+      ctx->chain_count = m;
+      ctx->chain_thresh = thresh;
+    }
+    if (mgs_step_launch(ctx, 1.0, r[i], nullptr, r + i + 1, m, n, chain + 32 * i, &direct))
+      return 1;
+    ITSOLV_REQUIRE(direct, "itsolv_mgs_chain_f64: the sums were not delivered by the kernel");
+    offset += size_t(m + 1);
+  }
+  // one wait for the whole chain: the sequence word of the last launch implies all earlier ones (stream order)
+  if (wait_host_result(ctx))
+    return 1;
+  for (size_t e = 0; e < offset; ++e)
+    rows[e] = ctx->h_result[e];
+  return 0;
 }
 
 } // extern "C"

@@ -221,6 +221,29 @@ public:
     return dots;
   }
   static constexpr size_t max_mgs_step_dots = 16;
+  //! can the R-R Gram-Schmidt of these vectors run as one chain of launches (itsolv_mgs_chain_f64)?
+  bool mgs_chain_supported(const VecRef<AL>& rr) const {
+    return !rr.empty() &&
+           itsolv_mgs_chain_supported(rr[0].get().context(), int(rr.size()), rr[0].get().local_size()) != 0;
+  }
+  //! the chain; returns the rows of inner products in the layout of include/itsolv_b200.h
+  std::vector<double> mgs_chain(const VecRef<AL>& rr, double thresh) {
+    const size_t w = rr.size();
+    this->m_counter->scal += int(w);
+    this->m_counter->axpy += int(w * (w - 1) / 2);
+    this->m_counter->dot += int(w * (w + 1) / 2 + w);
+    std::vector<double*> pr(w);
+    for (size_t i = 0; i < w; ++i) {
+      rr[0].get().require_compatible(rr[i].get(), "mgs_chain");
+      pr[i] = rr[i].get().data();
+    }
+    std::vector<double> rows(w + w * (w + 1) / 2);
+    check(itsolv_mgs_chain_f64(rr[0].get().context(), pr.data(), int(w), rr[0].get().local_size(), thresh, rows.data()),
+          "ArrayHandlerCUDA::mgs_chain");
+    if (m_observer)
+      m_observer('g', 1, rows.size(), rows.data());
+    return rows;
+  }
   //! yy[j] = yscale[j] * yy[j] + sum_i alphas(i,j) xx[i]: scal_batch followed by gemm_outer, in one pass
   void gemm_outer_scaled(const Matrix<value_type>& alphas, const CVecRef<AR>& xx, const VecRef<AL>& yy,
                          const std::vector<double>& yscale) {

@@ -698,7 +698,25 @@ protected:
     std::vector<int> null_params;
     std::vector<double> final_dot(nN, -1.0); // <r_i, r_i> after the step, where known
     std::vector<double> row;                  // {<r_i, r_i>, <r_i, r_j> for j > i} of the current pivot
-    for (size_t i = 0; i < nN; ++i) {
+    const bool chained = nN > 0 && m_dense->mgs_chain_supported(wresidual);
+    if (chained) {
+      // all pivot steps as one chain of launches: the coefficients of a step are formed on the device by the tail of
+      // the launch before it, with this loop's arithmetic; the decisions are repeated here from the returned sums
+      const auto rows = m_dense->mgs_chain(wresidual, this->propose_rspace_norm_thresh);
+      size_t at = 0;
+      for (size_t i = 0; i < nN; ++i) {
+        const double rr = i == 0 ? rows[0] : rows[at + 1]; // <r_i, r_i> before its own step
+        if (i == 0)
+          at = nN;               // block of step 0
+        else
+          at += nN - i + 1;      // block of step i (the block of step i-1 has nN - i + 1 entries)
+        if (std::sqrt(std::abs(rr)) > this->propose_rspace_norm_thresh)
+          final_dot[i] = rows[at];
+        else
+          null_params.push_back(int(i));
+      }
+    }
+    for (size_t i = 0; i < nN && !chained; ++i) {
       VecRef<R> later(wresidual.begin() + i + 1, wresidual.end());
       if (row.size() != nN - i) {
         const auto g = m_dense->gemm_inner(CVecRef<R>{std::cref(wresidual[i].get())},

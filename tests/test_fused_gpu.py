@@ -193,3 +193,78 @@ def test_equation_solvers_on_the_fused_x_space_match_reference_golden(ctx, name)
     for s, chk, head in zip(sol, want["solution_checksums"], want["solution_head"]):
         assert abs(np.sum(s) - chk) <= vtol * max(1.0, np.abs(s).sum())
         assert np.abs(s[:8] - np.array(head)).max() <= vtol * max(1.0, np.abs(np.array(head)).max())
+
+
+def unchained_mgs(ctx, rs, thresh):
+    """the R-R Gram-Schmidt as FusedDavidson.h runs it without the chain: one Gram row, then a step per pivot with the
+    coefficients formed on the host"""
+    w = len(rs)
+    row, nulls = None, []
+    for i in range(w):
+        if row is None:
+            row = ctx.gemm_inner([rs[i]], rs[i:])[0]
+        norm = np.sqrt(abs(row[0]))
+        if norm > thresh:
+            dots = ctx.mgs_step_dots(1.0 / norm, rs[i], row[1:] / norm, rs[i + 1:])
+            row = dots[1:]
+        else:
+            nulls.append(i)
+            row = None
+    return nulls
+
+
+@pytest.mark.parametrize("n,w", [(1000, 1), (4097, 2), (50001, 4), (20000, 7), (3001, 17)])
+def test_mgs_chain_equals_the_steps_one_by_one(ctx, n, w):
+    """itsolv_mgs_chain_f64: the coefficients the kernel tails leave on the device are the host's, bit for bit, so the
+    vectors after the chain are bit-identical to the step-by-step sequence"""
+    rng = np.random.default_rng(n + w)
+    R = rng.standard_normal((w, n)) + 0.3 * rng.standard_normal(n)[None, :]  # correlated: the projections matter
+    a, b = dev_rows(R), dev_rows(R)
+    old = ctx.set_option("MGS_CHAIN", 1)
+    try:
+        rows = ctx.mgs_chain(a, 1e-10)
+    finally:
+        ctx.set_option("MGS_CHAIN", old)
+    assert unchained_mgs(ctx, b, 1e-10) == []
+    assert np.array_equal(host(a), host(b))
+    Q = host(a)
+    assert np.abs(Q @ Q.T - np.eye(w)).max() <= 1e-12
+    assert rows.size == w + w * (w + 1) // 2 and abs(rows[0] - R[0] @ R[0]) <= 1e-12 * (R[0] @ R[0])
+
+
+def test_mgs_chain_leaves_a_null_pivot_alone(ctx):
+    rng = np.random.default_rng(11)
+    R = rng.standard_normal((4, 6000))
+    R[1] = 0.0  # a null vector in the middle: neither scaled nor projected out of the later ones
+    a, b = dev_rows(R), dev_rows(R)
+    old = ctx.set_option("MGS_CHAIN", 1)
+    try:
+        ctx.mgs_chain(a, 1e-10)
+    finally:
+        ctx.set_option("MGS_CHAIN", old)
+    assert unchained_mgs(ctx, b, 1e-10) == [1]
+    A, B = host(a), host(b)
+    assert np.array_equal(A[1], np.zeros(6000)) and np.array_equal(A[0], B[0])
+    assert np.abs(A - B).max() <= 1e-13  # after the null pivot the next row comes from a different kernel: rounding only
+    keep = [0, 2, 3]
+    assert np.abs(A[keep] @ A[keep].T - np.eye(3)).max() <= 1e-12
+
+
+@pytest.mark.parametrize("name", DAVIDSON)
+def test_fused_solve_with_chained_gram_schmidt_matches_reference_golden(ctx, name):
+    want = GOLDEN[name]
+    old = ctx.set_option("MGS_CHAIN", 1)
+    try:
+        res, sol = H.solve(ctx, H.make_spec(fused=1, **want["spec"]), want_solutions=True)
+        plain, _ = H.solve(ctx, H.make_spec(fused=1, **want["spec"]))
+    finally:
+        ctx.set_option("MGS_CHAIN", old)
+    unchained, _ = H.solve(ctx, H.make_spec(fused=1, **want["spec"]))
+    assert res.iterations == want["iterations"] and res.converged == want["converged"]
+    assert [res.r_creations, res.q_creations, res.p_creations, res.d_creations] == want["creations"]
+    ev = np.array([res.eigenvalues[i] for i in range(res.nroots)])
+    assert np.abs(ev / np.array(want["eigenvalues"]) - 1).max() <= 1e-10
+    # bit-identical vectors along the way: the same eigenvalues as without the chain, to the last bit
+    assert [plain.eigenvalues[i] for i in range(res.nroots)] == [unchained.eigenvalues[i] for i in range(res.nroots)]
+    for s, chk in zip(sol, want["solution_checksums"]):
+        assert abs(np.sum(s) - chk) <= 1e-7 * max(1.0, np.abs(s).sum())
