@@ -26,7 +26,7 @@ int finish_result(itsolv_ctx* ctx, int count, double* out, bool host_direct);   
 
 constexpr int kMfThreads = 256;
 constexpr int kMfMaxLater = 16; // later vectors per launch
-constexpr int kMgsChainDefault = 0; // option MGS_CHAIN is added to this: > 0 chains the steps on the device
+constexpr int kMgsChainDefault = 1; // option MGS_CHAIN is added to this: > 0 chains the steps on the device (MGS_CHAIN=-1: off)
 
 struct MfParams {
   double* ri;

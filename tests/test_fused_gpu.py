@@ -257,9 +257,11 @@ def test_fused_solve_with_chained_gram_schmidt_matches_reference_golden(ctx, nam
     try:
         res, sol = H.solve(ctx, H.make_spec(fused=1, **want["spec"]), want_solutions=True)
         plain, _ = H.solve(ctx, H.make_spec(fused=1, **want["spec"]))
+        ctx.set_option("MGS_CHAIN", -1)  # the steps one by one, coefficients formed on the host
+        unchained, _ = H.solve(ctx, H.make_spec(fused=1, **want["spec"]))
+        assert unchained.kernel_launches == plain.kernel_launches  # the same launches, only the waiting differs
     finally:
         ctx.set_option("MGS_CHAIN", old)
-    unchained, _ = H.solve(ctx, H.make_spec(fused=1, **want["spec"]))
     assert res.iterations == want["iterations"] and res.converged == want["converged"]
     assert [res.r_creations, res.q_creations, res.p_creations, res.d_creations] == want["creations"]
     ev = np.array([res.eigenvalues[i] for i in range(res.nroots)])
