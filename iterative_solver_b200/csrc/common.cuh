@@ -98,7 +98,6 @@ struct itsolv_ctx {
   int opt_go_ctas = 0;    // gemm_outer CTAs per SM
   int opt_blas1_ctas = 0; // CTAs per SM for streaming kernels
   int opt_ds_ring = 0;    // davidson_residual: <0 never use the cp.async ring kernel
-  int opt_stream_ring = 0; // gemm_outer / mgs_step_dots: <0 never use the cp.async ring kernels
   int opt_mgs_chain = 0;   // R-R Gram-Schmidt steps chained on the device: 0 default (on, see mgs_fused.cu), -1 off
   int opt_p2p_allreduce = 0; // <0: use ncclAllReduce even when the peer buffers are mapped
 
