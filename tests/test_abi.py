@@ -48,6 +48,20 @@ def test_host_library_exports_the_flat_solver_interface():
     assert lib.ItsolvB200Finalize() != 0
 
 
+@pytest.mark.parametrize("header", ["itsolv_b200.h", "itsolv_b200_harness.h", "itsolv_b200_solver.h"])
+def test_public_headers_are_plain_c(header):
+    """the boundary is a C ABI: every public header must compile as C99 (no C++ types, no torch types) and as C++"""
+    import shutil
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    for compiler, flags in (("gcc", ["-std=c99", "-x", "c"]), ("g++", ["-std=c++17", "-x", "c++"])):
+        if shutil.which(compiler) is None:
+            pytest.skip(f"{compiler} is not installed")
+        r = subprocess.run([compiler, "-fsyntax-only", "-Wall", "-Wextra", "-pedantic", "-I" + inc] + flags +
+                           [os.path.join(inc, header)], capture_output=True, text=True)
+        assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+
+
 def test_struct_layouts_match_the_header():
     import ctypes as C
     assert C.sizeof(N.SolveSpec) == 80
