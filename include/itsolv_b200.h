@@ -203,7 +203,9 @@ int itsolv_csr_apply_multi_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_of
                                const int64_t* row_ptr, const int32_t* col, const double* val, int w,
                                const double* const* x, const double* const* x_lo, const double* const* x_hi,
                                double* const* y);
-/* d[i] = row_offset+i+1 ; fills a vector with f(global index): kind 0 = diagonal, 1 = rhs_solution(k) (harness RHS generator) */
+/* d[i] = row_offset+i+1 ; fills a vector with f(global index): kind 0 = diagonal,
+ * 1 = u_k(i), 2 = ((k+1) + u_k(i)) / (i+1) with u_k(i) = ((i (k+2) + k) mod (2k+5)) / (2k+5) - 1/2 (known solutions of the
+ * harness' LinearEquations right-hand sides, include/itsolv_b200_harness.h ITSOLV_RHS_*) */
 int itsolv_banded_fill_f64(itsolv_ctx* ctx, int kind, int k, int64_t row_offset, size_t n, double* out);
 /* P-space part of the action (reference Problem::p_action, itsolv/IterativeSolver.h:160-171; example
  * examples/ExampleProblemDistrArray.h:100-116): actions[k] += sum_p pcoef[k*nP+p] * A * P_p for the banded operator */

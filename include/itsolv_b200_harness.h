@@ -26,6 +26,14 @@ enum {
   ITSOLV_PROBLEM_BANDED = 0, /* synthetic banded symmetric operator, SURVEY.md section 8(d) */
   ITSOLV_PROBLEM_EXAMPLE = 1 /* dense matrix of the reference's examples/ExampleProblem.h:8 (small n only) */
 };
+/* Right-hand sides of the LinearEquations cases, b_k = A x_k with a known x_k; u_k(i) = ((i (k+2) + k) mod (2k+5)) / (2k+5) - 1/2.
+ *   SCALED (default): x_k(i) = ((k+1) + u_k(i)) / (i+1): b_k has entries of order one in every row, so the relative
+ *     residual weighs all rows alike and the reference's solver converges in a size-independent number of iterations
+ *     (the right-hand sides of the reference's own test, test/itsolv/test_LinearEquations.cpp:29-33, are A (k+1) 1; on
+ *     this operator, whose diagonal grows like i, those are parallel and dominated by the last rows).
+ *   LEGACY: x_k(i) = u_k(i): b_k(i) ~ i u_k(i); the reference's solver stagnates on it from n ~ 1e5 on (kept as a test of
+ *     identical behaviour on an ill-posed input). */
+enum { ITSOLV_RHS_SCALED = 0, ITSOLV_RHS_LEGACY = 1 };
 #define ITSOLV_MAX_ROOTS 64
 
 typedef struct itsolv_solve_spec {
@@ -48,6 +56,7 @@ typedef struct itsolv_solve_spec {
   int32_t fused;                /* CUDA backend: 1 = fused driver path (Davidson: FusedDavidson.h, 2 = its batched pieces under
                                    the reference's solve() loop; LinearEquations / DIIS: fused X space, FusedEquations.h);
                                    0 = the reference's classes call for call; ignored by the oracle */
+  int32_t rhs_kind;             /* LinearEquations right-hand sides b_k = A x_k of the harness (ITSOLV_RHS_*) */
 } itsolv_solve_spec;
 
 typedef struct itsolv_solve_result {

@@ -34,7 +34,7 @@ class SolveSpec(C.Structure):
                 ("nbuffers", C.c_int32), ("half_bandwidth", C.c_int32), ("hermitian", C.c_int32), ("eps", C.c_double),
                 ("convergence_threshold", C.c_double), ("max_iter", C.c_int32), ("max_size_qspace", C.c_int32),
                 ("reset_D", C.c_int32), ("max_p", C.c_int32), ("verbosity", C.c_int32), ("trace", C.c_int32),
-                ("explicit_csr", C.c_int32), ("fused", C.c_int32)]
+                ("explicit_csr", C.c_int32), ("fused", C.c_int32), ("rhs_kind", C.c_int32)]
 
 
 class SolveResult(C.Structure):
@@ -60,6 +60,7 @@ class TraceEntry(C.Structure):
 
 KIND_DAVIDSON, KIND_LINEQ, KIND_DIIS = 0, 1, 2
 PROBLEM_BANDED, PROBLEM_EXAMPLE = 0, 1
+RHS_SCALED, RHS_LEGACY = 0, 1
 
 # name -> (restype, argtypes); the names are exactly the declarations of include/itsolv_b200.h
 KERNEL_API = {

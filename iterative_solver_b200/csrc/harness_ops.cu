@@ -245,7 +245,12 @@ __global__ void __launch_bounds__(256) csr_apply_multi_wide_kernel(const __grid_
 __global__ void __launch_bounds__(256) banded_fill_kernel(int kind, int k, long long off, long long n, double* __restrict__ out) {
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
     const long long i = off + r;
-    out[r] = kind == 0 ? double(i + 1) : double((i * (k + 2) + k) % (2 * k + 5)) / double(2 * k + 5) - 0.5;
+    if (kind == 0) {
+      out[r] = double(i + 1);
+    } else {
+      const double u = __dsub_rn(__ddiv_rn(double((i * (k + 2) + k) % (2 * k + 5)), double(2 * k + 5)), 0.5);
+      out[r] = kind == 1 ? u : __ddiv_rn(__dadd_rn(double(k + 1), u), double(i + 1));
+    }
   }
 }
 

@@ -12,11 +12,11 @@ from .api import BackendError, Context, _dbl
 
 def make_spec(n, kind=N.KIND_DAVIDSON, problem=N.PROBLEM_BANDED, nroots=1, nbuffers=0, half_bandwidth=4, hermitian=1,
               eps=1e-3, convergence_threshold=0.0, max_iter=0, max_size_qspace=0, reset_D=0, max_p=0, verbosity=0,
-              trace=0, explicit_csr=0, fused=0) -> N.SolveSpec:
+              trace=0, explicit_csr=0, fused=0, rhs_kind=N.RHS_SCALED) -> N.SolveSpec:
     return N.SolveSpec(n=n, kind=kind, problem=problem, nroots=nroots, nbuffers=nbuffers, half_bandwidth=half_bandwidth,
                        hermitian=hermitian, eps=eps, convergence_threshold=convergence_threshold, max_iter=max_iter,
                        max_size_qspace=max_size_qspace, reset_D=reset_D, max_p=max_p, verbosity=verbosity, trace=trace,
-                       explicit_csr=explicit_csr, fused=fused)
+                       explicit_csr=explicit_csr, fused=fused, rhs_kind=rhs_kind)
 
 
 def _hcheck(rc: int):

@@ -43,7 +43,8 @@ inline double band_entry_host(int64_t i, int64_t j, double eps) {
 class DeviceProblem : public its::Problem<R>, public itsolv_b200::UsesDefaultDiagonalPreconditioner {
 public:
   DeviceProblem(itsolv_ctx* ctx, const itsolv_solve_spec& spec)
-      : ctx(ctx), n(spec.n), b(spec.half_bandwidth), eps(spec.eps), kind(spec.problem), scratch(size_t(spec.n), ctx) {
+      : ctx(ctx), n(spec.n), b(spec.half_bandwidth), eps(spec.eps), kind(spec.problem), rhs_kind(spec.rhs_kind),
+        scratch(size_t(spec.n), ctx) {
     nranks = itsolv_comm_size(ctx);
     rank = itsolv_comm_rank(ctx);
     start = int64_t(scratch.local_start());
@@ -69,6 +70,7 @@ public:
   const int b;
   const double eps;
   const int kind;
+  int rhs_kind; //!< ITSOLV_RHS_*: which known solutions x_k the right-hand sides b_k = A x_k are built from
   int nranks = 1, rank = 0;
   int64_t start = 0;
   size_t nloc = 0;
@@ -238,8 +240,12 @@ public:
   }
 
   void make_rhs(int k, R& out) const {
-    check(itsolv_banded_fill_f64(ctx, 1, k, start, nloc, scratch.data()), "make_rhs");
+    rhs_solution(k, scratch);
     apply(scratch, out);
+  }
+  //! the known solution x_k of right-hand side k
+  void rhs_solution(int k, R& out) const {
+    check(itsolv_banded_fill_f64(ctx, rhs_kind == ITSOLV_RHS_LEGACY || kind == ITSOLV_PROBLEM_EXAMPLE ? 1 : 2, k, start, nloc, out.data()), "rhs_solution");
   }
 };
 
@@ -369,6 +375,7 @@ int itsolv_harness_problem_solve(itsolv_harness_problem* p, const itsolv_solve_s
   return guarded([&] {
     if (spec->n != p->problem->n || spec->half_bandwidth != p->problem->b || spec->problem != p->problem->kind)
       throw std::invalid_argument("itsolv_harness_problem_solve: spec does not describe this operator");
+    p->problem->rhs_kind = spec->rhs_kind;
     DeviceBackend backend(p->ctx, *p->problem, size_t(spec->n));
     itsolv_ctx_reset_counters(p->ctx);
     itsolv_b200::harness::run_solve(*spec, backend, *result, solutions);

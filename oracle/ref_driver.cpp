@@ -86,10 +86,11 @@ inline double band_entry(int64_t i, int64_t j, double eps) {
  */
 class BandedProblemHost : public its::Problem<Vec> {
 public:
-  BandedProblemHost(int64_t n, int b, double eps) : n(n), b(b), eps(eps) {}
+  BandedProblemHost(int64_t n, int b, double eps, int rhs_kind = ITSOLV_RHS_SCALED) : n(n), b(b), eps(eps), rhs_kind(rhs_kind) {}
   const int64_t n;
   const int b;
   const double eps;
+  const int rhs_kind;
   mutable double seconds_action = 0, seconds_precond = 0;
 
   void apply(const Vec& v, Vec& a) const {
@@ -160,11 +161,16 @@ public:
         }
     }
   }
-  static double rhs_solution(int k, int64_t i) { return double((i * (k + 2) + k) % (2 * k + 5)) / double(2 * k + 5) - 0.5; }
+  //! known solutions of the right-hand sides (include/itsolv_b200_harness.h, ITSOLV_RHS_*); the CUDA harness generates the same numbers
+  static double rhs_u(int k, int64_t i) { return double((i * (k + 2) + k) % (2 * k + 5)) / double(2 * k + 5) - 0.5; }
+  static double rhs_solution(int rhs_kind, int k, int64_t i) {
+    const double u = rhs_u(k, i);
+    return rhs_kind == ITSOLV_RHS_LEGACY ? u : (double(k + 1) + u) / double(i + 1);
+  }
   void make_rhs(int k, Vec& out) const {
     Vec u(n);
     for (int64_t i = 0; i < n; ++i)
-      u[i] = rhs_solution(k, i);
+      u[i] = rhs_solution(rhs_kind, k, i);
     apply(u, out);
   }
 };
@@ -177,7 +183,7 @@ public:
   void make_rhs(int k, Vec& out) const {
     Vec u(n);
     for (size_t i = 0; i < n; ++i)
-      u[i] = BandedProblemHost::rhs_solution(k, int64_t(i));
+      u[i] = BandedProblemHost::rhs_u(k, int64_t(i));
     ExampleProblem::action(its::cwrap_arg(u), its::wrap_arg(out));
   }
 };
@@ -234,7 +240,7 @@ int ref_solve(const itsolv_solve_spec* spec, itsolv_solve_result* result, double
       HostBackend<ExampleProblemHost> backend(problem, spec->n);
       return itsolv_b200::harness::run_solve(*spec, backend, *result, solutions);
     }
-    BandedProblemHost problem(spec->n, spec->half_bandwidth, spec->eps);
+    BandedProblemHost problem(spec->n, spec->half_bandwidth, spec->eps, spec->rhs_kind);
     HostBackend<BandedProblemHost> backend(problem, spec->n);
     return itsolv_b200::harness::run_solve(*spec, backend, *result, solutions);
   } catch (const std::exception& e) {

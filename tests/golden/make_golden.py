@@ -35,11 +35,16 @@ SOLVE_CASES = {
     "banded_davidson_n30000_r6_buf2": dict(n=30000, kind=N.KIND_DAVIDSON, nroots=6, nbuffers=2, hermitian=1),
     "banded_davidson_n30000_r4_p20": dict(n=30000, kind=N.KIND_DAVIDSON, nroots=4, hermitian=1, max_p=20),
     "banded_davidson_n30000_r4_wide": dict(n=30000, kind=N.KIND_DAVIDSON, nroots=4, hermitian=1, half_bandwidth=16, eps=1e-2),
+    # LinearEquations: right-hand sides b_k = A x_k with the scaled known solutions (ITSOLV_RHS_SCALED, the default)
     "banded_lineq_n50000_r1": dict(n=50000, kind=N.KIND_LINEQ, nroots=1, hermitian=1),
     "banded_lineq_n1000_r3": dict(n=1000, kind=N.KIND_LINEQ, nroots=3, hermitian=1),
     "banded_lineq_n100000_r3": dict(n=100000, kind=N.KIND_LINEQ, nroots=3, hermitian=1),
     "banded_lineq_n20000_r8": dict(n=20000, kind=N.KIND_LINEQ, nroots=8, hermitian=1),
     "banded_lineq_n20000_r8_qcap12": dict(n=20000, kind=N.KIND_LINEQ, nroots=8, hermitian=1, max_size_qspace=12),
+    "banded_lineq_n30000_r8_buf3": dict(n=30000, kind=N.KIND_LINEQ, nroots=8, nbuffers=3, hermitian=1),
+    "banded_lineq_n30000_r4_p20": dict(n=30000, kind=N.KIND_LINEQ, nroots=4, hermitian=1, max_p=20),
+    "banded_lineq_n1000_r3_legacy_rhs": dict(n=1000, kind=N.KIND_LINEQ, nroots=3, hermitian=1, rhs_kind=N.RHS_LEGACY),
+    "banded_lineq_n20000_r8_legacy_rhs": dict(n=20000, kind=N.KIND_LINEQ, nroots=8, hermitian=1, rhs_kind=N.RHS_LEGACY),
     "banded_diis_n50000": dict(n=50000, kind=N.KIND_DIIS, max_size_qspace=6),
 }
 

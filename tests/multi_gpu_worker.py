@@ -149,19 +149,19 @@ def main():
         mark("fused " + name)
 
     # the reference's solver classes on sharded vectors against the reference's golden results, call for call.
-    # Eigenvectors are compared to 1e-7; solutions of the linear and non-linear equations to 1e-4 as in
-    # tests/test_solve_gpu.py: two runs that both meet the residual threshold (1e-8 relative to a right-hand side of norm
-    # ~2e6) agree only to that threshold times the conditioning, and the summation order of the inner products changes
-    # with the number of ranks (measured: 3.3e-6 on 8 ranks for banded_lineq_n50000_r1, below 1e-7 on 1, 2 and 4 ranks).
+    # Eigenvectors are compared to 1e-7; solutions of the linear and non-linear equations to 1e-6 as in
+    # tests/test_solve_gpu.py: two runs that both meet the residual threshold agree to that threshold times the
+    # conditioning, and the summation order of the inner products changes with the number of ranks.
     report = {}
     for name in ("banded_davidson_n100000_r4", "banded_davidson_n30000_r6_qcap8", "banded_davidson_n30000_r4_p20",
-                 "banded_lineq_n50000_r1", "banded_diis_n50000", "banded_davidson_n30000_r16"):
+                 "banded_lineq_n50000_r1", "banded_lineq_n20000_r8_qcap12", "banded_diis_n50000",
+                 "banded_davidson_n30000_r16"):
         want = golden[name]
         spec = H.make_spec(trace=1, **want["spec"])
         res, sol = H.solve(ctx, spec, want_solutions=True)
         expect(res.iterations == want["iterations"] and res.converged == want["converged"], f"{name}: iterations")
         expect([[op, r, c] for op, r, c, _ in H.read_trace()] == want["trace_shapes"], f"{name}: call trace")
-        check_solutions(name, want, res, sol, 1e-7 if want["eigenvalues"] else 1e-4)
+        check_solutions(name, want, res, sol, 1e-7 if want["eigenvalues"] else 1e-6)
         report[name] = res.iterations
         mark("unfused " + name)
     mark("problems: " + repr(problems))

@@ -97,8 +97,8 @@ def test_linear_equations_through_the_flat_interface(ctx, options):
     kernels = N.kernels()
     scratch = torch.zeros(n, dtype=torch.float64, device="cuda")
     rhs = torch.zeros((nroots, n), dtype=torch.float64, device="cuda")
-    for k in range(nroots):  # the harness's right-hand sides: A applied to a generated vector
-        assert kernels.itsolv_banded_fill_f64(ctx.handle, 1, k, 0, n, scratch.data_ptr()) == 0
+    for k in range(nroots):  # the harness's right-hand sides: A applied to the known solutions (ITSOLV_RHS_SCALED)
+        assert kernels.itsolv_banded_fill_f64(ctx.handle, 2, k, 0, n, scratch.data_ptr()) == 0
         ctx.banded_apply(scratch, rhs[k], n, 0, B, EPS)
     lo, hi = C.c_size_t(), C.c_size_t()
     check(lib, lib.ItsolvB200LinearEquationsInitialize(ctx.handle, n, nroots, C.byref(lo), C.byref(hi), rhs.data_ptr(), 0.0,
