@@ -70,11 +70,13 @@ int itsolv_ctx_timer_stop(itsolv_ctx* ctx, int id, double* milliseconds);
 int itsolv_alloc(itsolv_ctx* ctx, size_t n, double** out);
 int itsolv_free(itsolv_ctx* ctx, double* p);
 int itsolv_upload(itsolv_ctx* ctx, double* dst_device, const double* src_host, size_t n);   /* synchronous */
-int itsolv_download(itsolv_ctx* ctx, double* dst_host, const double* src_device, size_t n); /* synchronous */
+int itsolv_download(itsolv_ctx* ctx, double* dst, const double* src_device, size_t n); /* synchronous; dst: host or device memory */
 int itsolv_upload_bytes(itsolv_ctx* ctx, void* dst_device, const void* src_host, size_t bytes);  /* synchronous */
 /* bytes currently handed out by itsolv_alloc and their high-water mark (memory planning of the large configurations) */
 int itsolv_mem_usage(itsolv_ctx* ctx, size_t* live_bytes, size_t* peak_bytes, int reset_peak);
 int itsolv_mem_info(itsolv_ctx* ctx, size_t* free_bytes, size_t* total_bytes);
+/* hands the pool's unused memory back to the driver (the pool otherwise keeps every freed vector for reuse) */
+int itsolv_mem_trim(itsolv_ctx* ctx);
 
 /* ---- communicator: row-sharded vectors, one rank per GPU; replaces the reference's MPI communicator
  * (array/DistrArray.h:100,109). The unique id is created on rank 0 and broadcast by the host (torch.distributed, MPI, ...) ---- */
@@ -217,6 +219,11 @@ int itsolv_banded_p_action_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_of
 int itsolv_example_apply_f64(itsolv_ctx* ctx, size_t n, const double* x, double* y);
 /* out[i] = x[i] + c */
 int itsolv_shift_f64(itsolv_ctx* ctx, double c, const double* x, double* out, size_t n);
+/* out[i] = x[i] - t(row_offset + i): the argument of the harness' non-linear residual r(v) = A (v - t) (DIIS cases);
+ * target_kind 0: t(i) = 1 / (i+1) (residual entries of order one in every row), 1: t(i) = 1 (legacy; its rounding floor
+ * grows like n^1.5 and passes 1e-8 at n ~ 1e6) */
+int itsolv_banded_target_shift_f64(itsolv_ctx* ctx, int target_kind, int64_t row_offset, const double* x, double* out,
+                                   size_t n);
 
 #ifdef __cplusplus
 }

@@ -56,7 +56,8 @@ typedef struct itsolv_solve_spec {
   int32_t fused;                /* CUDA backend: 1 = fused driver path (Davidson: FusedDavidson.h, 2 = its batched pieces under
                                    the reference's solve() loop; LinearEquations / DIIS: fused X space, FusedEquations.h);
                                    0 = the reference's classes call for call; ignored by the oracle */
-  int32_t rhs_kind;             /* LinearEquations right-hand sides b_k = A x_k of the harness (ITSOLV_RHS_*) */
+  int32_t rhs_kind;             /* LinearEquations right-hand sides b_k = A x_k of the harness (ITSOLV_RHS_*); DIIS: the target t of
+                                   the residual r(v) = A (v - t): SCALED t(i) = 1/(i+1), LEGACY t = 1 */
 } itsolv_solve_spec;
 
 typedef struct itsolv_solve_result {

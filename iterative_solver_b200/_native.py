@@ -84,6 +84,7 @@ KERNEL_API = {
     "itsolv_upload_bytes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "itsolv_mem_usage": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_int]),
     "itsolv_mem_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "itsolv_mem_trim": (C.c_int, [C.c_void_p]),
     "itsolv_comm_unique_id": (C.c_int, [C.c_void_p]),
     "itsolv_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "itsolv_comm_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -139,6 +140,7 @@ KERNEL_API = {
                                              c_void_pp, C.c_int, c_int32_p, c_int64_p, c_double_p, c_double_p]),
     "itsolv_example_apply_f64": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "itsolv_shift_f64": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "itsolv_banded_target_shift_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t]),
 }
 
 # declarations of include/itsolv_b200_harness.h

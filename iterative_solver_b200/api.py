@@ -79,6 +79,16 @@ class Context:
         self._check(self.lib.itsolv_mem_usage(self.handle, C.byref(live), C.byref(peak), int(reset_peak)))
         return live.value, peak.value
 
+    def mem_info(self):
+        """(free, total) bytes of the device as the driver sees them"""
+        free, total = C.c_size_t(), C.c_size_t()
+        self._check(self.lib.itsolv_mem_info(self.handle, C.byref(free), C.byref(total)))
+        return free.value, total.value
+
+    def mem_trim(self):
+        """give the pool's unused memory back to the driver"""
+        self._check(self.lib.itsolv_mem_trim(self.handle))
+
     def counters(self) -> N.Counters:
         c = N.Counters()
         self.lib.itsolv_ctx_counters(self.handle, C.byref(c))

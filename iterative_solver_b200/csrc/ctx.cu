@@ -382,8 +382,14 @@ int itsolv_upload_bytes(itsolv_ctx* ctx, void* dst, const void* src, size_t byte
   return 0;
 }
 int itsolv_download(itsolv_ctx* ctx, double* dst, const double* src, size_t n) {
-  ITSOLV_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  // cudaMemcpyDefault: dst may be host memory or, for callers that keep results on the GPU, device memory
+  ITSOLV_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDefault, ctx->stream));
   ITSOLV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int itsolv_mem_trim(itsolv_ctx* ctx) {
+  ITSOLV_CUDA(cudaStreamSynchronize(ctx->stream));
+  ITSOLV_CUDA(cudaMemPoolTrimTo(ctx->pool, 0));
   return 0;
 }
 int itsolv_mem_info(itsolv_ctx* ctx, size_t* free_bytes, size_t* total_bytes) {

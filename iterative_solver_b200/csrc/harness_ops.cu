@@ -254,6 +254,14 @@ __global__ void __launch_bounds__(256) banded_fill_kernel(int kind, int k, long 
   }
 }
 
+__global__ void __launch_bounds__(256) target_shift_kernel(int kind, long long off, long long n, const double* __restrict__ x,
+                                                           double* __restrict__ out) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const double t = kind == 1 ? 1.0 : __ddiv_rn(1.0, double(off + r + 1));
+    out[r] = __dsub_rn(x[r], t);
+  }
+}
+
 __global__ void __launch_bounds__(128) example_apply_kernel(long long n, const double* __restrict__ x, double* __restrict__ y) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n)
@@ -405,6 +413,17 @@ int itsolv_banded_fill_f64(itsolv_ctx* ctx, int kind, int k, int64_t row_offset,
   if (n == 0)
     return 0;
   banded_fill_kernel<<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(kind, k, row_offset, (long long)n, out);
+  ITSOLV_CUDA(cudaGetLastError());
+  ctx->counters.launches += 1;
+  return 0;
+}
+
+int itsolv_banded_target_shift_f64(itsolv_ctx* ctx, int target_kind, int64_t row_offset, const double* x, double* out,
+                                   size_t n) {
+  ++ctx->write_epoch;
+  if (n == 0)
+    return 0;
+  target_shift_kernel<<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(target_kind, row_offset, (long long)n, x, out);
   ITSOLV_CUDA(cudaGetLastError());
   ctx->counters.launches += 1;
   return 0;

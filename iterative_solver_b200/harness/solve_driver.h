@@ -156,6 +156,11 @@ int run_solve(const itsolv_solve_spec& spec, Backend& backend, itsolv_solve_resu
       solver.set_reset_D(spec.reset_D);
     if (spec.max_p > 0)
       solver.set_max_p(spec.max_p);
+    // Initial guess: the solver's own (unit vectors on the smallest diagonal elements, generate_initial_guess = true, as
+    // the reference's test does, test/itsolv/test_LinearEquations.cpp:83); with the legacy inputs c = rhs. The latter puts a
+    // vector with |A c| ~ n |c| into the subspace, whose coefficient then has to vanish to ~1e-8 / n: the error after a
+    // fixed number of iterations grows with n (3e-10 at n = 1e6, 1.5e-9 at 1e7 on the reference's CPU path).
+    const bool default_guess = spec.rhs_kind != ITSOLV_RHS_LEGACY;
     {
       // right-hand sides are built one at a time in a scratch R vector; the solver keeps its own Q copies
       // (XSpace::add_rhs_equations, reference subspace/XSpace.h:208-220)
@@ -163,14 +168,14 @@ int run_solve(const itsolv_solve_spec& spec, Backend& backend, itsolv_solve_resu
         R rhs = backend.make_vector();
         problem.make_rhs(k, rhs);
         solver.add_equations(rhs);
-        if (k < nbuf)
+        if (k < nbuf && !default_guess)
           handlers->rr().copy(parameters[k], rhs); // initial guess c = rhs (reference test_simplified.cpp:131-134)
       }
     }
     backend.synchronize();
     const double t0 = now_seconds();
     backend.timer_start();
-    const bool ok = solver.solve(parameters, actions, problem, false);
+    const bool ok = solver.solve(parameters, actions, problem, default_guess);
     finish(solver, ok, t0);
     export_solutions(solver);
   } else if (spec.kind == ITSOLV_KIND_DIIS) {

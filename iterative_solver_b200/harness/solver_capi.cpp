@@ -188,10 +188,12 @@ public:
     seconds_precond += now_seconds() - t0;
   }
 
-  //! r = A (v - 1), value = (v-1).r / 2  (cf. reference examples/ExampleProblem.h:24-34)
+  //! r = A (v - t), value = (v-t).r / 2  (cf. reference examples/ExampleProblem.h:24-34, where t = 1); the banded operator
+  //! takes t(i) = 1/(i+1) unless the legacy inputs are asked for (include/itsolv_b200.h, itsolv_banded_target_shift_f64)
   double residual(const R& v, R& a) const override {
     const double t0 = now_seconds();
-    check(itsolv_shift_f64(ctx, -1.0, v.data(), scratch.data(), nloc), "residual shift");
+    const int target = kind == ITSOLV_PROBLEM_EXAMPLE || rhs_kind == ITSOLV_RHS_LEGACY ? 1 : 0;
+    check(itsolv_banded_target_shift_f64(ctx, target, start, v.data(), scratch.data(), nloc), "residual shift");
     apply(scratch, a);
     const double value = 0.5 * a.dot(scratch);
     seconds_action += now_seconds() - t0;

@@ -172,6 +172,15 @@ public:
     return fresh;
   }
 
+  //! Frees the device memory now and leaves an empty() vector of the same shape: for owners that know the contents are
+  //! dead before the object itself is destroyed (the fused D-space construction, memory-capped runs)
+  void release_storage() noexcept {
+    if (m_data && m_ctx && m_owner) {
+      itsolv_free(m_ctx, m_data);
+      m_data = nullptr;
+    }
+  }
+
   void require_compatible(const DistrArrayCUDA& o, const char* op) const {
     if (!m_data || !o.m_data || !compatible(o))
       throw std::runtime_error(std::string("DistrArrayCUDA::") + op + ": incompatible arrays");

@@ -519,10 +519,8 @@ protected:
     if (nD == 0 || (qparams.empty() && dparams.empty()))
       return std::make_tuple(std::move(dparams_new), std::move(dactions_new));
     const R& shape = !qparams.empty() ? qparams.front().get() : dparams.front().get();
-    for (size_t i = 0; i < nD; ++i) {
-      dparams_new.emplace_back(shape.size(), shape.context());
-      dactions_new.emplace_back(shape.size(), shape.context());
-    }
+    const size_t dimension = shape.size();
+    itsolv_ctx* const context = shape.context();
     CVecRef<R> xpar, xact;
     for (auto j : q_delete) {
       xpar.emplace_back(qparams.at(j));
@@ -534,8 +532,21 @@ protected:
     for (size_t i = 0; i < nD; ++i)
       for (size_t j = 0; j < nQd + dims.nD; ++j)
         c(j, i) = solutions_proj(i, j);
+    // The sources - the Q vectors that leave and the whole old D space - are erased by the caller right after this
+    // function (eraseq, DSpace::update) without being read again. Their memory is given back as soon as each half is
+    // consumed, so the transient is nD vectors instead of 2 nD: what decides which configurations fit.
+    auto release = [](const CVecRef<R>& dead) {
+      for (const auto& v : dead)
+        const_cast<R&>(v.get()).release_storage();
+    };
+    for (size_t i = 0; i < nD; ++i)
+      dparams_new.emplace_back(dimension, context);
     m_dense->gemm_outer_assign(c, xpar, its::wrap(dparams_new));
+    release(xpar);
+    for (size_t i = 0; i < nD; ++i)
+      dactions_new.emplace_back(dimension, context);
     m_dense->gemm_outer_assign(c, xact, its::wrap(dactions_new));
+    release(xact);
     const auto d = m_dense->self_dots(its::cwrap(dparams_new));
     std::vector<double> alpha(2 * nD);
     VecRef<R> both = its::wrap(dparams_new);

@@ -124,8 +124,8 @@ public:
   double residual(const Vec& v, Vec& a) const override {
     const double t0 = now_seconds();
     Vec shifted(v.size());
-    for (size_t i = 0; i < v.size(); ++i)
-      shifted[i] = v[i] - 1;
+    for (size_t i = 0; i < v.size(); ++i) // target t(i) of the DIIS cases: 1/(i+1), or 1 for the legacy inputs
+      shifted[i] = v[i] - (rhs_kind == ITSOLV_RHS_LEGACY ? 1.0 : 1.0 / double(i + 1));
     apply(shifted, a);
     double value = 0;
     for (size_t i = 0; i < v.size(); ++i)

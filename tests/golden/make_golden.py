@@ -45,7 +45,10 @@ SOLVE_CASES = {
     "banded_lineq_n30000_r4_p20": dict(n=30000, kind=N.KIND_LINEQ, nroots=4, hermitian=1, max_p=20),
     "banded_lineq_n1000_r3_legacy_rhs": dict(n=1000, kind=N.KIND_LINEQ, nroots=3, hermitian=1, rhs_kind=N.RHS_LEGACY),
     "banded_lineq_n20000_r8_legacy_rhs": dict(n=20000, kind=N.KIND_LINEQ, nroots=8, hermitian=1, rhs_kind=N.RHS_LEGACY),
+    # DIIS on r(v) = A (v - t): t(i) = 1/(i+1) by default, t = 1 for the legacy inputs
     "banded_diis_n50000": dict(n=50000, kind=N.KIND_DIIS, max_size_qspace=6),
+    "banded_diis_n200000_qcap3": dict(n=200000, kind=N.KIND_DIIS, max_size_qspace=3),
+    "banded_diis_n50000_legacy_target": dict(n=50000, kind=N.KIND_DIIS, max_size_qspace=6, rhs_kind=N.RHS_LEGACY),
 }
 
 

@@ -104,7 +104,11 @@ def test_linear_equations_through_the_flat_interface(ctx, options):
     check(lib, lib.ItsolvB200LinearEquationsInitialize(ctx.handle, n, nroots, C.byref(lo), C.byref(hi), rhs.data_ptr(), 0.0,
                                                       1e-8, HUGE, 1, 0, options))
     try:
-        params = rhs.clone()  # initial guess c = rhs (reference test_simplified.cpp:131-134)
+        # initial guess of the golden run: unit vectors on the smallest diagonal elements (what solve() generates with
+        # generate_initial_guess = true, reference IterativeSolverTemplate.h:337-350)
+        params = torch.zeros_like(rhs)
+        for k in range(nroots):
+            params[k, k] = 1.0
         action = torch.zeros_like(params)
         diag = torch.arange(1, n + 1, dtype=torch.float64, device="cuda")
         check(lib, lib.ItsolvB200SetDiagonals(diag.data_ptr()))
