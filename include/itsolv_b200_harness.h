@@ -158,6 +158,15 @@ int itsolv_harness_banded_apply(struct itsolv_ctx* ctx, int64_t n, int b, double
 /* Host subspace algebra entry points (restated helper, reference helper-implementation.h:318-543), exported for tests */
 int itsolv_host_eigenproblem(const double* matrix, const double* metric, size_t dimension, int hermitian,
                              double svd_threshold, double* eigenvalues, double* eigenvectors, size_t* nfound);
+/* svd_system (helper-implementation.h:263-296): values[k], vectors[k*ncols .. ] for the nfound entries of the returned list */
+int itsolv_host_svd_system(size_t nrows, size_t ncols, const double* m, double threshold, int hermitian,
+                           int reduce_to_rank, double* values, double* vectors, size_t* nfound);
+/* solve_LinearEquations (:553-617): solution is dimension x nroot column-major; eigenvalues (nroot) only with augmented_hessian > 0 */
+int itsolv_host_solve_linear_equations(const double* matrix, const double* metric, const double* rhs, size_t dimension,
+                                       size_t nroot, double augmented_hessian, double svd_threshold, double* solution,
+                                       double* eigenvalues);
+/* solve_DIIS (:619-669) */
+int itsolv_host_solve_diis(const double* matrix, size_t dimension, double svd_threshold, double* solution);
 
 #ifdef __cplusplus
 }

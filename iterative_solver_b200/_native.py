@@ -176,6 +176,11 @@ HARNESS_API = {
                                               c_double_p]),
     "itsolv_host_eigenproblem": (C.c_int, [c_double_p, c_double_p, C.c_size_t, C.c_int, C.c_double, c_double_p,
                                            c_double_p, C.POINTER(C.c_size_t)]),
+    "itsolv_host_svd_system": (C.c_int, [C.c_size_t, C.c_size_t, c_double_p, C.c_double, C.c_int, C.c_int, c_double_p,
+                                         c_double_p, C.POINTER(C.c_size_t)]),
+    "itsolv_host_solve_linear_equations": (C.c_int, [c_double_p, c_double_p, c_double_p, C.c_size_t, C.c_size_t,
+                                                     C.c_double, C.c_double, c_double_p, c_double_p]),
+    "itsolv_host_solve_diis": (C.c_int, [c_double_p, C.c_size_t, C.c_double, c_double_p]),
 }
 
 

@@ -104,7 +104,10 @@ def build_host(force: bool = False) -> str:
         list(ex.map(_run, jobs))
     blas = _openblas()
     if force or jobs or _stale(lib, objs):
-        _run([CXX, "-shared", "-o", lib] + objs +
+        # -Bsymbolic: the library's own references to the reference's template instantiations (eigenproblem, svd_system,
+        # ...) bind to ITS definitions even when another library with the same symbols (the oracle build of the
+        # reference, tests only) is loaded into the same process
+        _run([CXX, "-shared", "-Wl,-Bsymbolic", "-o", lib] + objs +
              ["-L" + LIBDIR, "-litsolv_b200", "-Wl,-rpath,$ORIGIN", blas, "-Wl,-rpath," + os.path.dirname(blas)])
     return lib
 

@@ -620,4 +620,43 @@ int itsolv_host_eigenproblem(const double* matrix, const double* metric, size_t 
   });
 }
 
+int itsolv_host_svd_system(size_t nrows, size_t ncols, const double* m, double threshold, int hermitian, int reduce_to_rank,
+                      double* values, double* vectors, size_t* nfound) {
+  return guarded([&] {
+    std::vector<double> copy(m, m + nrows * ncols);
+    auto svds = its::svd_system(nrows, ncols, molpro::linalg::array::Span<double>(copy.data(), copy.size()), threshold,
+                                hermitian != 0, reduce_to_rank != 0);
+    size_t k = 0;
+    for (const auto& s : svds) {
+      values[k] = s.value;
+      std::copy(s.v.begin(), s.v.end(), vectors + k * ncols);
+      ++k;
+    }
+    *nfound = k;
+  });
+}
+
+int itsolv_host_solve_linear_equations(const double* matrix, const double* metric, const double* rhs, size_t dimension,
+                                  size_t nroot, double augmented_hessian, double svd_threshold, double* solution,
+                                  double* eigenvalues) {
+  return guarded([&] {
+    std::vector<double> sol, eval;
+    its::solve_LinearEquations(sol, eval, std::vector<double>(matrix, matrix + dimension * dimension),
+                               std::vector<double>(metric, metric + dimension * dimension),
+                               std::vector<double>(rhs, rhs + dimension * nroot), dimension, nroot, augmented_hessian,
+                               svd_threshold, 0);
+    std::copy(sol.begin(), sol.end(), solution);
+    if (eigenvalues)
+      std::copy(eval.begin(), eval.end(), eigenvalues);
+  });
+}
+
+int itsolv_host_solve_diis(const double* matrix, size_t dimension, double svd_threshold, double* solution) {
+  return guarded([&] {
+    std::vector<double> sol;
+    its::solve_DIIS(sol, std::vector<double>(matrix, matrix + dimension * dimension), dimension, svd_threshold, 0);
+    std::copy(sol.begin(), sol.end(), solution);
+  });
+}
+
 } // extern "C"

@@ -11,6 +11,7 @@
 //   * the host dense algebra the solver templates call (eigenproblem, svd_system, ...): the reference implements it
 //     over Eigen/LAPACKE, neither present; iterative_solver_b200/host/helper_lapack.cpp restates it over LAPACK;
 //   * the synthetic banded operator (BandedProblemHost below), the CPU twin of the harness' CUDA operator.
+#include <cstdio>
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -228,6 +229,17 @@ PMap to_map(const int64_t* idx, const double* val, int nnz) {
 }
 } // namespace
 
+template <class F>
+static int ref_guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "oracle: %s\n", e.what());
+    return 1;
+  }
+}
+
 extern "C" {
 
 const char* ref_last_error() { return g_error.c_str(); }
@@ -386,6 +398,58 @@ void ref_sparse_gemm_outer(int nmap, int ndense, size_t n, const double* alpha, 
 }
 
 //! util::make_distribution_spread_remainder, reference array/util/Distribution.h:99-110; borders has nproc+1 entries
+// ---- the oracle's host algebra (oracle/helper_literal.cpp), for the fixtures of tests/test_host_algebra.py
+int ref_host_eigenproblem(const double* matrix, const double* metric, size_t dimension, int hermitian,
+                          double svd_threshold, double* eigenvalues, double* eigenvectors, size_t* nfound) {
+  return ref_guarded([&] {
+    std::vector<double> evec, eval;
+    std::vector<double> m(matrix, matrix + dimension * dimension), s(metric, metric + dimension * dimension);
+    its::eigenproblem(evec, eval, m, s, dimension, hermitian != 0, svd_threshold, 0, false);
+    *nfound = eval.size();
+    std::copy(eval.begin(), eval.end(), eigenvalues);
+    std::copy(evec.begin(), evec.end(), eigenvectors);
+  });
+}
+
+int ref_host_svd_system(size_t nrows, size_t ncols, const double* m, double threshold, int hermitian, int reduce_to_rank,
+                      double* values, double* vectors, size_t* nfound) {
+  return ref_guarded([&] {
+    std::vector<double> copy(m, m + nrows * ncols);
+    auto svds = its::svd_system(nrows, ncols, molpro::linalg::array::Span<double>(copy.data(), copy.size()), threshold,
+                                hermitian != 0, reduce_to_rank != 0);
+    size_t k = 0;
+    for (const auto& s : svds) {
+      values[k] = s.value;
+      std::copy(s.v.begin(), s.v.end(), vectors + k * ncols);
+      ++k;
+    }
+    *nfound = k;
+  });
+}
+
+int ref_host_solve_linear_equations(const double* matrix, const double* metric, const double* rhs, size_t dimension,
+                                  size_t nroot, double augmented_hessian, double svd_threshold, double* solution,
+                                  double* eigenvalues) {
+  return ref_guarded([&] {
+    std::vector<double> sol, eval;
+    its::solve_LinearEquations(sol, eval, std::vector<double>(matrix, matrix + dimension * dimension),
+                               std::vector<double>(metric, metric + dimension * dimension),
+                               std::vector<double>(rhs, rhs + dimension * nroot), dimension, nroot, augmented_hessian,
+                               svd_threshold, 0);
+    std::copy(sol.begin(), sol.end(), solution);
+    if (eigenvalues)
+      std::copy(eval.begin(), eval.end(), eigenvalues);
+  });
+}
+
+int ref_host_solve_diis(const double* matrix, size_t dimension, double svd_threshold, double* solution) {
+  return ref_guarded([&] {
+    std::vector<double> sol;
+    its::solve_DIIS(sol, std::vector<double>(matrix, matrix + dimension * dimension), dimension, svd_threshold, 0);
+    std::copy(sol.begin(), sol.end(), solution);
+  });
+}
+
 void ref_distribution(size_t n, int nproc, int64_t* borders) {
   auto d = la::util::make_distribution_spread_remainder<size_t>(n, nproc);
   for (int i = 0; i <= nproc; ++i)
