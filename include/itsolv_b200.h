@@ -87,6 +87,7 @@ int itsolv_comm_init(itsolv_ctx* ctx, int rank, int nranks, const void* id);
  * each) and every rank imports them. Without this step dot/gemm_inner fall back to ncclAllReduce + copy + sync. */
 #define ITSOLV_IPC_HANDLE_BYTES 64
 int itsolv_comm_p2p_export(itsolv_ctx* ctx, void* handle);
+int itsolv_comm_p2p_disable(itsolv_ctx* ctx); /* back to the ncclAllReduce path (all ranks must agree) */
 int itsolv_comm_p2p_import(itsolv_ctx* ctx, const void* handles /* nranks * ITSOLV_IPC_HANDLE_BYTES */);
 int itsolv_comm_rank(itsolv_ctx* ctx);
 int itsolv_comm_size(itsolv_ctx* ctx);

@@ -89,6 +89,7 @@ KERNEL_API = {
     "itsolv_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "itsolv_comm_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "itsolv_comm_p2p_import": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "itsolv_comm_p2p_disable": (C.c_int, [C.c_void_p]),
     "itsolv_comm_rank": (C.c_int, [C.c_void_p]),
     "itsolv_comm_size": (C.c_int, [C.c_void_p]),
     "itsolv_comm_barrier": (C.c_int, [C.c_void_p]),

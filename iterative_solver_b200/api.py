@@ -123,9 +123,13 @@ class Context:
         self._check(self.lib.itsolv_comm_p2p_export(self.handle, buf))
         return buf.raw
 
-    def p2p_import(self, handles: bytes):
+    def p2p_import(self, handles: bytes) -> bool:
+        """map the other ranks' exchange buffers; False (nothing left mapped) when a peer cannot be reached"""
         buf = C.create_string_buffer(handles, len(handles))
-        self._check(self.lib.itsolv_comm_p2p_import(self.handle, buf))
+        return self.lib.itsolv_comm_p2p_import(self.handle, buf) == 0
+
+    def p2p_disable(self):
+        self._check(self.lib.itsolv_comm_p2p_disable(self.handle))
 
     @property
     def rank(self) -> int:

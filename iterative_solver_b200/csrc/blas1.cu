@@ -243,6 +243,7 @@ using namespace itsolv;
 extern "C" {
 
 int itsolv_fill_f64(itsolv_ctx* ctx, double alpha, double* x, size_t n) {
+  ++ctx->write_epoch; // before any early return: every rank advances alike, also one with an empty shard
   ctx->counters.n_fill++;
   if (n == 0)
     return 0;
@@ -252,6 +253,7 @@ int itsolv_fill_f64(itsolv_ctx* ctx, double alpha, double* x, size_t n) {
 }
 
 int itsolv_scal_f64(itsolv_ctx* ctx, double alpha, double* x, size_t n) {
+  ++ctx->write_epoch; // before any early return: every rank advances alike, also one with an empty shard
   ctx->counters.n_scal++;
   if (n == 0)
     return 0;
@@ -261,6 +263,7 @@ int itsolv_scal_f64(itsolv_ctx* ctx, double alpha, double* x, size_t n) {
 }
 
 int itsolv_copy_f64(itsolv_ctx* ctx, double* dst, const double* src, size_t n) {
+  ++ctx->write_epoch; // before any early return: every rank advances alike, also one with an empty shard
   ctx->counters.n_copy++;
   if (n == 0 || dst == src)
     return 0;
@@ -270,6 +273,7 @@ int itsolv_copy_f64(itsolv_ctx* ctx, double* dst, const double* src, size_t n) {
 }
 
 int itsolv_axpy_f64(itsolv_ctx* ctx, double alpha, const double* x, double* y, size_t n) {
+  ++ctx->write_epoch; // before any early return: every rank advances alike, also one with an empty shard
   ctx->counters.n_axpy++;
   if (n == 0)
     return 0;
@@ -279,6 +283,7 @@ int itsolv_axpy_f64(itsolv_ctx* ctx, double alpha, const double* x, double* y, s
 }
 
 int itsolv_scal_batch_f64(itsolv_ctx* ctx, const double* alpha, double* const* x, int w, size_t n) {
+  ++ctx->write_epoch; // before any early return: every rank advances alike, also one with an empty shard
   ctx->counters.n_scal += w > 0 ? w : 0;
   if (n == 0 || w <= 0)
     return 0;
@@ -300,6 +305,7 @@ int itsolv_scal_batch_f64(itsolv_ctx* ctx, const double* alpha, double* const* x
 }
 
 int itsolv_axpy_batch_f64(itsolv_ctx* ctx, const double* alpha, const double* const* x, double* const* y, int w, size_t n) {
+  ++ctx->write_epoch; // before any early return: every rank advances alike, also one with an empty shard
   ctx->counters.n_axpy += w > 0 ? w : 0;
   if (n == 0 || w <= 0)
     return 0;
@@ -325,6 +331,7 @@ int itsolv_axpy_batch_f64(itsolv_ctx* ctx, const double* alpha, const double* co
 }
 
 int itsolv_mgs_step_f64(itsolv_ctx* ctx, double inv_norm, double* ri, const double* ov, double* const* rj, int m, size_t n) {
+  ++ctx->write_epoch; // before any early return: every rank advances alike, also one with an empty shard
   ctx->counters.n_scal += 1;
   ctx->counters.n_axpy += m > 0 ? m : 0;
   if (n == 0)
@@ -348,6 +355,7 @@ int itsolv_mgs_step_f64(itsolv_ctx* ctx, double inv_norm, double* ri, const doub
 }
 
 int itsolv_shift_f64(itsolv_ctx* ctx, double c, const double* x, double* out, size_t n) {
+  ++ctx->write_epoch; // before any early return: every rank advances alike, also one with an empty shard
   if (n == 0)
     return 0;
   LAUNCH_STREAM(shift_kernel, aligned16(x) && aligned16(out), c, x, out, n);
@@ -355,6 +363,7 @@ int itsolv_shift_f64(itsolv_ctx* ctx, double c, const double* x, double* out, si
 }
 
 int itsolv_precondition_f64(itsolv_ctx* ctx, double* const* r, int w, const double* diag, const double* shift, size_t n) {
+  ++ctx->write_epoch; // before any early return: every rank advances alike, also one with an empty shard
   ctx->counters.n_precondition++;
   if (n == 0 || w == 0)
     return 0;

@@ -84,6 +84,8 @@ struct Comm {
   char* d_exchange = nullptr; // [2][size][kPeerSlotDoubles] doubles, then [2][size] sequence words
   void* peer_base[kMaxPeers] = {};
   bool peers_ready = false;
+  unsigned int* d_error = nullptr;        // sticky failure word of the fused all-reduce (GiPeers::error)
+  unsigned long long timeout_ns = 600ull * 1000000000ull;
   size_t exchange_bytes() const { return 2 * size_t(size) * kPeerSlotDoubles * sizeof(double) + 2 * size_t(size) * 8 + 64; }
 };
 
@@ -104,6 +106,8 @@ bool comm_peers(itsolv_ctx* ctx, GiPeers* peers) {
   peers->nranks = c->size;
   peers->rank = c->rank;
   peers->slot_doubles = int(kPeerSlotDoubles);
+  peers->error = c->d_error;
+  peers->timeout_ns = c->timeout_ns;
   const size_t data_bytes = 2 * size_t(c->size) * kPeerSlotDoubles * sizeof(double);
   for (int r = 0; r < c->size; ++r) {
     peers->data[r] = reinterpret_cast<double*>(c->peer_base[r]);
@@ -119,6 +123,7 @@ void comm_destroy(itsolv_ctx* ctx) {
     if (ctx->comm->peers_ready && r != ctx->comm->rank && ctx->comm->peer_base[r])
       cudaIpcCloseMemHandle(ctx->comm->peer_base[r]);
   cudaFree(ctx->comm->d_exchange);
+  cudaFree(ctx->comm->d_error);
   NcclApi* api = nccl_api();
   if (api && ctx->comm->comm && api->CommDestroy)
     api->CommDestroy(ctx->comm->comm);
@@ -188,6 +193,10 @@ int itsolv_comm_p2p_export(itsolv_ctx* ctx, void* handle) {
   if (!c->d_exchange) {
     ITSOLV_CUDA(cudaMalloc(&c->d_exchange, c->exchange_bytes()));
     ITSOLV_CUDA(cudaMemset(c->d_exchange, 0, c->exchange_bytes()));
+    ITSOLV_CUDA(cudaMalloc(&c->d_error, 64));
+    ITSOLV_CUDA(cudaMemset(c->d_error, 0, 64));
+    if (const char* t = std::getenv("ITSOLV_P2P_TIMEOUT_S")) // seconds a rank waits for its peers; 0 = for ever
+      c->timeout_ns = static_cast<unsigned long long>(std::atof(t) * 1e9);
     ITSOLV_CUDA(cudaDeviceSynchronize());
   }
   cudaIpcMemHandle_t h;
@@ -207,9 +216,36 @@ int itsolv_comm_p2p_import(itsolv_ctx* ctx, const void* handles) {
     }
     cudaIpcMemHandle_t h;
     std::memcpy(&h, static_cast<const char*>(handles) + size_t(r) * ITSOLV_IPC_HANDLE_BYTES, sizeof(h));
-    ITSOLV_CUDA(cudaIpcOpenMemHandle(&c->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+    const cudaError_t err = cudaIpcOpenMemHandle(&c->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) {
+      // no peer access to rank r (another node, no NVLink/PCIe P2P): unmap what was mapped so far and leave the
+      // communicator on its ncclAllReduce path
+      cudaGetLastError();
+      for (int q = 0; q < r; ++q)
+        if (q != c->rank && c->peer_base[q])
+          cudaIpcCloseMemHandle(c->peer_base[q]);
+      for (int q = 0; q < kMaxPeers; ++q)
+        c->peer_base[q] = nullptr;
+      set_error(std::string("itsolv_comm_p2p_import: rank ") + std::to_string(r) + ": " + cudaGetErrorString(err));
+      return 1;
+    }
   }
   c->peers_ready = true;
+  return 0;
+}
+
+int itsolv_comm_p2p_disable(itsolv_ctx* ctx) {
+  Comm* c = ctx->comm;
+  if (!c)
+    return 0;
+  ITSOLV_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (c->peers_ready)
+    for (int r = 0; r < c->size && r < kMaxPeers; ++r)
+      if (r != c->rank && c->peer_base[r])
+        cudaIpcCloseMemHandle(c->peer_base[r]);
+  for (int q = 0; q < kMaxPeers; ++q)
+    c->peer_base[q] = nullptr;
+  c->peers_ready = false;
   return 0;
 }
 

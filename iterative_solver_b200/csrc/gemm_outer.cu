@@ -189,6 +189,7 @@ int itsolv_gemm_outer_scaled_f64(itsolv_ctx* ctx, const double* alpha, int k, in
 static int gemm_outer_impl(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* xx,
                            double* const* yy, size_t n, int beta_zero, const double* yscale) {
   ctx->counters.n_gemm_outer++;
+  ++ctx->write_epoch; // before any early return: every rank advances alike, also one with an empty shard
   if (m <= 0)
     return 0;
   if (k <= 0) {

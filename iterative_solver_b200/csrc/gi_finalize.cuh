@@ -22,6 +22,10 @@ struct GiPeers {
   unsigned long long* flags[kMaxPeers]; // rank r's sequence words: [2][nranks]
   int nranks, rank;
   int slot_doubles;
+  // A rank that gave up waiting sets *error (device memory of THIS rank) and never clears it: every later launch
+  // reports the failure instead of exchanging, so no result computed from a half-finished exchange is ever delivered.
+  unsigned int* error;
+  unsigned long long timeout_ns; // 0: wait for ever, as MPI_Allreduce does (ITSOLV_P2P_TIMEOUT_S, default 600 s)
 };
 
 struct GiFinalize {
@@ -54,6 +58,12 @@ __device__ __forceinline__ void gi_chain(const GiFinalize& f) {
     f.chain_out[1 + t] = ok ? -__ddiv_rn(row[t], norm) : 0.0;
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ unsigned long long ld_volatile_sys(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -62,13 +72,17 @@ __device__ __forceinline__ unsigned long long ld_volatile_sys(const unsigned lon
 
 /*!
  * Executed by ONE CTA per rank: `local` (km doubles, visible to this CTA) -> all peers, wait, sum in rank order -> out.
- * Returns false on timeout (a peer never arrived); the caller reports it through the host word.
+ * Returns false when a peer did not arrive within the time limit, or when an earlier call of this rank already failed
+ * (sticky); the caller reports it through the host word. The limit only exists so that a dead peer turns into an error
+ * instead of a hung GPU: skew between ranks (an unbalanced user callback, I/O) is waited for.
  */
 __device__ __forceinline__ bool gi_peer_allreduce(const GiPeers& pr, const double* local, int km, unsigned long long seq,
                                                   double* out, double* dev_copy = nullptr) {
   const int tid = threadIdx.x;
   const int parity = int(seq & 1ull);
   const size_t slot = (size_t(parity) * pr.nranks + pr.rank) * pr.slot_doubles;
+  if (*reinterpret_cast<volatile unsigned int*>(pr.error) != 0u)
+    return false; // uniform over the CTA: the word is only written by this CTA's predecessors
   for (int r = 0; r < pr.nranks; ++r)
     for (int e = tid; e < km; e += blockDim.x)
       pr.data[r][slot + e] = local[e];
@@ -82,9 +96,10 @@ __device__ __forceinline__ bool gi_peer_allreduce(const GiPeers& pr, const doubl
   __syncthreads();
   if (tid < pr.nranks) {
     const unsigned long long* mine = pr.flags[pr.rank] + size_t(parity) * pr.nranks + tid;
-    const long long t0 = clock64();
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int spins = 0;
     while (ld_volatile_sys(mine) != seq) {
-      if (clock64() - t0 > 8000000000ll) { // ~4 s: a peer is gone
+      if (pr.timeout_ns != 0ull && (++spins & 0x3FFu) == 0u && global_timer_ns() - t0 > pr.timeout_ns) {
         s_ok = 0;
         break;
       }
@@ -92,8 +107,11 @@ __device__ __forceinline__ bool gi_peer_allreduce(const GiPeers& pr, const doubl
   }
   __threadfence_system();
   __syncthreads();
-  if (!s_ok)
+  if (!s_ok) {
+    if (tid == 0)
+      *reinterpret_cast<volatile unsigned int*>(pr.error) = 1u;
     return false;
+  }
   const double* base = pr.data[pr.rank] + size_t(parity) * pr.nranks * pr.slot_doubles;
   for (int e = tid; e < km; e += blockDim.x) {
     double sum = 0.0;
@@ -140,8 +158,16 @@ __device__ __forceinline__ void gi_finalize(const GiFinalize& f, int km, int* s_
     __syncthreads();
   }
   if (tid == 0) {
-    if (f.chain_out)
-      gi_chain(f);
+    if (f.chain_out) {
+      if (ok) {
+        gi_chain(f);
+      } else { // no sums: the next step of the chain must leave the vectors alone
+        f.chain_out[0] = 1.0;
+        f.chain_out[1] = 1.0;
+        for (int t = 1; t < f.chain_count; ++t)
+          f.chain_out[1 + t] = 0.0;
+      }
+    }
     *f.counter = 0u;
     if (f.flag) {
       __threadfence_system();

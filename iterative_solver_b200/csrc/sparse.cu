@@ -136,6 +136,7 @@ int itsolv_sparse_copy_f64(itsolv_ctx* ctx, double* x, size_t n, size_t global_o
   if (itsolv_fill_f64(ctx, 0.0, x, n))
     return 1;
   ctx->counters.n_fill--;
+  ++ctx->write_epoch; // before any early return: every rank advances alike
   if (nnz <= 0 || n == 0)
     return 0;
   const int32_t ptr[2] = {0, nnz};
@@ -200,6 +201,7 @@ int itsolv_sparse_gemm_outer_f64(itsolv_ctx* ctx, const double* alpha, int nmap,
                                  size_t global_offset) {
   ++ctx->write_epoch;
   ctx->counters.n_sparse++;
+  ++ctx->write_epoch; // before any early return: every rank advances alike
   if (nmap <= 0 || ndense <= 0 || n == 0)
     return 0;
   // the parallel kernel needs every (index) to be touched by one entry only

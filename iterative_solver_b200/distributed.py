@@ -36,11 +36,23 @@ def attach_communicator(ctx: Context, peer_memory: bool = True) -> None:
     uid = broadcast_bytes(uid, 128, 0)
     ctx.init_comm(dist.get_rank(), dist.get_world_size(), uid)
     if peer_memory and dist.get_world_size() <= 8 and dist.get_backend() == "nccl":
-        # the fused all-reduce of the Gram kernels writes into the other ranks' exchange buffers over NVLink:
-        # gather every rank's CUDA IPC handle (64 bytes) and map them
+        # the fused all-reduce of the Gram kernels writes into the other ranks' exchange buffers over NVLink. That needs
+        # all ranks on one host with peer access between their GPUs: compare host names first, then gather every rank's
+        # CUDA IPC handle (64 bytes) and map them; if any rank fails, every rank unmaps and the communicator stays on
+        # its ncclAllReduce path.
+        import socket
         import torch
+        world = dist.get_world_size()
+        names = [None] * world
+        dist.all_gather_object(names, socket.gethostname())
+        if len(set(names)) != 1:
+            return
         mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).cuda()
-        allh = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+        allh = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allh, mine)
-        ctx.p2p_import(b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh))
+        ok = ctx.p2p_import(b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh))
+        status = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(status, op=dist.ReduceOp.MIN)
+        if int(status.item()) == 0:
+            ctx.p2p_disable()
         dist.barrier()

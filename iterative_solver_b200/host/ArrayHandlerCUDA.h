@@ -223,8 +223,13 @@ public:
   static constexpr size_t max_mgs_step_dots = 16;
   //! can the R-R Gram-Schmidt of these vectors run as one chain of launches (itsolv_mgs_chain_f64)?
   bool mgs_chain_supported(const VecRef<AL>& rr) const {
-    return !rr.empty() &&
-           itsolv_mgs_chain_supported(rr[0].get().context(), int(rr.size()), rr[0].get().local_size()) != 0;
+    // decided from rank-independent inputs only (global length, number of ranks, options): every rank must take the
+    // same branch, also one whose shard is empty
+    if (rr.empty())
+      return false;
+    const auto& first = rr[0].get();
+    const size_t nranks = size_t(itsolv_comm_size(first.context()));
+    return first.size() >= nranks && itsolv_mgs_chain_supported(first.context(), int(rr.size()), first.size() / nranks) != 0;
   }
   //! the chain; returns the rows of inner products in the layout of include/itsolv_b200.h
   std::vector<double> mgs_chain(const VecRef<AL>& rr, double thresh) {

@@ -651,31 +651,17 @@ protected:
       for (size_t x = 0; x < nX; ++x)
         ov(nX + i, x) = ov(x, nX + i) = g0(i, x);
     }
-    auto redundant = det::redundant_parameters(ov, nX, nN, this->propose_rspace_svd_thresh, logger);
-    // keep the rows of the overlap block that belong to the surviving vectors
-    std::vector<size_t> kept(nN);
-    for (size_t i = 0; i < nN; ++i)
-      kept[i] = i;
-    {
-      auto sorted = redundant;
-      std::sort(sorted.begin(), sorted.end(), std::greater<int>());
-      for (auto i : sorted)
-        kept.erase(kept.begin() + i);
-    }
-    its::util::delete_parameters(redundant, wresidual);
-    nN = wresidual.size();
-    std::vector<double> kept_factor(nN);
-    for (size_t j = 0; j < nN; ++j)
-      kept_factor[j] = factor[kept[j]];
-
-    // projection against P, Q, D: sequential coefficients by forward substitution, applied in one expansion that also
-    // multiplies the normalisation factor in
+    // Projection against P, Q, D: sequential coefficients by forward substitution, applied in one expansion that also
+    // multiplies the normalisation factor in. The coefficients of a vector depend on that vector alone, so the expansion is
+    // launched for ALL new vectors BEFORE the redundancy test: the host's SVD below then runs while the kernel does
+    // (SURVEY.md section 8 f2). A vector the test drops is discarded after having been projected, which changes nothing
+    // for the others (each column of the expansion is its own chain of operations).
     bool scaled = nP > 0;
     if (nN > 0 && nX > 0) {
       Matrix<double> c({nX, nN});
       for (size_t j = 0; j < nN; ++j)
         for (size_t i = 0; i < nX; ++i) {
-          double t = g0(kept[j], i);
+          double t = g0(j, i);
           for (size_t l = 0; l < i; ++l)
             t += c(l, j) * S(l, i);
           c(i, j) = -t / std::abs(S(i, i));
@@ -698,12 +684,15 @@ protected:
         if (scaled)
           m_dense->gemm_outer(cd, xdense, wresidual);
         else
-          m_dense->gemm_outer_scaled(cd, xdense, wresidual, kept_factor);
+          m_dense->gemm_outer_scaled(cd, xdense, wresidual, factor);
         scaled = true;
       }
     }
     if (!scaled && nN > 0)
-      m_dense->scal_batch(kept_factor, wresidual);
+      m_dense->scal_batch(factor, wresidual);
+    auto redundant = det::redundant_parameters(ov, nX, nN, this->propose_rspace_svd_thresh, logger);
+    its::util::delete_parameters(redundant, wresidual);
+    nN = wresidual.size();
     // R-R modified Gram-Schmidt: one pass per pivot, which scales the pivot, updates the later vectors and returns the
     // norm and overlaps of the next pivot together with <r_i, r_i> of the finished one
     std::vector<int> null_params;
