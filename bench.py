@@ -30,6 +30,7 @@ N_PER_GPU = 10_000_000
 NROOTS = 4
 HALF_BANDWIDTH = 4
 EPS = 1e-3
+NOMINAL_HBM_GBS = 8000.0  # the north star's "B200's ~8 TB/s"; the measured copy rate is MEASURED_PEAKS.json
 METRIC = "davidson_iterations_per_s"
 UNIT = "iterations/s"
 
@@ -63,27 +64,60 @@ def ncu_traffic(family):
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons sampled during the timed region"""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in-process every few milliseconds (the timed
+    region of the default run is a fraction of a second), nvidia-smi as the fallback"""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         self.index = index
-        self.samples = []
+        self.samples = []  # (sm_mhz, sm_max_mhz, [reason flags])
         self.stop_flag = threading.Event()
         self.thread = threading.Thread(target=self.run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if visible:
+                ids = [v.strip() for v in visible.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self.source = "nvidia-smi"
+
+    def sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(get(self.handle))
+        bits = [n.nvmlClocksThrottleReasonHwSlowdown, n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                n.nvmlClocksThrottleReasonSwThermalSlowdown, n.nvmlClocksThrottleReasonSwPowerCap]
+        self.samples.append((sm, self.sm_max, [bool(mask & b) for b in bits]))
+
+    def sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [p.strip() for p in out.strip().split(",")]
+        if len(parts) >= 6:
+            self.samples.append((float(parts[0]), float(parts[1]), [p.lower().startswith("active") for p in parts[2:6]]))
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                if self.nvml:
+                    self.sample_nvml()
+                else:
+                    self.sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.004 if self.nvml else 0.2)
 
     def __enter__(self):
         self.thread.start()
@@ -95,12 +129,11 @@ class ClockSampler:
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (nvml and nvidia-smi unavailable)"]}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2][i] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": reasons, "samples": len(sm),
+                "source": self.source}
 
 
 def reference_arm(args):
@@ -116,15 +149,12 @@ def reference_arm(args):
     o = itsolv_oracle_lib.load()
     if o.ref is None:
         raise SystemExit("oracle/_ref/libitsolv_ref.so is missing: run __graft_entry__.build() where /root/reference exists")
-    # bounded sample: the same solve at the largest n (<= the full 1e7) for which steps+warmup solves end in ~4 minutes;
-    # the path streams vectors (time is linear in n), so the sample's rate is scaled by n_sample / n_full
-    per_row_seconds = 2.4e-6  # measured ~2.2 us per row per solve on this class of host
-    budget = 220.0
+    # Every step is one complete solve of the full workload (n = 1e7 rows, 4 roots), as many steps and warm-up steps as
+    # asked for: ~14 s each on this class of host, so the default driver run (20 + 5) ends in about six minutes.
+    # At N > 1 the GPU arm is weak-scaled (N shards of 1e7 rows, value = N x iterations / time); the path is linear in n
+    # and single-threaded, so on N x 1e7 rows the reference makes 1/N of the iterations per second and its value in the
+    # same unit is the one measured here.
     n_sample = args.n
-    for cand in (args.n, args.n // 2, args.n // 5, args.n // 10, args.n // 20, args.n // 50):
-        n_sample = cand
-        if (args.steps + args.warmup) * cand * per_row_seconds <= budget:
-            break
     spec = H.make_spec(n_sample, kind=N.KIND_DAVIDSON, nroots=args.roots, hermitian=1, half_bandwidth=HALF_BANDWIDTH,
                        eps=EPS)
     for _ in range(args.warmup):
@@ -135,15 +165,17 @@ def reference_arm(args):
         res, _ = o.ref.solve(spec)
         seconds += time.perf_counter() - t0
         iterations += res.iterations
-    scale = n_sample / args.n
-    value = iterations / seconds * scale
-    sample = (f"{args.steps} solve(s) of the same operator at n={n_sample} "
-              f"({'the full workload' if n_sample == args.n else 'rate scaled by n_sample/n, the path is linear in n'})")
+    scale = 1.0
+    value = iterations / seconds
+    sample = (f"{args.steps} complete solve(s) of the full workload (n={n_sample} rows, {args.roots} roots) after "
+              f"{args.warmup} warm-up solve(s); single-threaded path, host has {os.cpu_count()} logical cores")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": seconds / args.steps * 1e3 / scale, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.n, args.roots), "n_per_gpu": args.n, "nroots": args.roots},
+        "config": {"workload": workload_name(args.n, args.roots), "n_per_gpu": args.n, "nroots": args.roots,
+                   "n_global": args.n * args.gpus, "sharding": f"rows/{args.gpus}" if args.gpus > 1 else "none",
+                   "value_unit_note": "iterations/s x number of 1e7-row shards (weak scaling)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "iterations_per_solve": iterations / args.steps,
@@ -165,6 +197,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-path", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the comparison with the reference at 1e6 rows per GPU")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip BASELINE.json's other configurations at their stated sizes (the `configs` key)")
     ap.add_argument("--min-warmup", type=int, default=3, help="profiling runs only: allow fewer than 3 warm-up steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -194,6 +229,12 @@ def main():
                        eps=EPS, explicit_csr=1, fused=fused)
     borders = pkg.distribution(n_global, world)
     lo, hi = int(borders[rank]), int(borders[rank + 1])
+
+    # ---- parity with the reference, outside the timed region: the same solver path on 1e6 rows per GPU (sharded over all
+    # ranks) against the reference's own std::vector path on the same GLOBAL problem, run on rank 0's host cores
+    parity = None
+    if not args.no_parity:
+        parity = parity_with_reference(ctx, rank, world, args.roots, fused)
 
     # ---- device-resident leg: operator (stored CSR) in HBM before the timed region starts
     problem = H.Problem(ctx, spec)
@@ -311,6 +352,11 @@ def main():
                              f"std::vector/ArrayHandlerIterable path, {dt:.1f} s; host has {os.cpu_count()} logical cores, "
                              f"the path is single-threaded", "parity_with_gpu_run": bool(same)}
 
+    # ---- BASELINE.json's other configurations at their stated sizes, gated (tools/config_runs.py); which ones depends on N
+    configs = None
+    if not args.no_configs and os.environ.get("ITSOLV_BENCH_CONFIGS", "1") != "0":
+        configs = run_configs(ctx, rank, world)
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         # kernel families of the subspace path (itsolv_counters): algorithmic bytes, event time and calls of each, summed
@@ -342,7 +388,8 @@ def main():
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(sums[4]),
             "roofline": {"bound": "hbm", "kernel": dom["kernel"], "family": dominant,
                          "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak if peak else None,
-                         "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src, "peak_nominal": NOMINAL_HBM_GBS,
+                         "frac_nominal": dom_gbs / NOMINAL_HBM_GBS, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": dom["bytes"] / max(dom["calls"], 1.0),
                          "launch_share_of_handler_time": dom["secs"] / maxs[0] if maxs[0] else None,
                          "families": {k: {"gbs": agg_gbs(v["bytes"] / world, v["secs"]),
@@ -352,16 +399,83 @@ def main():
             "cpu_baseline": cpu,
             "subspace_update": {"gbs_per_gpu": agg_gbs(sums[0] / world, maxs[0]),
                                 "frac_of_measured_hbm": agg_gbs(sums[0] / world, maxs[0]) / peak,
+                                "frac_of_nominal_hbm": agg_gbs(sums[0] / world, maxs[0]) / NOMINAL_HBM_GBS,
                                 "gemm_outer_gbs": agg_gbs(sums[2] / world, maxs[2]),
                                 "streaming_gbs": agg_gbs(sums[3] / world, maxs[3]),
                                 "device_seconds_per_step": maxs[0] / args.steps},
             "iterations_per_solve": iterations / args.steps, "converged": int(converged), "eigenvalues": eig,
             "driver_path": args.path, "other_driver_path": other,
+            "parity_with_reference": parity, "configs": configs,
         }
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_with_reference(ctx, rank, world, nroots, fused, rows_per_gpu=1_000_000):
+    """The bench's solver path on rows_per_gpu x world rows, sharded over all ranks, against the reference's CPU path on
+    the same global problem (rank 0): iteration count, convergence, eigenvalues to 1e-10."""
+    from iterative_solver_b200 import _native as N
+    from iterative_solver_b200 import harness as H
+    n_global = rows_per_gpu * world
+    kw = dict(kind=N.KIND_DAVIDSON, nroots=nroots, hermitian=1, half_bandwidth=HALF_BANDWIDTH, eps=EPS)
+    res, _ = H.solve(ctx, H.make_spec(n_global, fused=fused, explicit_csr=1, **kw))
+    out = {"n_global": n_global, "rows_per_gpu": rows_per_gpu, "iterations": int(res.iterations),
+           "converged": int(res.converged), "reference": None, "ok": None}
+    if rank == 0:
+        import itsolv_oracle_lib
+        o = itsolv_oracle_lib.load()
+        if o.ref is not None:
+            t0 = time.perf_counter()
+            rres, _ = o.ref.solve(H.make_spec(n_global, **kw))
+            dev = max(abs(res.eigenvalues[i] / rres.eigenvalues[i] - 1) for i in range(nroots))
+            out["reference"] = {"iterations": int(rres.iterations), "converged": int(rres.converged),
+                                "seconds": time.perf_counter() - t0, "kind": "oracle/_ref (the reference's own templates)"}
+            out["eigenvalues_max_rel_dev"] = dev
+            out["ok"] = bool(rres.iterations == res.iterations and rres.converged == res.converged and dev <= 1e-10)
+    return out
+
+
+def config_plan(world):
+    """(name, overrides) of the configurations run at `world` GPUs. C4's stated shape (16 roots, 8 buffers, Q capped at 8)
+    needs 8 GPUs for n = 2e9; on 4 and 2 GPUs the largest (roots, buffers, Q cap) whose high-water mark fits is run instead
+    (profiles/memory_table_r02.jsonl)."""
+    if world == 1:
+        return [("c3", {})]
+    if world == 2:
+        return [("c3", {}), ("c4", dict(nroots=2, nbuffers=2, max_size_qspace=2)), ("c5a", {}), ("c5b", {})]
+    if world == 4:
+        return [("c4", dict(nroots=4, nbuffers=4, max_size_qspace=4)), ("c5a", {}), ("c5b", {})]
+    return [("c4", {}), ("c5a", {}), ("c5b", {})]
+
+
+def run_configs(ctx, rank, world):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import config_runs as CR
+    import iterative_solver_b200 as pkg
+    records = []
+    for name, ov in config_plan(world):
+        try:
+            # dry run at 2e5 rows: the high-water mark in vectors does not depend on n
+            dry = CR.run(ctx, name, rank, world, n=200_000, overrides=ov, verify=True, reference=False, warm=False)
+            n_full = CR.CONFIGS[name]["n"]
+            nloc = int(pkg.distribution(n_full, world)[1])
+            need = dry["peak_vectors"] * 8.0 * nloc
+            ctx.mem_trim()
+            free_min = float(ctx.allreduce_host(np.array([-float(ctx.mem_info()[0])]), op_max=True)[0]) * -1.0
+            if need + 6e9 > free_min:
+                records.append({"config": name, "overrides": ov, "skipped": "does not fit",
+                                "peak_vectors": dry["peak_vectors"], "need_gb_per_gpu": need / 1e9,
+                                "free_gb_per_gpu": free_min / 1e9})
+                continue
+            rec = CR.run(ctx, name, rank, world, overrides=ov)
+            rec["overrides"] = ov
+            rec["need_gb_per_gpu_predicted"] = need / 1e9
+            records.append(rec)
+        except Exception as e:  # a failed configuration must not take the bench line with it
+            records.append({"config": name, "overrides": ov, "error": repr(e)[:300]})
+    return records
 
 
 def agg_gbs(nbytes, seconds):

@@ -166,6 +166,19 @@ int itsolv_davidson_residual_f64(itsolv_ctx* ctx, const double* coef, int k, int
                                  const double* const* a, const double* lambda, const double* diag, const double* shift,
                                  double* const* out_x, double* const* out_r, size_t n, double* norm2,
                                  double* norm2_out);
+/*
+ * The same pass for the other residual forms of the reference's solvers:
+ *   mode 0   r_j = sum_i c_ij a_i - lambda_j x_j                       (LinearEigensystemDavidson.h:186-192; as above)
+ *   mode 1   r_j = (sum_i c_ij a_i - rhs_j) * rscale_j                 (LinearEquationsDavidson.h:173-184: axpy(-1, rhs) then
+ *                                                                        scal(1/|rhs|), each operation rounded)
+ * accumulate != 0: the expansions start from the present contents of out_x[j] / out_r[j] instead of zero - the P-space
+ * parts (IterativeSolverTemplate.h:44-64 puts them first; the caller's apply_p contribution, :210-211) - out_x is then
+ * required. With a diagonal the residuals are preconditioned as above (shift = 0 for linear equations).
+ */
+int itsolv_subspace_residual_f64(itsolv_ctx* ctx, int mode, int accumulate, const double* coef, int k, int m,
+                                 const double* const* q, const double* const* a, const double* lambda,
+                                 const double* const* rhs, const double* rscale, const double* diag, const double* shift,
+                                 double* const* out_x, double* const* out_r, size_t n, double* norm2, double* norm2_out);
 
 /* ---- select / select_max_dot (reference array/util/select.h:28-55, ArrayHandler.h:212,222): the nsel entries that are
  * largest under the reference's (key, index) pair ordering, key = max ? v : -v (|v| when ignore_sign); for

@@ -119,6 +119,9 @@ KERNEL_API = {
     "itsolv_davidson_residual_f64": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_int, c_void_pp, c_void_pp, c_double_p,
                                                C.c_void_p, c_double_p, c_void_pp, c_void_pp, C.c_size_t, c_double_p,
                                                c_double_p]),
+    "itsolv_subspace_residual_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int, C.c_int, c_void_pp,
+                                               c_void_pp, c_double_p, c_void_pp, c_double_p, C.c_void_p, c_double_p,
+                                               c_void_pp, c_void_pp, C.c_size_t, c_double_p, c_double_p]),
     "itsolv_select_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
                                     C.c_int, c_int64_p, c_double_p, C.POINTER(C.c_int)]),
     "itsolv_select_merge": (C.c_int, [c_int64_p, c_double_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, c_int64_p,

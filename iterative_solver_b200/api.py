@@ -79,6 +79,15 @@ class Context:
         self._check(self.lib.itsolv_mem_usage(self.handle, C.byref(live), C.byref(peak), int(reset_peak)))
         return live.value, peak.value
 
+    def alloc(self, n: int) -> int:
+        """n doubles from the context's stream-ordered pool (where the solver's vectors live); returns the device address"""
+        p = C.c_void_p()
+        self._check(self.lib.itsolv_alloc(self.handle, int(n), C.byref(p)))
+        return int(p.value)
+
+    def free(self, address: int):
+        self._check(self.lib.itsolv_free(self.handle, C.c_void_p(address)))
+
     def mem_info(self):
         """(free, total) bytes of the device as the driver sees them"""
         free, total = C.c_size_t(), C.c_size_t()
@@ -237,6 +246,25 @@ class Context:
             self.handle, _dbl(c), k, m, _ptr_array(q), _ptr_array(a), _dbl(l), _ptr(diag) if diag is not None else None,
             _dbl(l), _ptr_array(out_x) if out_x is not None else None, _ptr_array(out_r), out_r[0].numel(), _dbl(n2),
             _dbl(n2w)))
+        return n2, n2w
+
+    def subspace_residual(self, coef: np.ndarray, q: Sequence, a: Sequence, out_r: Sequence, lam=None, rhs=None,
+                          rscale=None, diag=None, shift=None, out_x: Sequence | None = None, accumulate: bool = False):
+        """itsolv_subspace_residual_f64. Eigenproblem form with `lam` (r = sum c a - lam x), linear-equations form with
+        `rhs` and `rscale` (r = (sum c a - rhs) * rscale); `accumulate`: continue from the contents of out_x / out_r.
+        Returns (<r_j, r_j> before preconditioning, <out_r_j, out_r_j>)."""
+        k, m = len(q), len(out_r)
+        mode = 0 if rhs is None else 1
+        c = np.ascontiguousarray(coef, dtype=np.float64).reshape(k, m)
+        l = np.ascontiguousarray(lam, dtype=np.float64) if lam is not None else None
+        s = np.ascontiguousarray(rscale, dtype=np.float64) if rscale is not None else None
+        sh = np.ascontiguousarray(shift if shift is not None else (lam if lam is not None else np.zeros(m)), dtype=np.float64)
+        n2, n2w = np.zeros(m), np.zeros(m)
+        self._check(self.lib.itsolv_subspace_residual_f64(
+            self.handle, mode, int(accumulate), _dbl(c), k, m, _ptr_array(q), _ptr_array(a), _dbl(l) if l is not None else None,
+            _ptr_array(rhs) if rhs is not None else None, _dbl(s) if s is not None else None,
+            _ptr(diag) if diag is not None else None, _dbl(sh), _ptr_array(out_x) if out_x is not None else None,
+            _ptr_array(out_r), out_r[0].numel(), _dbl(n2), _dbl(n2w)))
         return n2, n2w
 
     def select(self, x, nsel: int, max: bool = False, ignore_sign: bool = False, y=None, global_offset: int = 0):

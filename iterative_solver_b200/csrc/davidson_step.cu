@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "gi_finalize.cuh"
+#include "gi_pipeline.cuh"
 
 namespace itsolv {
 
@@ -41,10 +42,15 @@ struct DsParams {
   double shift[kDsMaxRoots];
   const double* coef; // device, k x ld row-major, zero padded columns
   const double* diag; // null: residuals are written as they are
+  // linear equations (mode 1): r_j = (sum_i c_ij a_i - rhs_j) * rscale_j instead of r_j = sum_i c_ij a_i - lambda_j x_j
+  const double* rhs[kDsMaxRoots];
+  double rscale[kDsMaxRoots];
   GiFinalize fin;
   size_t n;
   int k, m, ld;
   int write_x;
+  int mode;       // 0: eigenproblem residual, 1: linear equations residual
+  int accumulate; // the expansions start from the present contents of out_x / out_r (P-space parts) instead of zero
 };
 
 template <class RV>
@@ -58,6 +64,11 @@ struct DsOps<double2> {
   }
   static __device__ __forceinline__ double2 residual(const double2& r, double neg_lambda, const double2& x) {
     return make_double2(__dadd_rn(r.x, __dmul_rn(neg_lambda, x.x)), __dadd_rn(r.y, __dmul_rn(neg_lambda, x.y)));
+  }
+  //! (r - b) * s, every operation rounded: axpy(-1, rhs, r) then scal(s, r) of the reference
+  //! (LinearEquationsDavidson.h:173-184)
+  static __device__ __forceinline__ double2 residual_lineq(const double2& r, const double2& b, double s) {
+    return make_double2(__dmul_rn(__dadd_rn(r.x, -b.x), s), __dmul_rn(__dadd_rn(r.y, -b.y), s));
   }
   static __device__ __forceinline__ void square_to(double& acc, const double2& r) {
     acc = fma(r.x, r.x, acc);
@@ -74,6 +85,9 @@ struct DsOps<double> {
   static __device__ __forceinline__ void fma_to(double& acc, double c, const double& v) { acc = fma(c, v, acc); }
   static __device__ __forceinline__ double residual(const double& r, double neg_lambda, const double& x) {
     return __dadd_rn(r, __dmul_rn(neg_lambda, x));
+  }
+  static __device__ __forceinline__ double residual_lineq(const double& r, const double& b, double s) {
+    return __dmul_rn(__dadd_rn(r, -b), s);
   }
   static __device__ __forceinline__ void square_to(double& acc, const double& r) { acc = fma(r, r, acc); }
   static __device__ __forceinline__ double precondition(const double& r, const double& d, double shift) {
@@ -118,6 +132,14 @@ struct DsNorms<MJ, true> {
   __device__ __forceinline__ double get(int b) const { return col[b * kDsThreads]; }
 };
 
+//! residual of root j at row r (units of RV) from the two expansions
+template <class RV>
+__device__ __forceinline__ RV ds_residual(const DsParams& p, int j, size_t r, const RV& ar, const RV& ax) {
+  if (p.mode == 1)
+    return DsOps<RV>::residual_lineq(ar, reinterpret_cast<const RV*>(p.rhs[j])[r], p.rscale[j]);
+  return DsOps<RV>::residual(ar, -p.lambda[j], ax);
+}
+
 //! one thread, rows `r` (in units of RV): both expansions, residual, square, preconditioner
 template <int MJ, class RV, class Norms>
 __device__ __forceinline__ void ds_rows(const DsParams& p, const double* __restrict__ sc, size_t r, Norms& nrm) {
@@ -127,6 +149,10 @@ __device__ __forceinline__ void ds_rows(const DsParams& p, const double* __restr
   for (int b = 0; b < MJ; ++b) {
     ax[b] = Ops::zero();
     ar[b] = Ops::zero();
+    if (p.accumulate && b < p.m) {
+      ax[b] = reinterpret_cast<const RV*>(p.out_x[b])[r];
+      ar[b] = reinterpret_cast<const RV*>(p.out_r[b])[r];
+    }
   }
   // subspace vectors per trip: 2U independent loads in flight per thread
   constexpr int U = (sizeof(RV) == sizeof(double) || MJ <= 4) ? 4 : 2;
@@ -168,7 +194,7 @@ __device__ __forceinline__ void ds_rows(const DsParams& p, const double* __restr
     if (b < p.m) {
       if (p.write_x)
         reinterpret_cast<RV*>(p.out_x[b])[r] = ax[b];
-      RV res = Ops::residual(ar[b], -p.lambda[b], ax[b]);
+      RV res = ds_residual<RV>(p, b, r, ar[b], ax[b]);
       nrm.add(b, res);
       if (p.diag) {
         res = Ops::precondition(res, d, p.shift[b]);
@@ -317,6 +343,10 @@ __global__ void __launch_bounds__(kDsThreads, 2) davidson_residual_ring_kernel(c
       for (int b = 0; b < MJ; ++b) {
         ax[b] = Ops::zero();
         ar[b] = Ops::zero();
+        if (p.accumulate && b < p.m) {
+          ax[b] = reinterpret_cast<const double2*>(p.out_x[b])[cr];
+          ar[b] = reinterpret_cast<const double2*>(p.out_r[b])[cr];
+        }
       }
       if (p.diag)
         dg = st[2 * U * kDsThreads];
@@ -340,7 +370,7 @@ __global__ void __launch_bounds__(kDsThreads, 2) davidson_residual_ring_kernel(c
         if (b < p.m) {
           if (p.write_x)
             reinterpret_cast<double2*>(p.out_x[b])[cr] = ax[b];
-          double2 res = Ops::residual(ar[b], -p.lambda[b], ax[b]);
+          double2 res = ds_residual<double2>(p, b, cr, ar[b], ax[b]);
           nrm.add(b, res);
           if (p.diag) {
             res = Ops::precondition(res, dg, p.shift[b]);
@@ -360,6 +390,239 @@ __global__ void __launch_bounds__(kDsThreads, 2) davidson_residual_ring_kernel(c
   if ((p.n & 1) && tid == 0)
     ds_rows<MJ, double>(p, sc, p.n - 1, nrm);
   ds_finish<MJ>(p, nrm);
+}
+
+
+// ---- 9..16 roots: shared-memory tiles moved by TMA, consumed by two root groups -----------------------------------
+// With 16 roots the 2 x 16 running sums of one row pair (64 registers for a double2 lane) leave no room to keep enough
+// loads in flight from registers: the kernel above falls back to one row per thread and reaches half the copy rate. Here
+// the CTA's producer warps stream tiles of kTileRows rows of KC vector pairs at a time into a ring of stages with 1-D TMA
+// bulk copies (cp.async.bulk + mbarrier, as the Gram kernels, gi_pipeline.cuh); 512 consumer threads form two groups of
+// 256: thread (rp, g) owns row pair rp of the tile and roots 8g .. 8g+7, i.e. 2 x 8 double2 running sums, and both groups
+// read the same tile, so every HBM byte is still moved once: 8n(2k + m + 1) bytes. The k-loop runs across the stages of
+// a row tile in ascending i (one FMA per term, from zero), the epilogue is the one of the kernels above: bit-identical
+// vectors.
+constexpr int kTileRows = 512;               // rows per tile = 2 x 256 row pairs
+constexpr int kTileKC = 4;                   // vector pairs per stage
+constexpr int kTileSlots = 2 * kTileKC + 1;  // q and a of the chunk + the diagonal (with the first chunk of a tile)
+constexpr int kTileStages = 4;               // 4 x 9 x 4 KB = 144 KB (+ 64 KB of running squares, + the coefficients)
+constexpr int kTileConsumers = 512;
+constexpr int kTileProducers = 4;            // warps
+constexpr int kTileThreads = kTileConsumers + 32 * kTileProducers;
+constexpr int kTileGroupRoots = 8;
+static size_t ds_tile_bytes(int k) {
+  return size_t(kTileStages) * kTileSlots * kTileRows * sizeof(double) +
+         size_t(2 * kTileGroupRoots) * kTileConsumers * sizeof(double) + size_t(k) * 16 * sizeof(double) + 128;
+}
+
+__global__ void __launch_bounds__(kTileThreads, 1) davidson_residual_tile_kernel(const __grid_constant__ DsParams p) {
+  extern __shared__ __align__(128) unsigned char ds_smem_raw[];
+  double* stages = reinterpret_cast<double*>(ds_smem_raw);
+  // running <r,r> [0,8) and <out,out> [8,16) of each consumer thread's roots: one column per thread (conflict-free);
+  // in shared memory because the 2 x 8 double2 running sums of the expansions take the registers
+  double* sq = stages + size_t(kTileStages) * kTileSlots * kTileRows;
+  double* sc = sq + size_t(2 * kTileGroupRoots) * kTileConsumers; // k x 16 coefficients
+  __shared__ uint64_t full_bar[kTileStages];
+  __shared__ uint64_t empty_bar[kTileStages];
+  __shared__ double s_part[kTileConsumers / 32][2 * kTileGroupRoots];
+  __shared__ int s_is_last;
+  using Ops = DsOps<double2>;
+  const int tid = threadIdx.x;
+  const bool is_producer = tid >= kTileConsumers;
+  for (int e = tid; e < p.k * 16; e += blockDim.x)
+    sc[e] = p.coef[e];
+  if (tid == 0) {
+    for (int s = 0; s < kTileStages; ++s) {
+      mbar_init(&full_bar[s], kTileProducers);
+      mbar_init(&empty_bar[s], kTileConsumers / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long nfull = (long long)(p.n / kTileRows);
+  const long long my_tiles = nfull > (long long)blockIdx.x ? (nfull - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int nchunks = (p.k + kTileKC - 1) / kTileKC;
+  constexpr uint32_t kVecBytes = kTileRows * 8u;
+  if (!is_producer)
+    for (int b = 0; b < 2 * kTileGroupRoots; ++b)
+      sq[b * kTileConsumers + tid] = 0.0;
+
+  if (is_producer) {
+    const int pw = (tid - kTileConsumers) >> 5;
+    const bool leader = elect_one();
+    const uint32_t base = smem_u32(stages);
+    long long seq = 0;
+    for (long long s = 0; s < my_tiles; ++s) {
+      const size_t row0 = size_t(blockIdx.x + s * gridDim.x) * kTileRows;
+      for (int c = 0; c < nchunks; ++c, ++seq) {
+        const int stage = int(seq % kTileStages);
+        const long long use = seq / kTileStages;
+        if (use > 0)
+          mbar_wait(&empty_bar[stage], uint32_t((use - 1) & 1));
+        const int i0 = c * kTileKC;
+        const int kc = p.k - i0 < kTileKC ? p.k - i0 : kTileKC;
+        const int ncopies = 2 * kc + ((c == 0 && p.diag) ? 1 : 0);
+        const int mine = ncopies > pw ? (ncopies - pw + kTileProducers - 1) / kTileProducers : 0;
+        const uint32_t bar = smem_u32(&full_bar[stage]);
+        const uint32_t st = base + uint32_t(stage) * uint32_t(kTileSlots) * kVecBytes;
+        if (leader) {
+          mbar_expect_tx(&full_bar[stage], kVecBytes * uint32_t(mine));
+          for (int e = pw; e < ncopies; e += kTileProducers) {
+            // copy e of the stage: q of the chunk, then a of the chunk, then the diagonal
+            const double* src;
+            int slot;
+            if (e < kc) {
+              src = p.q[i0 + e];
+              slot = e;
+            } else if (e < 2 * kc) {
+              src = p.a[i0 + e - kc];
+              slot = kTileKC + (e - kc);
+            } else {
+              src = p.diag;
+              slot = 2 * kTileKC;
+            }
+            bulk_load(st + uint32_t(slot) * kVecBytes, src + row0, kVecBytes, bar);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int rp = tid & 255, g = tid >> 8;
+    double* mysq = sq + tid;
+    const int lane = tid & 31;
+    const double* cg = sc + g * kTileGroupRoots;
+    double2 ax[kTileGroupRoots], ar[kTileGroupRoots];
+    double2 dg = Ops::zero();
+    long long seq = 0;
+    for (long long s = 0; s < my_tiles; ++s) {
+      const size_t prow = (size_t(blockIdx.x + s * gridDim.x) * kTileRows) / 2 + rp; // this thread's row pair
+#pragma unroll
+      for (int b = 0; b < kTileGroupRoots; ++b) {
+        ax[b] = Ops::zero();
+        ar[b] = Ops::zero();
+        if (p.accumulate && g * kTileGroupRoots + b < p.m) {
+          ax[b] = reinterpret_cast<const double2*>(p.out_x[g * kTileGroupRoots + b])[prow];
+          ar[b] = reinterpret_cast<const double2*>(p.out_r[g * kTileGroupRoots + b])[prow];
+        }
+      }
+      for (int c = 0; c < nchunks; ++c, ++seq) {
+        const int stage = int(seq % kTileStages);
+        mbar_wait(&full_bar[stage], uint32_t((seq / kTileStages) & 1));
+        const double2* st = reinterpret_cast<const double2*>(stages + size_t(stage) * kTileSlots * kTileRows) + rp;
+        if (c == 0 && p.diag)
+          dg = st[2 * kTileKC * (kTileRows / 2)];
+        const int i0 = c * kTileKC;
+#pragma unroll
+        for (int u = 0; u < kTileKC; ++u) {
+          if (i0 + u < p.k) {
+            const double2 qv = st[u * (kTileRows / 2)], av = st[(kTileKC + u) * (kTileRows / 2)];
+            const double2* cu = reinterpret_cast<const double2*>(cg + size_t(i0 + u) * 16);
+#pragma unroll
+            for (int b2 = 0; b2 < kTileGroupRoots / 2; ++b2) {
+              const double2 cc = cu[b2];
+              Ops::fma_to(ax[2 * b2], cc.x, qv);
+              Ops::fma_to(ar[2 * b2], cc.x, av);
+              Ops::fma_to(ax[2 * b2 + 1], cc.y, qv);
+              Ops::fma_to(ar[2 * b2 + 1], cc.y, av);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0)
+          mbar_arrive(&empty_bar[stage]);
+      }
+#pragma unroll
+      for (int b = 0; b < kTileGroupRoots; ++b) {
+        const int j = g * kTileGroupRoots + b;
+        if (j < p.m) {
+          if (p.write_x)
+            reinterpret_cast<double2*>(p.out_x[j])[prow] = ax[b];
+          double2 res = ds_residual<double2>(p, j, prow, ar[b], ax[b]);
+          double t = mysq[b * kTileConsumers];
+          Ops::square_to(t, res);
+          mysq[b * kTileConsumers] = t;
+          if (p.diag) {
+            res = Ops::precondition(res, dg, p.shift[j]);
+            t = mysq[(kTileGroupRoots + b) * kTileConsumers];
+            Ops::square_to(t, res);
+            mysq[(kTileGroupRoots + b) * kTileConsumers] = t;
+          }
+          reinterpret_cast<double2*>(p.out_r[j])[prow] = res;
+        }
+      }
+    }
+    // rows past the last full tile: the CTA that would own tile number nfull takes them straight from global memory,
+    // one row per thread of group g (same chain of operations)
+    const size_t tail0 = size_t(nfull) * kTileRows;
+    if (tail0 < p.n && int(nfull % gridDim.x) == int(blockIdx.x)) {
+      for (size_t r = tail0 + size_t(rp); r < p.n; r += 256) {
+        double x1[kTileGroupRoots], r1[kTileGroupRoots];
+#pragma unroll
+        for (int b = 0; b < kTileGroupRoots; ++b) {
+          x1[b] = r1[b] = 0.0;
+          if (p.accumulate && g * kTileGroupRoots + b < p.m) {
+            x1[b] = p.out_x[g * kTileGroupRoots + b][r];
+            r1[b] = p.out_r[g * kTileGroupRoots + b][r];
+          }
+        }
+        for (int i = 0; i < p.k; ++i) {
+          const double q0 = p.q[i][r], a0 = p.a[i][r];
+          const double* cu = cg + size_t(i) * 16;
+#pragma unroll
+          for (int b = 0; b < kTileGroupRoots; ++b) {
+            x1[b] = fma(cu[b], q0, x1[b]);
+            r1[b] = fma(cu[b], a0, r1[b]);
+          }
+        }
+        const double d0 = p.diag ? p.diag[r] : 0.0;
+#pragma unroll
+        for (int b = 0; b < kTileGroupRoots; ++b) {
+          const int j = g * kTileGroupRoots + b;
+          if (j < p.m) {
+            if (p.write_x)
+              p.out_x[j][r] = x1[b];
+            double res = ds_residual<double>(p, j, r, r1[b], x1[b]);
+            double t = mysq[b * kTileConsumers];
+            DsOps<double>::square_to(t, res);
+            mysq[b * kTileConsumers] = t;
+            if (p.diag) {
+              res = DsOps<double>::precondition(res, d0, p.shift[j]);
+              t = mysq[(kTileGroupRoots + b) * kTileConsumers];
+              DsOps<double>::square_to(t, res);
+              mysq[(kTileGroupRoots + b) * kTileConsumers] = t;
+            }
+            p.out_r[j][r] = res;
+          }
+        }
+      }
+    }
+    // warp fold of the 16 running sums of this thread's group
+    const int warp = tid >> 5;
+#pragma unroll
+    for (int b = 0; b < kTileGroupRoots; ++b) {
+      double v = mysq[b * kTileConsumers], w = mysq[(kTileGroupRoots + b) * kTileConsumers];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        v += __shfl_down_sync(0xffffffffu, v, off);
+        w += __shfl_down_sync(0xffffffffu, w, off);
+      }
+      if (lane == 0) {
+        s_part[warp][b] = v;
+        s_part[warp][kTileGroupRoots + b] = w;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < 2 * p.m) { // partials laid out [<r,r> of the m roots | <out,out> of the m roots]
+    const int half = tid / p.m, j = tid % p.m;
+    const int g = j / kTileGroupRoots, b = j % kTileGroupRoots;
+    double sum = 0.0;
+    for (int w = 0; w < 8; ++w) // the 8 warps of group g, in warp order
+      sum += s_part[g * 8 + w][half * kTileGroupRoots + b];
+    p.fin.partials[size_t(blockIdx.x) * (2 * p.m) + tid] = sum;
+  }
+  gi_finalize(p.fin, 2 * p.m, &s_is_last);
 }
 
 using DsKernel = void (*)(const DsParams);
@@ -406,11 +669,28 @@ int itsolv_davidson_residual_f64(itsolv_ctx* ctx, const double* coef, int k, int
                                  const double* const* a, const double* lambda, const double* diag, const double* shift,
                                  double* const* out_x, double* const* out_r, size_t n, double* norm2,
                                  double* norm2_out) {
+  return itsolv_subspace_residual_f64(ctx, 0, 0, coef, k, m, q, a, lambda, nullptr, nullptr, diag, shift, out_x, out_r, n,
+                                      norm2, norm2_out);
+}
+
+int itsolv_subspace_residual_f64(itsolv_ctx* ctx, int mode, int accumulate, const double* coef, int k, int m,
+                                 const double* const* q, const double* const* a, const double* lambda,
+                                 const double* const* rhs, const double* rscale, const double* diag, const double* shift,
+                                 double* const* out_x, double* const* out_r, size_t n, double* norm2,
+                                 double* norm2_out) {
   ITSOLV_REQUIRE(k >= 1 && k <= ITSOLV_MAX_PANEL, "davidson_residual: 1 <= k <= ITSOLV_MAX_PANEL subspace vectors");
   ITSOLV_REQUIRE(m >= 1, "davidson_residual: m >= 1 roots");
-  ITSOLV_REQUIRE(out_r != nullptr && q != nullptr && a != nullptr && coef != nullptr && lambda != nullptr,
+  ITSOLV_REQUIRE(mode == 0 || mode == 1, "subspace_residual: mode 0 (eigenproblem) or 1 (linear equations)");
+  ITSOLV_REQUIRE(out_r != nullptr && q != nullptr && a != nullptr && coef != nullptr && (mode == 1 || lambda != nullptr),
                  "davidson_residual: null argument");
+  ITSOLV_REQUIRE(mode == 0 || (rhs != nullptr && rscale != nullptr), "subspace_residual: right-hand sides and scales");
+  ITSOLV_REQUIRE(!accumulate || out_x != nullptr, "subspace_residual: accumulation needs the solution vectors");
   ITSOLV_REQUIRE(diag == nullptr || shift != nullptr, "davidson_residual: shifts are needed with a diagonal");
+  if (mode == 1)
+    for (int j = 0; j < m; ++j)
+      for (int j2 = 0; j2 < m; ++j2)
+        ITSOLV_REQUIRE(out_r[j] != rhs[j2] && (!out_x || out_x[j] != rhs[j2]),
+                       "subspace_residual: an output vector is also a right-hand side");
   for (int j = 0; j < m; ++j) { // the outputs must not be inputs of the same pass
     for (int i = 0; i < k; ++i)
       ITSOLV_REQUIRE(out_r[j] != q[i] && out_r[j] != a[i] && (!out_x || (out_x[j] != q[i] && out_x[j] != a[i])),
@@ -424,7 +704,8 @@ int itsolv_davidson_residual_f64(itsolv_ctx* ctx, const double* coef, int k, int
     ctx->counters.n_precondition++;
   for (int j0 = 0; j0 < m; j0 += kDsMaxRoots) {
     const int mb = std::min(kDsMaxRoots, m - j0);
-    const double bytes = 8.0 * double(n) * (2.0 * k + mb * (out_x ? 2.0 : 1.0) + (diag ? 1.0 : 0.0));
+    const double bytes = 8.0 * double(n) * (2.0 * k + mb * (out_x ? 2.0 : 1.0) + (diag ? 1.0 : 0.0) +
+                                            (mode == 1 ? mb : 0) + (accumulate ? 2.0 * mb : 0.0));
     CallScope scope(ctx, OP_RESIDUAL, bytes);
     bool direct = false;
     if (n == 0) { // an empty shard still takes part in the all-reduce
@@ -443,9 +724,11 @@ int itsolv_davidson_residual_f64(itsolv_ctx* ctx, const double* coef, int k, int
         const int jj = j0 + std::min(j, mb - 1);
         p.out_x[j] = out_x ? out_x[jj] : nullptr;
         p.out_r[j] = out_r[jj];
-        p.lambda[j] = lambda[jj];
+        p.lambda[j] = mode == 0 ? lambda[jj] : 0.0;
         p.shift[j] = diag ? shift[jj] : 0.0;
-        vec = vec && aligned16(p.out_r[j]) && (!out_x || aligned16(p.out_x[j]));
+        p.rhs[j] = mode == 1 ? rhs[jj] : nullptr;
+        p.rscale[j] = mode == 1 ? rscale[jj] : 1.0;
+        vec = vec && aligned16(p.out_r[j]) && (!out_x || aligned16(p.out_x[j])) && (mode == 0 || aligned16(p.rhs[j]));
       }
       int mj = 1;
       while (mj < mb)
@@ -456,6 +739,8 @@ int itsolv_davidson_residual_f64(itsolv_ctx* ctx, const double* coef, int k, int
       p.n = n;
       p.diag = diag;
       p.write_x = out_x ? 1 : 0;
+      p.mode = mode;
+      p.accumulate = accumulate ? 1 : 0;
       char *h = nullptr, *d = nullptr;
       int slot = 0;
       const size_t cbytes = size_t(k) * p.ld * sizeof(double);
@@ -468,27 +753,33 @@ int itsolv_davidson_residual_f64(itsolv_ctx* ctx, const double* coef, int k, int
       if (stage_commit(ctx, slot, cbytes))
         return 1;
       p.coef = reinterpret_cast<const double*>(d);
-      if (mj == 16)
+      // 9..16 roots: the TMA tile kernel (needs 16-byte aligned vectors and at least one full tile per CTA to pay off)
+      const bool tile = mj == 16 && vec && ctx->opt_ds_ring >= 0 && n >= size_t(kTileRows) * 8 &&
+                        ds_tile_bytes(k) <= size_t(ctx->max_smem_optin);
+      if (mj == 16 && !tile)
         vec = false; // 16 roots: one row per thread keeps the 32 running sums in registers at two CTAs per SM
       // measured (profiles/opbench): the ring wins while the epilogue (divisions, stores) is a large part of a row's work,
       // the register kernel once the subspace has more than ~10 vector pairs
       const bool ring = vec && mj <= 8 && ctx->opt_ds_ring >= 0 && (k <= 10 || mj == 8 || ctx->opt_ds_ring > 0) &&
                         ((cbytes + 15) & ~size_t(15)) + ds_ring_bytes(mj) <= size_t(ctx->max_smem_optin) / 2 - 1024;
-      DsKernel kernel = ring ? ds_pick_ring(mj) : ds_pick(mj, vec);
+      DsKernel kernel = tile ? davidson_residual_tile_kernel : (ring ? ds_pick_ring(mj) : ds_pick(mj, vec));
       ITSOLV_REQUIRE(kernel != nullptr, "davidson_residual: root tile not instantiated");
-      const size_t smem = ring ? ((cbytes + 15) & ~size_t(15)) + ds_ring_bytes(mj)
-                               : cbytes + (mj > 8 ? size_t(2 * mj) * kDsThreads * sizeof(double) : 0);
+      const size_t smem = tile ? ds_tile_bytes(k)
+                               : ring ? ((cbytes + 15) & ~size_t(15)) + ds_ring_bytes(mj)
+                                      : cbytes + (mj > 8 ? size_t(2 * mj) * kDsThreads * sizeof(double) : 0);
       if (ensure_dynamic_smem(ctx, reinterpret_cast<const void*>(kernel), smem))
         return 1;
-      const int per_sm = ring ? 2 : (mj <= 2 ? 3 : 2);
+      const int per_sm = tile ? 1 : (ring ? 2 : (mj <= 2 ? 3 : 2));
       const size_t units = vec ? n / 2 : n;
-      const int grid = int(std::max<size_t>(
-          1, std::min<size_t>((units + kDsThreads - 1) / kDsThreads, size_t(ctx->num_sms) * per_sm)));
+      const int threads = tile ? kTileThreads : kDsThreads;
+      const int grid = tile ? int(std::min<size_t>((n + kTileRows - 1) / kTileRows, size_t(ctx->num_sms)))
+                            : int(std::max<size_t>(1, std::min<size_t>((units + kDsThreads - 1) / kDsThreads,
+                                                                       size_t(ctx->num_sms) * per_sm)));
       if (ensure_partials(ctx, size_t(grid) * 2 * mb))
         return 1;
       fill_finalize(ctx, ctx->num_sms * per_sm, 2 * mb, &p.fin, &direct);
       mark_launch(ctx);
-      kernel<<<grid, kDsThreads, smem, ctx->stream>>>(p);
+      kernel<<<grid, threads, smem, ctx->stream>>>(p);
       ITSOLV_CUDA(cudaGetLastError());
       ctx->counters.launches += 1;
       if (stage_done(ctx, slot))

@@ -249,6 +249,8 @@ void fill_finalize(itsolv_ctx* ctx, int grid_bound, int km, GiFinalize* f, bool*
   f->peers.nranks = 1;
   f->peers.rank = 0;
   f->peers.slot_doubles = 0;
+  f->peers.error = nullptr;
+  f->peers.timeout_ns = 0;
   f->dev_sums = nullptr;
   f->chain_out = nullptr;
   f->chain_offset = f->chain_count = 0;

@@ -81,10 +81,17 @@ class Problem:
                                                            C.byref(h)))
         self.handle = h
 
-    def solve(self, spec: N.SolveSpec, solutions: np.ndarray | None = None) -> N.SolveResult:
+    def solve(self, spec: N.SolveSpec, solutions: np.ndarray | int | None = None) -> N.SolveResult:
+        """solutions: host array (nroots x n_local), or the address of DEVICE memory of that size (the vectors then stay
+        on the GPU), or None"""
         res = N.SolveResult()
-        _hcheck(N.host().itsolv_harness_problem_solve(self.handle, C.byref(spec), C.byref(res),
-                                                      _dbl(solutions) if solutions is not None else None))
+        if solutions is None:
+            out = None
+        elif isinstance(solutions, int):
+            out = C.cast(C.c_void_p(solutions), N.c_double_p)
+        else:
+            out = _dbl(solutions)
+        _hcheck(N.host().itsolv_harness_problem_solve(self.handle, C.byref(spec), C.byref(res), out))
         return res
 
     def close(self):

@@ -91,6 +91,11 @@ public:
     for (size_t i = 0; i < xx.size(); ++i)
       m_primed.push_back({xx[i].get().data(), xx[i].get().data(), d[i]});
   }
+  //! x_k = alpha for every vector of the set
+  void fill_batch(double alpha, const VecRef<AL>& xx) {
+    for (auto& x : xx)
+      x.get().fill(alpha);
+  }
   //! x_k *= alpha[k], one launch
   void scal_batch(const std::vector<double>& alpha, const VecRef<AL>& xx) {
     if (xx.empty())
@@ -161,10 +166,24 @@ public:
   ResidualNorms davidson_residual(const Matrix<value_type>& c, const CVecRef<AR>& q, const CVecRef<AR>& a,
                                   const std::vector<double>& lambda, const AR* diag, const VecRef<AL>& solutions,
                                   const VecRef<AL>& residuals) {
+    return subspace_residual(0, false, c, q, a, lambda, CVecRef<AR>{}, std::vector<double>{}, diag, lambda, solutions,
+                             residuals);
+  }
+  /*!
+   * The same pass for both Davidson-type solvers (itsolv_subspace_residual_f64):
+   *   mode 0: r_j = sum_i c(i,j) a_i - lambda_j x_j;  mode 1: r_j = (sum_i c(i,j) a_i - rhs_j) * rscale_j
+   *   (reference LinearEquationsDavidson.h:173-184). `accumulate`: x_j and r_j continue from the present contents of
+   *   `solutions` / `residuals` (the P-space parts) instead of zero. `shift`: of the diagonal preconditioner.
+   */
+  ResidualNorms subspace_residual(int mode, bool accumulate, const Matrix<value_type>& c, const CVecRef<AR>& q,
+                                  const CVecRef<AR>& a, const std::vector<double>& lambda, const CVecRef<AR>& rhs,
+                                  const std::vector<double>& rscale, const AR* diag, const std::vector<double>& shift,
+                                  const VecRef<AL>& solutions, const VecRef<AL>& residuals) {
     const size_t k = c.rows(), m = c.cols();
-    if (k > q.size() || k > a.size() || m > residuals.size() || m > lambda.size() ||
-        (!solutions.empty() && m > solutions.size()))
-      throw std::out_of_range("davidson_residual: dimensions of the coefficients and the vector sets are different.");
+    if (k > q.size() || k > a.size() || m > residuals.size() || (mode == 0 && m > lambda.size()) ||
+        (mode == 1 && (m > rhs.size() || m > rscale.size())) || (diag && m > shift.size()) ||
+        (!solutions.empty() && m > solutions.size()) || (accumulate && solutions.empty()))
+      throw std::out_of_range("subspace_residual: dimensions of the coefficients and the vector sets are different.");
     ResidualNorms norms{std::vector<double>(m), std::vector<double>(m)};
     if (m == 0)
       return norms;
@@ -174,8 +193,12 @@ public:
     this->m_counter->axpy += int(m);
     this->m_counter->dot += int(m);
     const AL& first = residuals[0].get();
-    std::vector<const double*> pq(k), pa(k);
+    std::vector<const double*> pq(k), pa(k), prhs(mode == 1 ? m : 0);
     std::vector<double*> px(solutions.empty() ? 0 : m), pr(m);
+    for (size_t j = 0; j < prhs.size(); ++j) {
+      first.require_compatible(rhs[j].get(), "subspace_residual");
+      prhs[j] = rhs[j].get().data();
+    }
     for (size_t i = 0; i < k; ++i) {
       first.require_compatible(q[i].get(), "davidson_residual");
       first.require_compatible(a[i].get(), "davidson_residual");
@@ -192,11 +215,13 @@ public:
     }
     if (diag)
       first.require_compatible(*diag, "davidson_residual");
-    check(itsolv_davidson_residual_f64(first.context(), c.data().data(), int(k), int(m), pq.data(), pa.data(),
-                                       lambda.data(), diag ? diag->data() : nullptr, lambda.data(),
+    check(itsolv_subspace_residual_f64(first.context(), mode, accumulate ? 1 : 0, c.data().data(), int(k), int(m),
+                                       pq.data(), pa.data(), mode == 0 ? lambda.data() : nullptr,
+                                       mode == 1 ? prhs.data() : nullptr, mode == 1 ? rscale.data() : nullptr,
+                                       diag ? diag->data() : nullptr, diag ? shift.data() : nullptr,
                                        solutions.empty() ? nullptr : px.data(), pr.data(), first.local_size(),
                                        norms.residual.data(), norms.written.data()),
-          "ArrayHandlerCUDA::davidson_residual");
+          "ArrayHandlerCUDA::subspace_residual");
     if (m_observer)
       m_observer('g', 1, m, norms.residual.data());
     return norms;

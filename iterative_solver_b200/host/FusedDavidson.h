@@ -198,21 +198,26 @@ public:
   }
 };
 
-class LinearEigensystemDavidsonFused
-    : public its::LinearEigensystemDavidson<DistrArrayCUDA, DistrArrayCUDA, std::map<size_t, double>> {
+/*!
+ * The fused driver, shared by the two Davidson-type solvers of the reference: Base is
+ * its::LinearEigensystemDavidson<R,R,P> or its::LinearEquationsDavidson<R,R,P> (both are IterativeSolverTemplate
+ * instances with the same subspace solver, X space and proposal step, reference itsolv/LinearEigensystemDavidson.h:63-83 and
+ * LinearEquationsDavidson.h:49-62). What differs between them - the residual form, where the thresholds and the D-space
+ * resetter live - is behind the small set of hooks at the end of the class.
+ */
+template <class Base>
+class FusedDriver : public Base {
 public:
   using R = DistrArrayCUDA;
   using P = std::map<size_t, double>;
-  using Base = its::LinearEigensystemDavidson<R, R, P>;
   using Base::end_iteration;
   using Base::solution;
 
-  explicit LinearEigensystemDavidsonFused(const std::shared_ptr<HandlersCUDA>& handlers,
-                                          const std::shared_ptr<its::Logger>& logger_ = std::make_shared<its::Logger>())
+  explicit FusedDriver(const std::shared_ptr<HandlersCUDA>& handlers, const std::shared_ptr<its::Logger>& logger_)
       : Base(handlers, logger_) {
     m_dense = dynamic_cast<ArrayHandlerCUDA*>(&handlers->rr());
     if (!m_dense || dynamic_cast<ArrayHandlerCUDA*>(&handlers->rq()) != m_dense)
-      throw std::logic_error("LinearEigensystemDavidsonFused needs the handlers of make_handlers()");
+      throw std::logic_error("the fused solvers need the handlers of make_handlers()");
     this->m_xspace = std::make_shared<XSpaceFused>(handlers, logger_);
     this->set_hermiticity(this->get_hermiticity());
   }
@@ -226,7 +231,7 @@ public:
    *  - the R vectors that enter the Q space hand over their allocations instead of being copied (they are overwritten by
    *    the solution step that follows), and the proposal step swaps its result into the parameters instead of copying;
    *  - solutions, residuals, error norms and - for a Problem tagged UsesDefaultDiagonalPreconditioner - the diagonal
-   *    preconditioner of all roots are one pass over the subspace (ArrayHandlerCUDA::davidson_residual). The solution
+   *    preconditioner of all roots are one pass over the subspace (ArrayHandlerCUDA::subspace_residual). The solution
    *    vectors themselves are formed only once the working set is empty: during the iterations the reference overwrites
    *    them before anything reads them (parameters[0] receives the diagonal, :391, and the proposal step the new
    *    parameters);
@@ -352,7 +357,7 @@ public:
       auto pvectors = its::detail::construct_vectorP(roots, sol, dims.oP, dims.nP);
       this->m_apply_p(pvectors, xs.cparamsp(), residual);
     }
-    construct_residual(roots, its::cwrap(parameters), residual);
+    this->construct_residual(roots, its::cwrap(parameters), residual);
     // the caller asks for <res_i, res_i> of every root next (update_errors, IterativeSolverTemplate.h:96-102):
     // all of them in one launch, answered from the handler's primed results
     m_dense->prime_self_dots(its::cwrap(res));
@@ -360,14 +365,14 @@ public:
   }
 
   size_t end_iteration(const VecRef<R>& parameters, const VecRef<R>& action) override {
-    if (this->m_dspace_resetter.do_reset(this->m_stats->iterations, this->m_xspace->dimensions())) {
-      this->m_resetting_in_progress = true;
+    if (fused_resetter().do_reset(this->m_stats->iterations, this->m_xspace->dimensions())) {
+      fused_resetting(true);
       m_written_norms.clear();
-      this->m_working_set = this->m_dspace_resetter.run(
-          parameters, *this->m_xspace, this->m_subspace_solver->solutions(), this->propose_rspace_norm_thresh,
-          this->propose_rspace_svd_thresh, *this->m_handlers, *this->m_logger);
+      this->m_working_set =
+          fused_resetter().run(parameters, *this->m_xspace, this->m_subspace_solver->solutions(), fused_norm_thresh(),
+                               fused_svd_thresh(), *this->m_handlers, *this->m_logger);
     } else {
-      this->m_resetting_in_progress = false;
+      fused_resetting(false);
       this->m_working_set = propose_rspace_fused(parameters, action);
     }
     this->m_stats->iterations++;
@@ -401,9 +406,9 @@ protected:
     this->m_subspace_solver->solve(*this->m_xspace, this->n_roots());
     const auto nsol = this->m_subspace_solver->size();
     const auto dims = this->m_xspace->dimensions();
-    if (dims.nP != 0 || nsol == 0 || this->m_normalise_solution || dims.nQ + dims.nD == 0) {
-      // a P space or normalised solutions: the general routine (it solves the same subspace problem again, which is
-      // cheap next to these cases' vector work)
+    if (nsol == 0 || this->m_normalise_solution || dims.nQ + dims.nD == 0) {
+      // normalised solutions (none of the reference's three solvers asks for them): the general routine (it solves the
+      // same subspace problem again, which is cheap next to that case's vector work)
       const auto nwork = this->solve_and_generate_working_set(parameters, actions);
       its::read_handler_counts(this->m_stats, this->m_handlers);
       this->m_end_iteration_needed = true;
@@ -411,7 +416,6 @@ protected:
     }
     auto& xs = *this->m_xspace;
     const auto& sol = this->m_subspace_solver->solutions();
-    const auto eigvals = this->eigenvalues();
     auto stack = [](CVecRef<R> a, const CVecRef<R>& b) {
       a.insert(a.end(), b.begin(), b.end());
       return a;
@@ -428,16 +432,32 @@ protected:
       std::vector<int> roots(nb);
       std::iota(roots.begin(), roots.end(), int(start));
       Matrix<double> c({dims.nQ + dims.nD, nb});
-      std::vector<double> lambda(nb);
       for (size_t i = 0; i < nb; ++i) {
-        lambda[i] = eigvals.at(start + i);
         for (size_t j = 0; j < dims.nQ; ++j)
           c(j, i) = sol(start + i, dims.oQ + j);
         for (size_t j = 0; j < dims.nD; ++j)
           c(dims.nQ + j, i) = sol(start + i, dims.oD + j);
       }
-      const auto norms = m_dense->davidson_residual(c, xpar, xact, lambda, diagonals, VecRef<R>{},
-                                                    VecRef<R>(actions.begin(), actions.begin() + nb));
+      const auto form = fused_residual_form(roots);
+      const VecRef<R> wres(actions.begin(), actions.begin() + nb);
+      VecRef<R> wsol;
+      if (dims.nP != 0) {
+        // P space: its part of the solutions comes first, as in the reference (zero, scatter-add of the sparse vectors,
+        // IterativeSolverTemplate.h:44-57), and the caller's apply_p adds its part of the actions (:210-211) to zeroed
+        // residual buffers; the dense pass then continues from both (`accumulate`) instead of starting from zero
+        wsol = VecRef<R>(parameters.begin(), parameters.begin() + nb);
+        Matrix<double> cp({dims.nP, nb});
+        for (size_t i = 0; i < nb; ++i)
+          for (size_t j = 0; j < dims.nP; ++j)
+            cp(j, i) = sol(start + i, dims.oP + j);
+        m_dense->fill_batch(0.0, wsol);
+        m_dense->fill_batch(0.0, wres);
+        this->m_handlers->rp().gemm_outer(cp, xs.cparamsp(), wsol);
+        auto pvectors = its::detail::construct_vectorP(roots, sol, dims.oP, dims.nP);
+        this->m_apply_p(pvectors, xs.cparamsp(), wres);
+      }
+      const auto norms = m_dense->subspace_residual(form.mode, dims.nP != 0, c, xpar, xact, form.lambda, form.rhs,
+                                                    form.rscale, diagonals, form.shift, wsol, wres);
       std::vector<double> errors(nb);
       for (size_t i = 0; i < nb; ++i) {
         errors[i] = std::sqrt(std::abs(norms.residual[i]));
@@ -480,16 +500,6 @@ protected:
     return int(this->m_working_set.size());
   }
 
-  //! res_i -= lambda_i * x_i for all roots in one pass (reference LinearEigensystemDavidson.h:186-192)
-  void construct_residual(const std::vector<int>& roots, const CVecRef<R>& params, const VecRef<R>& actions) override {
-    const auto eigvals = this->eigenvalues();
-    std::vector<double> alpha(roots.size());
-    for (size_t i = 0; i < roots.size(); ++i)
-      alpha[i] = -eigvals.at(roots[i]);
-    m_dense->axpy_batch(alpha, CVecRef<R>(params.begin(), params.begin() + roots.size()),
-                        VecRef<R>(actions.begin(), actions.begin() + roots.size()));
-  }
-
   /*!
    * New D vectors from the Q vectors that leave the Q space and the old D vectors (reference
    * itsolv/propose_rspace.h:350-403). The host part - projected solutions, their overlaps, null-space removal - is the
@@ -504,8 +514,8 @@ protected:
     auto& logger = *this->m_logger;
     const auto dims = xspace.dimensions();
     const auto overlap = xspace.data.at(its::subspace::EqnData::S);
-    const auto norm_thresh = this->propose_rspace_norm_thresh;
-    const auto svd_thresh = this->propose_rspace_svd_thresh;
+    const auto norm_thresh = fused_norm_thresh();
+    const auto svd_thresh = fused_svd_thresh();
     auto solutions_proj = dsp::construct_projected_solution(solutions, dims, q_delete, logger);
     auto overlap_proj = dsp::construct_projected_solutions_overlap(solutions_proj, overlap, dims, q_delete, logger);
     dsp::remove_null_norm_and_normalise(solutions_proj, overlap_proj, norm_thresh, logger);
@@ -588,7 +598,7 @@ protected:
     auto& subspace_solver = *this->m_subspace_solver;
     auto solutions = subspace_solver.solutions();
     // Q-space limit -> D space: rare, left to the reference's routines (they go through the same handlers)
-    auto q_delete = det::limit_qspace_size(xspace.dimensions(), this->m_max_size_qspace, solutions, logger);
+    auto q_delete = det::limit_qspace_size(xspace.dimensions(), fused_max_size_qspace(), solutions, logger);
     if (!q_delete.empty()) {
       auto [dparams, dactions] = construct_dspace_fused(solutions, q_delete);
       std::sort(begin(q_delete), end(q_delete), std::greater<int>());
@@ -690,7 +700,7 @@ protected:
     }
     if (!scaled && nN > 0)
       m_dense->scal_batch(factor, wresidual);
-    auto redundant = det::redundant_parameters(ov, nX, nN, this->propose_rspace_svd_thresh, logger);
+    auto redundant = det::redundant_parameters(ov, nX, nN, fused_svd_thresh(), logger);
     its::util::delete_parameters(redundant, wresidual);
     nN = wresidual.size();
     // R-R modified Gram-Schmidt: one pass per pivot, which scales the pivot, updates the later vectors and returns the
@@ -702,7 +712,7 @@ protected:
     if (chained) {
       // all pivot steps as one chain of launches: the coefficients of a step are formed on the device by the tail of
       // the launch before it, with this loop's arithmetic; the decisions are repeated here from the returned sums
-      const auto rows = m_dense->mgs_chain(wresidual, this->propose_rspace_norm_thresh);
+      const auto rows = m_dense->mgs_chain(wresidual, fused_norm_thresh());
       size_t at = 0;
       for (size_t i = 0; i < nN; ++i) {
         const double rr = i == 0 ? rows[0] : rows[at + 1]; // <r_i, r_i> before its own step
@@ -710,7 +720,7 @@ protected:
           at = nN;               // block of step 0
         else
           at += nN - i + 1;      // block of step i (the block of step i-1 has nN - i + 1 entries)
-        if (std::sqrt(std::abs(rr)) > this->propose_rspace_norm_thresh)
+        if (std::sqrt(std::abs(rr)) > fused_norm_thresh())
           final_dot[i] = rows[at];
         else
           null_params.push_back(int(i));
@@ -724,7 +734,7 @@ protected:
         row.assign(g.data().begin(), g.data().end());
       }
       const double norm = std::sqrt(std::abs(row[0]));
-      if (norm > this->propose_rspace_norm_thresh) {
+      if (norm > fused_norm_thresh()) {
         std::vector<double> o(nN - i - 1);
         for (size_t j = 0; j < o.size(); ++j)
           o[j] = row[j + 1] / norm; // <r_i / |r_i|, r_j>
@@ -775,10 +785,61 @@ protected:
     return new_working_set;
   }
 
+  // ---- what differs between the two solvers ----
+  //! how the residual of the roots of one batch follows from the expansions (ArrayHandlerCUDA::subspace_residual)
+  struct ResidualForm {
+    int mode = 0;                //!< 0: r = sum c a - lambda x ; 1: r = (sum c a - rhs) * rscale
+    std::vector<double> lambda;  //!< mode 0
+    CVecRef<R> rhs;              //!< mode 1
+    std::vector<double> rscale;  //!< mode 1
+    std::vector<double> shift;   //!< of the diagonal preconditioner: what working_set_eigenvalues() would hand to it
+  };
+  virtual ResidualForm fused_residual_form(const std::vector<int>& roots) const = 0;
+  virtual double fused_norm_thresh() const = 0;
+  virtual double fused_svd_thresh() const = 0;
+  virtual int fused_max_size_qspace() const = 0;
+  virtual its::detail::DSpaceResetter<R>& fused_resetter() = 0;
+  virtual void fused_resetting(bool) {}
+
   ArrayHandlerCUDA* m_dense = nullptr;
   bool m_in_fused_solve = false;
   bool m_fuse_solve = true;
   std::vector<double> m_written_norms; //!< <r,r> of the working set's preconditioned residuals, from the residual kernel
+};
+
+//! LinearEigensystemDavidson of the reference on the fused driver
+class LinearEigensystemDavidsonFused
+    : public FusedDriver<its::LinearEigensystemDavidson<DistrArrayCUDA, DistrArrayCUDA, std::map<size_t, double>>> {
+public:
+  using Base = its::LinearEigensystemDavidson<DistrArrayCUDA, DistrArrayCUDA, std::map<size_t, double>>;
+  explicit LinearEigensystemDavidsonFused(const std::shared_ptr<HandlersCUDA>& handlers,
+                                          const std::shared_ptr<its::Logger>& logger_ = std::make_shared<its::Logger>())
+      : FusedDriver<Base>(handlers, logger_) {}
+
+protected:
+  ResidualForm fused_residual_form(const std::vector<int>& roots) const override {
+    ResidualForm f;
+    const auto eigvals = this->eigenvalues();
+    for (auto root : roots)
+      f.lambda.push_back(eigvals.at(size_t(root)));
+    f.shift = f.lambda; // the Davidson update divides by d - lambda_root (working_set_eigenvalues, :94-100)
+    return f;
+  }
+  double fused_norm_thresh() const override { return this->propose_rspace_norm_thresh; }
+  double fused_svd_thresh() const override { return this->propose_rspace_svd_thresh; }
+  int fused_max_size_qspace() const override { return this->m_max_size_qspace; }
+  its::detail::DSpaceResetter<R>& fused_resetter() override { return this->m_dspace_resetter; }
+  void fused_resetting(bool on) override { this->m_resetting_in_progress = on; }
+
+  //! res_i -= lambda_i * x_i for all roots in one pass (reference LinearEigensystemDavidson.h:186-192)
+  void construct_residual(const std::vector<int>& roots, const CVecRef<R>& params, const VecRef<R>& actions) override {
+    const auto eigvals = this->eigenvalues();
+    std::vector<double> alpha(roots.size());
+    for (size_t i = 0; i < roots.size(); ++i)
+      alpha[i] = -eigvals.at(roots[i]);
+    m_dense->axpy_batch(alpha, CVecRef<R>(params.begin(), params.begin() + roots.size()),
+                        VecRef<R>(actions.begin(), actions.begin() + roots.size()));
+  }
 };
 
 } // namespace itsolv_b200

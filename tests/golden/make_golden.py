@@ -34,6 +34,11 @@ SOLVE_CASES = {
     "banded_davidson_n30000_r6_qcap8": dict(n=30000, kind=N.KIND_DAVIDSON, nroots=6, hermitian=1, max_size_qspace=8),
     "banded_davidson_n30000_r6_buf2": dict(n=30000, kind=N.KIND_DAVIDSON, nroots=6, nbuffers=2, hermitian=1),
     "banded_davidson_n30000_r4_p20": dict(n=30000, kind=N.KIND_DAVIDSON, nroots=4, hermitian=1, max_p=20),
+    # P spaces too small to hold the solutions: P, Q (and D) together through several iterations
+    "banded_davidson_n30000_r4_p4": dict(n=30000, kind=N.KIND_DAVIDSON, nroots=4, hermitian=1, max_p=4),
+    "banded_davidson_n30000_r4_p6": dict(n=30000, kind=N.KIND_DAVIDSON, nroots=4, hermitian=1, max_p=6),
+    "banded_davidson_n30000_r6_qcap8_buf3_p8": dict(n=30000, kind=N.KIND_DAVIDSON, nroots=6, nbuffers=3, hermitian=1,
+                                                    max_size_qspace=8, max_p=8),
     "banded_davidson_n30000_r4_wide": dict(n=30000, kind=N.KIND_DAVIDSON, nroots=4, hermitian=1, half_bandwidth=16, eps=1e-2),
     # LinearEquations: right-hand sides b_k = A x_k with the scaled known solutions (ITSOLV_RHS_SCALED, the default)
     "banded_lineq_n50000_r1": dict(n=50000, kind=N.KIND_LINEQ, nroots=1, hermitian=1),

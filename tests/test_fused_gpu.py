@@ -49,7 +49,10 @@ def test_batched_kernels_bit_exact(ctx, oracle, n):
 
 
 @pytest.mark.parametrize("n,k,m", [(1, 1, 1), (2, 3, 2), (33, 5, 3), (1000, 4, 4), (4097, 9, 5), (50001, 12, 8),
-                                   (20000, 7, 16), (3001, 6, 19)])
+                                   (20000, 7, 16), (3001, 6, 19),
+                                   # the TMA tile kernel of 9..16 roots: odd tail, a second root group of one root, fewer
+                                   # vectors than a stage holds, several tiles per CTA, a chunked k loop
+                                   (70001, 24, 16), (5000, 13, 9), (8193, 3, 12), (227335, 5, 16), (4096, 40, 16)])
 @pytest.mark.parametrize("precondition", [False, True])
 def test_davidson_residual_kernel_equals_the_unfused_sequence(ctx, oracle, n, k, m, precondition):
     """itsolv_davidson_residual_f64 against the oracle's sequence of the reference's steps: two expansions (FMA chains
@@ -106,6 +109,69 @@ def test_gemm_outer_scaled_equals_scal_then_gemm_outer(ctx, oracle, n, k, m):
     ctx.gemm_outer_scaled(alpha, xs, ys, scale)
     scaled = np.stack([oracle.c.scal(scale[j], Y[j].copy()) for j in range(m)])
     assert np.array_equal(host(ys), oracle.c.gemm_outer(alpha, X, scaled, fma=True))
+
+
+@pytest.mark.parametrize("n,k,m", [(1, 1, 1), (33, 5, 3), (4097, 9, 5), (50001, 12, 8), (20001, 7, 16), (70002, 24, 13)])
+@pytest.mark.parametrize("precondition", [False, True])
+def test_subspace_residual_linear_equations_form(ctx, oracle, n, k, m, precondition):
+    """mode 1 of itsolv_subspace_residual_f64 against the reference's sequence for LinearEquations: two expansions from
+    zero, axpy(-1, rhs, r), scal(1/|rhs|, r) (LinearEquationsDavidson.h:173-184), the norms, precondition_default with a
+    zero shift. Vectors bit for bit."""
+    rng = np.random.default_rng(77 * n + 10 * k + m)
+    Q, A, B = rng.standard_normal((k, n)), rng.standard_normal((k, n)), rng.standard_normal((m, n))
+    coef = rng.standard_normal((k, m))
+    scale = 1.0 / np.sqrt(np.array([oracle.c.dot(B[j], B[j]) for j in range(m)]))
+    diag = np.arange(1, n + 1, dtype=np.float64)
+    want_x = oracle.c.gemm_outer(coef, Q, np.zeros((m, n)), fma=True)
+    want_r = oracle.c.gemm_outer(coef, A, np.zeros((m, n)), fma=True)
+    want_r = np.stack([oracle.c.scal(scale[j], oracle.c.axpy(-1.0, B[j], want_r[j])) for j in range(m)])
+    want_n2 = np.array([oracle.c.dot(want_r[j], want_r[j]) for j in range(m)])
+    want_out = oracle.c.precondition(want_r, np.zeros(m), diag) if precondition else want_r
+    want_n2w = np.array([oracle.c.dot(want_out[j], want_out[j]) for j in range(m)])
+    out_r = [torch.full((n,), np.nan, dtype=torch.float64, device="cuda") for _ in range(m)]
+    out_x = [torch.full((n,), np.nan, dtype=torch.float64, device="cuda") for _ in range(m)]
+    n2, n2w = ctx.subspace_residual(coef, dev_rows(Q), dev_rows(A), out_r, rhs=dev_rows(B), rscale=scale,
+                                    diag=dev_rows(diag[None])[0] if precondition else None, shift=np.zeros(m), out_x=out_x)
+    assert np.array_equal(host(out_r), want_out) and np.array_equal(host(out_x), want_x)
+    assert np.abs(n2 - want_n2).max() <= 1e-12 * want_n2.max()
+    assert np.abs(n2w - want_n2w).max() <= 1e-12 * want_n2w.max()
+
+
+@pytest.mark.parametrize("n,k,m", [(33, 5, 3), (4097, 9, 4), (50001, 12, 8), (20001, 7, 16)])
+def test_subspace_residual_continues_from_the_p_space_parts(ctx, oracle, n, k, m):
+    """accumulate: x_j and r_j start from what the output vectors hold (the P-space parts, which the reference adds first
+    for the solutions, IterativeSolverTemplate.h:44-57) and the FMA chains continue from there"""
+    rng = np.random.default_rng(5 * n + k + m)
+    Q, A = rng.standard_normal((k, n)), rng.standard_normal((k, n))
+    X0, R0 = rng.standard_normal((m, n)), rng.standard_normal((m, n))
+    coef, lam = rng.standard_normal((k, m)), np.arange(1, m + 1) * 0.75
+    want_x = oracle.c.gemm_outer(coef, Q, X0, fma=True)
+    want_r = oracle.c.gemm_outer(coef, A, R0, fma=True)
+    want_r = np.stack([oracle.c.axpy(-lam[j], want_x[j], want_r[j]) for j in range(m)])
+    out_x, out_r = dev_rows(X0), dev_rows(R0)
+    n2, _ = ctx.subspace_residual(coef, dev_rows(Q), dev_rows(A), out_r, lam=lam, out_x=out_x, accumulate=True)
+    assert np.array_equal(host(out_x), want_x) and np.array_equal(host(out_r), want_r)
+    want_n2 = np.array([oracle.c.dot(want_r[j], want_r[j]) for j in range(m)])
+    assert np.abs(n2 - want_n2).max() <= 1e-12 * want_n2.max()
+
+
+def test_fused_linear_equations_match_the_reference_run_here_at_2e6_rows(ctx, oracle):
+    """LinearEquationsDavidsonFused against the reference's own class on its std::vector path, run in this process:
+    n = 2e6, 8 right-hand sides, Q capped at 24 (BASELINE.json configs[2] at 1/100 of its rows)"""
+    if oracle.ref is None:
+        pytest.skip("oracle/_ref is not built")
+    kw = dict(n=2_000_000, kind=N.KIND_LINEQ, nroots=8, hermitian=1, max_size_qspace=24)
+    want, wsol = oracle.ref.solve(H.make_spec(**kw), want_solutions=True)
+    got, sol = H.solve(ctx, H.make_spec(fused=1, **kw), want_solutions=True)
+    plain, _ = H.solve(ctx, H.make_spec(**kw))
+    assert want.converged == 1
+    assert got.iterations == want.iterations and got.converged == want.converged
+    assert [got.r_creations, got.q_creations, got.p_creations, got.d_creations] == \
+        [want.r_creations, want.q_creations, want.p_creations, want.d_creations]
+    assert got.kernel_launches < 0.5 * plain.kernel_launches
+    for k in range(8):
+        assert np.abs(sol[k] - wsol[k]).max() <= 1e-6 * max(1.0, np.abs(wsol[k]).max())
+        assert got.errors[k] <= 1e-8
 
 
 def test_davidson_residual_rejects_aliased_outputs(ctx):

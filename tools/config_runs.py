@@ -126,19 +126,43 @@ def _allmax(vals, world):
     return t.cpu().numpy()
 
 
-def verify_solutions(kind, n, start, sol_host, eigenvalues, rank, world, legacy=False):
-    """residuals (and distances to the known solutions) of the solution vectors, one root at a time on the GPU"""
-    import torch
-    nroots = sol_host.shape[0]
+class DeviceRows:
+    """nroots x nloc doubles from the context's own pool (so that they count in its high-water mark and need no host
+    memory); row(k) is a torch view of the k-th vector"""
+
+    def __init__(self, ctx, nroots, nloc):
+        self.ctx, self.nroots, self.nloc = ctx, nroots, nloc
+        self.address = ctx.alloc(nroots * max(nloc, 1))
+
+    def row(self, k):
+        import torch
+
+        class Raw:
+            pass
+        raw = Raw()
+        raw.__cuda_array_interface__ = {"shape": (self.nloc,), "typestr": "<f8", "version": 3,
+                                        "data": (self.address + 8 * k * self.nloc, False)}
+        return torch.as_tensor(raw, device="cuda")
+
+    def free(self):
+        if self.address:
+            self.ctx.free(self.address)
+            self.address = 0
+
+
+def verify_solutions(kind, n, start, rows, nroots, eigenvalues, rank, world, legacy=False):
+    """residuals (and distances to the known solutions) of the solution vectors, one root at a time on the GPU;
+    rows(k) returns the k-th solution as a torch tensor on the device"""
     res_norm, sol_err = [], []
     for k in range(nroots):
-        x = torch.from_numpy(sol_host[k]).cuda()
+        x = rows(k)
         nloc = x.numel()
         if kind == "davidson":
             y = torch_banded_apply(x, n, start, rank, world)
             r = y - eigenvalues[k] * x
             num, den = _allsum([float((r * r).sum()), float((x * x).sum())], world)
             res_norm.append(float(np.sqrt(num / den)))
+            del y
         elif kind == "lineq":
             xk = known_solution(kind, k, start, nloc, x.device, legacy)
             bk = torch_banded_apply(xk, n, start, rank, world)
@@ -201,15 +225,15 @@ def run(ctx, name, rank, world, n=None, overrides=None, fused=None, verify=True,
     nroots = 1 if kind == "diis" else kw["nroots"]
     ctx.set_profiling(True)
     ctx.mem_usage(reset_peak=True)
+    # the solution vectors stay on the GPU, in memory of the context's pool allocated BEFORE the solve: the high-water mark
+    # below is then what the whole run needs, and nothing of size n goes through the host
+    sol = DeviceRows(ctx, nroots, nloc) if verify else None
     problem = H.Problem(ctx, spec)
     t0 = time.perf_counter()
     res = problem.solve(spec)
     cold_s = time.perf_counter() - t0
-    sol = np.empty((nroots, nloc)) if verify else None
-    if warm:
-        res = problem.solve(spec, solutions=sol)
-    elif verify:
-        res = problem.solve(spec, solutions=sol)
+    if warm or verify:
+        res = problem.solve(spec, solutions=sol.address if sol else None)
     problem.close()
     live, peak = ctx.mem_usage()
     ctx.set_profiling(False)
@@ -234,15 +258,16 @@ def run(ctx, name, rank, world, n=None, overrides=None, fused=None, verify=True,
     }
     gates = {"converged": bool(res.converged)}
     if verify:
-        ctx.mem_trim()  # the pool keeps every freed vector; the checker's torch tensors need the memory back
-        res_norm, sol_err = verify_solutions(kind, spec.n, start, sol, eig, rank, world, legacy)
+        ctx.mem_trim()  # the pool keeps every freed vector; the checker's torch temporaries need some of it back
+        res_norm, sol_err = verify_solutions(kind, spec.n, start, sol.row, nroots, eig, rank, world, legacy)
         rec["independent_residual_max"] = max(res_norm)
         gates["residual_ok"] = max(res_norm) <= 1e-7
         if sol_err:
             rec["solution_error_max"] = max(sol_err)
             gates["solution_ok"] = max(sol_err) <= 1e-6
-        del sol
+        sol.free()
         torch.cuda.empty_cache()
+        ctx.mem_trim()
     if reference and n_small:
         small = None
         if rank == 0:
