@@ -231,6 +231,19 @@ int itsolv_banded_p_action_f64(itsolv_ctx* ctx, int64_t n_global, int64_t row_of
 /* dense toy operator of the reference's examples/ExampleProblem.h:8 (single rank, small n): y = M x,
  * M(i,j) = i==j ? i+1 : 0.001*((i+j) mod n) */
 int itsolv_example_apply_f64(itsolv_ctx* ctx, size_t n, const double* x, double* y);
+/* Element-wise members of the reference's DistrArray that the solvers do not call but its conformance tests do
+ * (array/DistrArray.cpp:79-167; test/array/testDistrArray.h:496-678): c is updated in place from a, b and a scalar. */
+enum {
+  ITSOLV_EW_ADD_SCALAR = 0,            /* c += s            add(value)  / sub(value)  */
+  ITSOLV_EW_RECIP = 1,                 /* c = 1 / c         recip()                   */
+  ITSOLV_EW_TIMES_INPLACE = 2,         /* c *= a            times(y)                  */
+  ITSOLV_EW_TIMES = 3,                 /* c = a * b         times(y, z)               */
+  ITSOLV_EW_DIVIDE = 4,                /* c = a / (b + s)   divide(y, z, s, false, false) */
+  ITSOLV_EW_DIVIDE_NEGATIVE = 5,       /* c = -a / (b + s)  divide(y, z, s, false, true)  */
+  ITSOLV_EW_DIVIDE_APPEND = 6,         /* c += a / (b + s)  divide(y, z, s, true, false)  */
+  ITSOLV_EW_DIVIDE_APPEND_NEGATIVE = 7 /* c -= a / (b + s)  divide(y, z, s, true, true)   */
+};
+int itsolv_elementwise_f64(itsolv_ctx* ctx, int op, double* c, const double* a, const double* b, double scalar, size_t n);
 /* out[i] = x[i] + c */
 int itsolv_shift_f64(itsolv_ctx* ctx, double c, const double* x, double* out, size_t n);
 /* out[i] = x[i] - t(row_offset + i): the argument of the harness' non-linear residual r(v) = A (v - t) (DIIS cases);

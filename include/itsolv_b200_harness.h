@@ -151,6 +151,14 @@ int itsolv_handler_sparse_gemm_inner(struct itsolv_ctx* ctx, int k, int m, size_
                                      const int32_t* map_ptr, const int64_t* idx, const double* val, double* out);
 int itsolv_handler_sparse_gemm_outer(struct itsolv_ctx* ctx, int nmap, int ndense, size_t n, const double* alpha,
                                      const int32_t* map_ptr, const int64_t* idx, const double* val, double* Y);
+/* The element-wise and sparse members of the container itself (DistrArrayCUDA, mirroring reference array/DistrArray.cpp:79-167,
+ * 248-262, 419-465), for the reference's conformance tests (test/array/testDistrArray.h:496-678). c is updated in place.
+ * op: 0 add(b) 1 sub(b) 2 add(scalar) 3 sub(scalar) 4 recip 5 times(a) 6 times(a, b) 7 divide(a, b, scalar, flags&1 append,
+ * flags&2 negative) 8 axpy(scalar, sparse) 9 dot(sparse) -> *result 10 select_max_dot(n = flags, sparse) -> sel_* (returns
+ * the count) 11 zero. Returns -1 on error. */
+int itsolv_handler_distr_array(struct itsolv_ctx* ctx, int op, size_t n, double scalar, int flags, const double* a,
+                               const double* b, double* c, int nnz, const int64_t* idx, const double* val,
+                               double* result, int64_t* sel_idx, double* sel_val);
 /* harness operator on host vectors (single rank: whole vector; multi rank: global x in, this rank's rows of y out) */
 int itsolv_harness_banded_apply(struct itsolv_ctx* ctx, int64_t n, int b, double eps, int explicit_csr, const double* x,
                                 double* y);

@@ -144,6 +144,7 @@ KERNEL_API = {
                                              c_void_pp, C.c_int, c_int32_p, c_int64_p, c_double_p, c_double_p]),
     "itsolv_example_apply_f64": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "itsolv_shift_f64": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "itsolv_elementwise_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_size_t]),
     "itsolv_banded_target_shift_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t]),
 }
 
@@ -176,6 +177,8 @@ HARNESS_API = {
                                                    c_int64_p, c_double_p, c_double_p]),
     "itsolv_handler_sparse_gemm_outer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, c_double_p, c_int32_p,
                                                    c_int64_p, c_double_p, c_double_p]),
+    "itsolv_handler_distr_array": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_double, C.c_int, c_double_p, c_double_p,
+                                             c_double_p, C.c_int, c_int64_p, c_double_p, c_double_p, c_int64_p, c_double_p]),
     "itsolv_harness_banded_apply": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, c_double_p,
                                               c_double_p]),
     "itsolv_host_eigenproblem": (C.c_int, [c_double_p, c_double_p, C.c_size_t, C.c_int, C.c_double, c_double_p,

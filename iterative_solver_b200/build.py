@@ -22,7 +22,11 @@ LIBDIR = os.path.join(PKG, "lib")
 OBJDIR = os.path.join(PKG, "build")
 REFERENCE = os.environ.get("ITSOLV_REFERENCE", "/root/reference")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-CXX = os.environ.get("CXX", "/usr/bin/g++")
+# The system compiler, whatever CXX says: a toolchain that links libstdc++ statically (this image exports
+# CXX=/opt/gcc/bin/g++, which does) would put a second copy of the iostream/locale state into the library, and with
+# -Bsymbolic (below) the library would use that copy while the process uses libstdc++.so's: a crash in the first
+# operator<<(double). ITSOLV_CXX overrides.
+CXX = os.environ.get("ITSOLV_CXX", "/usr/bin/g++")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

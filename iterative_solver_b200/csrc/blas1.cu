@@ -115,6 +115,45 @@ __global__ void __launch_bounds__(kThreads, 4) shift_kernel(double c, const doub
       [&](size_t i) { out[i] = __dadd_rn(x[i], c); });
 }
 
+// element-wise members of the reference's DistrArray (array/DistrArray.cpp:79-167), one rounding per operation as there
+__device__ __forceinline__ double elementwise_op(int op, double c, double a, double b, double s) {
+  switch (op) {
+  case ITSOLV_EW_ADD_SCALAR:
+    return __dadd_rn(c, s);                                   // c += s            (:81-85)
+  case ITSOLV_EW_RECIP:
+    return __ddiv_rn(1.0, c);                                 // c = 1 / c         (:91-95)
+  case ITSOLV_EW_TIMES_INPLACE:
+    return __dmul_rn(c, a);                                   // c *= a            (:97-107)
+  case ITSOLV_EW_TIMES:
+    return __dmul_rn(a, b);                                   // c = a * b         (:109-122)
+  case ITSOLV_EW_DIVIDE:
+    return __ddiv_rn(a, __dadd_rn(b, s));                     // c = a / (b + s)   (:164-165)
+  case ITSOLV_EW_DIVIDE_NEGATIVE:
+    return __ddiv_rn(-a, __dadd_rn(b, s));                    // c = -a / (b + s)  (:161-162)
+  case ITSOLV_EW_DIVIDE_APPEND:
+    return __dadd_rn(c, __ddiv_rn(a, __dadd_rn(b, s)));       // c += a / (b + s)  (:157-158)
+  default:
+    return __dsub_rn(c, __ddiv_rn(a, __dadd_rn(b, s)));       // c -= a / (b + s)  (:154-155)
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 4) elementwise_kernel(int op, double* __restrict__ c, const double* a,
+                                                                  const double* b, double s, size_t n) {
+  const bool use_c = op != ITSOLV_EW_TIMES && op != ITSOLV_EW_DIVIDE && op != ITSOLV_EW_DIVIDE_NEGATIVE;
+  stream_rows<VEC>(
+      n,
+      [&](size_t p) {
+        double2 cv = use_c ? reinterpret_cast<const double2*>(c)[p] : make_double2(0.0, 0.0);
+        const double2 av = a ? reinterpret_cast<const double2*>(a)[p] : make_double2(0.0, 0.0);
+        const double2 bv = b ? reinterpret_cast<const double2*>(b)[p] : make_double2(0.0, 0.0);
+        cv.x = elementwise_op(op, cv.x, av.x, bv.x, s);
+        cv.y = elementwise_op(op, cv.y, av.y, bv.y, s);
+        reinterpret_cast<double2*>(c)[p] = cv;
+      },
+      [&](size_t i) { c[i] = elementwise_op(op, use_c ? c[i] : 0.0, a ? a[i] : 0.0, b ? b[i] : 0.0, s); });
+}
+
 // r_k[i] = r_k[i] / ((diag[i] - shift_k) + 1e-15): the diagonal is read once for all w residuals
 template <bool VEC>
 __global__ void __launch_bounds__(kThreads, 4) precondition_kernel(const __grid_constant__ PrecondParams prm) {
@@ -359,6 +398,22 @@ int itsolv_shift_f64(itsolv_ctx* ctx, double c, const double* x, double* out, si
   if (n == 0)
     return 0;
   LAUNCH_STREAM(shift_kernel, aligned16(x) && aligned16(out), c, x, out, n);
+  return 0;
+}
+
+int itsolv_elementwise_f64(itsolv_ctx* ctx, int op, double* c, const double* a, const double* b, double scalar, size_t n) {
+  ++ctx->write_epoch;
+  ITSOLV_REQUIRE(op >= ITSOLV_EW_ADD_SCALAR && op <= ITSOLV_EW_DIVIDE_APPEND_NEGATIVE, "itsolv_elementwise_f64: unknown operation");
+  const bool need_a = op >= ITSOLV_EW_TIMES_INPLACE, need_b = op >= ITSOLV_EW_TIMES;
+  ITSOLV_REQUIRE(c != nullptr && (!need_a || a != nullptr) && (!need_b || b != nullptr), "itsolv_elementwise_f64: null argument");
+  if (n == 0)
+    return 0;
+  if (!need_a)
+    a = nullptr;
+  if (!need_b)
+    b = nullptr;
+  CallScope scope(ctx, OP_BLAS1, 8.0 * n * (2 + (need_a ? 1 : 0) + (need_b ? 1 : 0)));
+  LAUNCH_STREAM(elementwise_kernel, aligned16(c) && (!a || aligned16(a)) && (!b || aligned16(b)), op, c, a, b, scalar, n);
   return 0;
 }
 

@@ -3,9 +3,36 @@
 #include <cstring>
 #include <string>
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 #include "common.cuh"
 
 namespace itsolv {
+
+//! ITSOLV_BACKTRACE=1: print the native call stack when the process receives SIGSEGV / SIGABRT (diagnostics on boxes
+//! without a debugger), then let the default action run
+static void backtrace_handler(int sig) {
+  void* frames[64];
+  const int n = backtrace(frames, 64);
+  const char msg[] = "itsolv_b200: fatal signal, native backtrace:\n";
+  if (write(2, msg, sizeof(msg) - 1) < 0) {
+  }
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
+static void install_backtrace_handler() {
+  static bool done = false;
+  const char* e = std::getenv("ITSOLV_BACKTRACE");
+  if (done || !e || !*e || *e == '0')
+    return;
+  done = true;
+  signal(SIGSEGV, backtrace_handler);
+  signal(SIGABRT, backtrace_handler);
+  signal(SIGBUS, backtrace_handler);
+}
 
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
@@ -161,6 +188,7 @@ int ensure_dynamic_smem(itsolv_ctx* ctx, const void* kernel, size_t bytes) {
 }
 
 static int ctx_init(itsolv_ctx* ctx, int device, cudaStream_t stream, bool own) {
+  install_backtrace_handler();
   ITSOLV_CUDA(cudaSetDevice(device));
   ctx->device = device;
   cudaDeviceProp prop;

@@ -191,6 +191,24 @@ def handler_modified_gram_schmidt(ctx, V, thresh=1e-14):
     return V, [nulls[i] for i in range(c)]
 
 
+def handler_distr_array(ctx, op, c, a=None, b=None, scalar=0.0, flags=0, sparse=None):
+    """A member of the container itself (DistrArrayCUDA) through include/itsolv_b200_harness.h:
+    itsolv_handler_distr_array. Returns (c after the call, scalar result, selection dict)."""
+    c = np.ascontiguousarray(c, dtype=np.float64).copy()
+    idx = np.asarray(sorted(sparse) if sparse else [], dtype=np.int64)
+    val = np.asarray([sparse[k] for k in sorted(sparse)] if sparse else [], dtype=np.float64)
+    res = C.c_double()
+    sel_i = np.zeros(max(1, int(flags)), dtype=np.int64)
+    sel_v = np.zeros(max(1, int(flags)))
+    cnt = N.host().itsolv_handler_distr_array(
+        ctx.handle, op, c.size, scalar, int(flags), _dbl(a) if a is not None else None, _dbl(b) if b is not None else None,
+        _dbl(c), idx.size, idx.ctypes.data_as(N.c_int64_p), _dbl(val), C.byref(res), sel_i.ctypes.data_as(N.c_int64_p),
+        _dbl(sel_v))
+    if cnt < 0:
+        raise BackendError(N.host().itsolv_harness_last_error().decode())
+    return c, res.value, {int(sel_i[k]): float(sel_v[k]) for k in range(cnt)}
+
+
 def pack_maps(maps):
     ptr = np.zeros(len(maps) + 1, dtype=np.int32)
     idx, val = [], []

@@ -544,6 +544,66 @@ int itsolv_handler_modified_gram_schmidt(itsolv_ctx* ctx, int nvec, size_t n, do
   return rc ? -1 : count;
 }
 
+static PMap to_map(const int64_t* idx, const double* val, int nnz);
+
+int itsolv_handler_distr_array(itsolv_ctx* ctx, int op, size_t n, double scalar, int flags, const double* a,
+                               const double* b, double* c, int nnz, const int64_t* idx, const double* val,
+                               double* result, int64_t* sel_idx, double* sel_val) {
+  int count = 0;
+  const int rc = guarded([&] {
+    R x = shard_from_host(ctx, n, c);
+    switch (op) {
+    case 0:
+      x.add(shard_from_host(ctx, n, b));
+      break;
+    case 1:
+      x.sub(shard_from_host(ctx, n, b));
+      break;
+    case 2:
+      x.add(scalar);
+      break;
+    case 3:
+      x.sub(scalar);
+      break;
+    case 4:
+      x.recip();
+      break;
+    case 5:
+      x.times(shard_from_host(ctx, n, a));
+      break;
+    case 6:
+      x.times(shard_from_host(ctx, n, a), shard_from_host(ctx, n, b));
+      break;
+    case 7:
+      x.divide(shard_from_host(ctx, n, a), shard_from_host(ctx, n, b), scalar, (flags & 1) != 0, (flags & 2) != 0);
+      break;
+    case 8:
+      x.axpy(scalar, to_map(idx, val, nnz));
+      break;
+    case 9:
+      *result = x.dot(to_map(idx, val, nnz));
+      break;
+    case 10: {
+      itsolv_b200::ArrayHandlerCUDASparse h;
+      const auto sel = h.select_max_dot(size_t(flags), x, to_map(idx, val, nnz));
+      for (const auto& s : sel) {
+        sel_idx[count] = int64_t(s.first);
+        sel_val[count] = s.second;
+        ++count;
+      }
+      break;
+    }
+    case 11:
+      x.zero();
+      break;
+    default:
+      throw std::invalid_argument("itsolv_handler_distr_array: unknown op");
+    }
+    shard_to_host(x, c);
+  });
+  return rc ? -1 : count;
+}
+
 static PMap to_map(const int64_t* idx, const double* val, int nnz) {
   PMap m;
   for (int i = 0; i < nnz; ++i)

@@ -515,9 +515,11 @@ public:
     return mat;
   }
 
-  std::map<size_t, value_type_abs> select_max_dot(size_t, const AL&, const AR&) override {
-    error("ArrayHandlerCUDASparse::select_max_dot() is not provided (used by perturbation theory only)");
-    return {};
+  //! as ArrayHandlerDistrSparse (reference array/ArrayHandlerDistrSparse.h:65-67): the container's own member
+  std::map<size_t, value_type_abs> select_max_dot(size_t n, const AL& x, const AR& y) override {
+    if (n > x.size() || n > y.size())
+      error("ArrayHandlerCUDASparse::select_max_dot() n is too large");
+    return x.select_max_dot(n, y);
   }
 
   std::map<size_t, value_type> select(size_t n, const AL& x, bool max = false, bool ignore_sign = false) override {

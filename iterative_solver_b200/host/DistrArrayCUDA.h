@@ -10,7 +10,10 @@
 // (reference array/DistrArray.h:90-300) where the operation makes sense for device memory.
 #ifndef ITSOLV_B200_HOST_DISTRARRAYCUDA_H
 #define ITSOLV_B200_HOST_DISTRARRAYCUDA_H
+#include <algorithm>
+#include <cmath>
 #include <cstddef>
+#include <functional>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -139,6 +142,100 @@ public:
     check(itsolv_dot_f64(m_ctx, m_data, y.m_data, m_local, &r), "DistrArrayCUDA::dot");
     return r;
   }
+  // the remaining element-wise members of the reference's DistrArray (array/DistrArray.cpp:79-167); not used by the
+  // solvers, present so that the reference's conformance tests (test/array/testDistrArray.h:496-678) apply
+  void add(const DistrArrayCUDA& y) { axpy(1, y); }
+  void sub(const DistrArrayCUDA& y) { axpy(-1, y); }
+  void add(double a) { elementwise(ITSOLV_EW_ADD_SCALAR, nullptr, nullptr, a, "add"); }
+  void sub(double a) { add(-a); }
+  void recip() { elementwise(ITSOLV_EW_RECIP, nullptr, nullptr, 0.0, "recip"); }
+  void times(const DistrArrayCUDA& y) { elementwise(ITSOLV_EW_TIMES_INPLACE, &y, nullptr, 0.0, "times"); }
+  void times(const DistrArrayCUDA& y, const DistrArrayCUDA& z) { elementwise(ITSOLV_EW_TIMES, &y, &z, 0.0, "times"); }
+  //! this[i] (=|+=|-=) (-)y[i] / (z[i] + shift)   (reference DistrArray::_divide, array/DistrArray.cpp:140-167)
+  void divide(const DistrArrayCUDA& y, const DistrArrayCUDA& z, double shift = 0, bool append = false,
+              bool negative = false) {
+    const int op = append ? (negative ? ITSOLV_EW_DIVIDE_APPEND_NEGATIVE : ITSOLV_EW_DIVIDE_APPEND)
+                          : (negative ? ITSOLV_EW_DIVIDE_NEGATIVE : ITSOLV_EW_DIVIDE);
+    elementwise(op, &y, &z, shift, "divide");
+  }
+  void zero() { fill(0.0); }
+  //! this[index] += a * value for the entries of the sparse array that this rank owns (reference DistrArray.cpp:419-437)
+  void axpy(double a, const std::map<size_t, double>& y) {
+    if (y.empty())
+      return;
+    std::vector<int32_t> ptr{0, int32_t(y.size())};
+    std::vector<int64_t> idx;
+    std::vector<double> val;
+    for (const auto& e : y) {
+      idx.push_back(int64_t(e.first));
+      val.push_back(e.second);
+    }
+    double* py = data();
+    check(itsolv_sparse_gemm_outer_f64(m_ctx, &a, 1, 1, ptr.data(), idx.data(), val.data(), &py, m_local, m_start),
+          "DistrArrayCUDA::axpy(sparse)");
+  }
+  //! sum over the entries of the sparse array of this[index] * value (reference DistrArray.cpp:439-465)
+  double dot(const std::map<size_t, double>& y) const {
+    if (y.empty())
+      return 0.0;
+    std::vector<int32_t> ptr{0, int32_t(y.size())};
+    std::vector<int64_t> idx;
+    std::vector<double> val;
+    for (const auto& e : y) {
+      idx.push_back(int64_t(e.first));
+      val.push_back(e.second);
+    }
+    const double* px = m_data;
+    double d = 0;
+    check(itsolv_sparse_gemm_inner_f64(m_ctx, &px, 1, m_local, m_start, 1, ptr.data(), idx.data(), val.data(), &d),
+          "DistrArrayCUDA::dot(sparse)");
+    return d;
+  }
+  //! the elements at the given global indices, on every rank (each entry is owned by one rank; the others add zero)
+  std::vector<double> gather(const std::vector<size_t>& indices) const {
+    std::vector<double> out(indices.size(), 0.0);
+    if (indices.empty())
+      return out;
+    std::vector<int32_t> ptr(indices.size() + 1);
+    std::vector<int64_t> idx(indices.size());
+    std::vector<double> one(indices.size(), 1.0);
+    for (size_t e = 0; e < indices.size(); ++e) {
+      ptr[e] = int32_t(e);
+      idx[e] = int64_t(indices[e]);
+    }
+    ptr[indices.size()] = int32_t(indices.size());
+    const double* px = m_data;
+    check(itsolv_sparse_gemm_inner_f64(m_ctx, &px, 1, m_local, m_start, int(indices.size()), ptr.data(), idx.data(),
+                                       one.data(), out.data()),
+          "DistrArrayCUDA::gather");
+    return out;
+  }
+  /*!
+   * The n entries of the sparse array with the largest |this[index] * value| (reference DistrArray.cpp:248-262 with
+   * util::select_max_dot_iter_sparse, array/util/select_max_dot.h:60-83: a min-heap of (value, index) pairs keeps the n
+   * largest pairs in lexicographic order).
+   */
+  std::map<size_t, double> select_max_dot(size_t n, const std::map<size_t, double>& y) const {
+    if (!y.empty() && size() < y.rbegin()->first + 1)
+      throw std::runtime_error("DistrArrayCUDA::select_max_dot: sparse array x is too large");
+    if (n > size() || n > y.size())
+      throw std::runtime_error("DistrArrayCUDA::select_max_dot: n is too large");
+    std::vector<size_t> indices;
+    for (const auto& e : y)
+      indices.push_back(e.first);
+    const auto x = gather(indices);
+    std::vector<std::pair<double, size_t>> pairs;
+    size_t e = 0;
+    for (const auto& item : y) {
+      pairs.emplace_back(std::abs(x[e] * item.second), item.first);
+      ++e;
+    }
+    std::sort(pairs.begin(), pairs.end(), std::greater<std::pair<double, size_t>>());
+    std::map<size_t, double> result;
+    for (size_t i = 0; i < n && i < pairs.size(); ++i)
+      result.emplace(pairs[i].second, pairs[i].first);
+    return result;
+  }
   std::map<size_t, double> select(size_t n, bool max = false, bool ignore_sign = false) const {
     return select_impl(n, nullptr, max, ignore_sign);
   }
@@ -187,6 +284,14 @@ public:
   }
 
 private:
+  void elementwise(int op, const DistrArrayCUDA* a, const DistrArrayCUDA* b, double scalar, const char* name) {
+    if (a)
+      require_compatible(*a, name);
+    if (b)
+      require_compatible(*b, name);
+    check(itsolv_elementwise_f64(m_ctx, op, data(), a ? a->m_data : nullptr, b ? b->m_data : nullptr, scalar, m_local),
+          "DistrArrayCUDA: element-wise operation");
+  }
   std::map<size_t, double> select_impl(size_t n, const double* y, bool max, bool ignore_sign) const {
     if (n > m_dimension)
       throw std::runtime_error("DistrArrayCUDA::select: n is too large");
