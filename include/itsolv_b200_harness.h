@@ -119,6 +119,11 @@ int itsolv_harness_problem_create(struct itsolv_ctx* ctx, const itsolv_solve_spe
                                   itsolv_harness_problem** problem);
 int itsolv_harness_problem_solve(itsolv_harness_problem* problem, const itsolv_solve_spec* spec,
                                  itsolv_solve_result* result, double* solutions);
+/* As itsolv_harness_problem_solve, but the solution vectors stay on the GPU: *device_solutions receives nroots * n_local
+ * doubles taken from the context's pool (itsolv_alloc) AFTER the solver has finished, so they do not add to the solver's
+ * high-water mark; the caller releases them with itsolv_free. */
+int itsolv_harness_problem_solve_device(itsolv_harness_problem* problem, const itsolv_solve_spec* spec,
+                                        itsolv_solve_result* result, double** device_solutions);
 void itsolv_harness_problem_destroy(itsolv_harness_problem* problem);
 
 size_t itsolv_harness_trace_entries(void);

@@ -157,6 +157,8 @@ HARNESS_API = {
     "itsolv_harness_problem_create": (C.c_int, [C.c_void_p, C.POINTER(SolveSpec), c_int64_p, c_int32_p, c_double_p,
                                                 c_double_p, c_void_pp]),
     "itsolv_harness_problem_solve": (C.c_int, [C.c_void_p, C.POINTER(SolveSpec), C.POINTER(SolveResult), c_double_p]),
+    "itsolv_harness_problem_solve_device": (C.c_int, [C.c_void_p, C.POINTER(SolveSpec), C.POINTER(SolveResult),
+                                                      c_void_pp]),
     "itsolv_harness_problem_destroy": (None, [C.c_void_p]),
     "itsolv_harness_trace_entries": (C.c_size_t, []),
     "itsolv_harness_trace_values": (C.c_size_t, []),

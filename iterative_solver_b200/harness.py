@@ -94,6 +94,14 @@ class Problem:
         _hcheck(N.host().itsolv_harness_problem_solve(self.handle, C.byref(spec), C.byref(res), out))
         return res
 
+    def solve_device(self, spec: N.SolveSpec):
+        """solve and leave the solution vectors on the GPU: returns (result, device address of nroots x n_local doubles
+        from the context's pool, to be released with Context.free)"""
+        res = N.SolveResult()
+        out = C.c_void_p()
+        _hcheck(N.host().itsolv_harness_problem_solve_device(self.handle, C.byref(spec), C.byref(res), C.byref(out)))
+        return res, int(out.value or 0)
+
     def close(self):
         if self.handle:
             N.host().itsolv_harness_problem_destroy(self.handle)

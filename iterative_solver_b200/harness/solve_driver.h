@@ -53,7 +53,9 @@ inline double now_seconds() {
  *   using R;                                          container type
  *   std::shared_ptr<ArrayHandlers<R,R,P>> handlers(); handler set
  *   R make_vector();                                  zero vector of the problem's global length
- *   void export_local(const R&, double*);             this rank's rows to host memory
+ *   void export_local(const R&, double*);             this rank's rows to the caller's memory
+ *   double* solutions_target(double* given, size_t count);  where the solutions go: `given`, or memory the backend
+ *                                                     provides at that moment (after the solver has finished)
  *   size_t n_local();
  *   ProblemT& problem();                              Problem<R> with make_rhs(k, R&), seconds_action, seconds_precond
  *   void synchronize();                               wait for outstanding device work (no-op on the host)
@@ -112,6 +114,7 @@ int run_solve(const itsolv_solve_spec& spec, Backend& backend, itsolv_solve_resu
     res.seconds_precond = problem.seconds_precond;
   };
   auto export_solutions = [&](auto& solver) {
+    solutions = backend.solutions_target(solutions, size_t(nroots) * backend.n_local());
     if (!solutions)
       return;
     const size_t nloc = backend.n_local();
@@ -187,6 +190,7 @@ int run_solve(const itsolv_solve_spec& spec, Backend& backend, itsolv_solve_resu
     backend.timer_start();
     const bool ok = solver.solve(parameters[0], actions[0], problem, false);
     finish(solver, ok, t0);
+    solutions = backend.solutions_target(solutions, backend.n_local());
     if (solutions) {
       solver.solution(parameters[0], actions[0]);
       backend.export_local(parameters[0], solutions);

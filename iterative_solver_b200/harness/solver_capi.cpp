@@ -268,6 +268,15 @@ struct DeviceBackend {
     return v;
   }
   void export_local(const R& v, double* out) { v.download(out); }
+  //! itsolv_harness_problem_solve_device: the solutions stay on the GPU, in memory taken from the context's pool only now,
+  //! after the solver has finished (its high-water mark is over), and handed to the caller
+  double** late_solutions = nullptr;
+  double* solutions_target(double* given, size_t count) {
+    if (given || !late_solutions)
+      return given;
+    check(itsolv_alloc(ctx, count, late_solutions), "solutions allocation");
+    return *late_solutions;
+  }
   size_t n_local() { return prob.nloc; }
   DeviceProblem& problem() { return prob; }
   void synchronize() { check(itsolv_ctx_synchronize(ctx), "synchronize"); }
@@ -381,6 +390,23 @@ int itsolv_harness_problem_solve(itsolv_harness_problem* p, const itsolv_solve_s
     DeviceBackend backend(p->ctx, *p->problem, size_t(spec->n));
     itsolv_ctx_reset_counters(p->ctx);
     itsolv_b200::harness::run_solve(*spec, backend, *result, solutions);
+    fill_counters(p->ctx, result);
+  });
+}
+
+int itsolv_harness_problem_solve_device(itsolv_harness_problem* p, const itsolv_solve_spec* spec,
+                                        itsolv_solve_result* result, double** device_solutions) {
+  return guarded([&] {
+    if (spec->n != p->problem->n || spec->half_bandwidth != p->problem->b || spec->problem != p->problem->kind)
+      throw std::invalid_argument("itsolv_harness_problem_solve_device: spec does not describe this operator");
+    if (!device_solutions)
+      throw std::invalid_argument("itsolv_harness_problem_solve_device: null argument");
+    *device_solutions = nullptr;
+    p->problem->rhs_kind = spec->rhs_kind;
+    DeviceBackend backend(p->ctx, *p->problem, size_t(spec->n));
+    backend.late_solutions = device_solutions;
+    itsolv_ctx_reset_counters(p->ctx);
+    itsolv_b200::harness::run_solve(*spec, backend, *result, nullptr);
     fill_counters(p->ctx, result);
   });
 }

@@ -130,9 +130,9 @@ class DeviceRows:
     """nroots x nloc doubles from the context's own pool (so that they count in its high-water mark and need no host
     memory); row(k) is a torch view of the k-th vector"""
 
-    def __init__(self, ctx, nroots, nloc):
+    def __init__(self, ctx, nroots, nloc, address=0):
         self.ctx, self.nroots, self.nloc = ctx, nroots, nloc
-        self.address = ctx.alloc(nroots * max(nloc, 1))
+        self.address = address or ctx.alloc(nroots * max(nloc, 1))
 
     def row(self, k):
         import torch
@@ -225,15 +225,19 @@ def run(ctx, name, rank, world, n=None, overrides=None, fused=None, verify=True,
     nroots = 1 if kind == "diis" else kw["nroots"]
     ctx.set_profiling(True)
     ctx.mem_usage(reset_peak=True)
-    # the solution vectors stay on the GPU, in memory of the context's pool allocated BEFORE the solve: the high-water mark
-    # below is then what the whole run needs, and nothing of size n goes through the host
-    sol = DeviceRows(ctx, nroots, nloc) if verify else None
+    # the solution vectors stay on the GPU, in memory of the context's pool that the harness takes only after the solver
+    # has finished (itsolv_harness_problem_solve_device): nothing of size n goes through the host, and the high-water mark
+    # below is the solver's own or (vectors alive at the end + solutions), whichever is larger
+    sol = None
     problem = H.Problem(ctx, spec)
     t0 = time.perf_counter()
     res = problem.solve(spec)
     cold_s = time.perf_counter() - t0
-    if warm or verify:
-        res = problem.solve(spec, solutions=sol.address if sol else None)
+    if verify:
+        res, address = problem.solve_device(spec)
+        sol = DeviceRows(ctx, nroots, nloc, address)
+    elif warm:
+        res = problem.solve(spec)
     problem.close()
     live, peak = ctx.mem_usage()
     ctx.set_profiling(False)
