@@ -119,13 +119,26 @@ class ClockSampler:
                 pass
             self.stop_flag.wait(0.004 if self.nvml else 0.2)
 
+    def sample_now(self):
+        """one sample from the calling thread (the edges of the timed region: an NVML query takes tens of milliseconds
+        while kernels are being launched, so the background thread gets few samples out of a 0.2 s region)"""
+        try:
+            if self.nvml:
+                self.sample_nvml()
+            else:
+                self.sample_smi()
+        except Exception:
+            pass
+
     def __enter__(self):
+        self.sample_now()
         self.thread.start()
         return self
 
     def __exit__(self, *a):
         self.stop_flag.set()
         self.thread.join(timeout=6)
+        self.sample_now()
 
     def summary(self):
         if not self.samples:
@@ -218,6 +231,7 @@ def main():
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
+    numa = D.bind_host_to_device(local_rank)  # before any pinned host buffer is allocated
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = pkg.Context(local_rank)
@@ -330,7 +344,8 @@ def main():
         h2d = row_ptr.nbytes + col.nbytes + val.nbytes + diag.nbytes
         d2h = sol_np.nbytes + 8 * args.roots * 2
         e2e = {"value": world * e_iter / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "steps": e_steps, "ms_per_step": e_ms / e_steps,
+               "d2h_bytes_per_step": int(d2h), "steps": e_steps, "ms_per_step": e_ms / e_steps, "host_binding": numa,
+               "h2d_gbs_per_gpu_implied": h2d / max(e_ms / e_steps * 1e-3 - ms_max / args.steps * 1e-3, 1e-9) / 1e9,
                "api": "itsolv_harness_problem_create(host CSR) + itsolv_harness_problem_solve(host solutions)"}
         del pinned, sol
 

@@ -94,6 +94,10 @@ int itsolv_comm_size(itsolv_ctx* ctx);
 int itsolv_comm_barrier(itsolv_ctx* ctx);
 /* in-place sum / max of a small HOST array over all ranks (through a device staging buffer) */
 int itsolv_comm_allreduce_host(itsolv_ctx* ctx, double* values, size_t count, int op_max);
+/* the same for all w vectors of a working set at once: out[k][0..b) receives the last b rows of x[k] on rank-1, out[k][b..2b)
+ * the first b rows of x[k] on rank+1 (zeros at the ends of the global vector). One launch with stores into the
+ * neighbours' exchange buffers over NVLink when they are mapped (itsolv_comm_p2p_import), else w NCCL exchanges. */
+int itsolv_comm_halo_exchange_multi(itsolv_ctx* ctx, const double* const* x, int w, size_t n_local, int b, double* out);
 /* exchange of `count` doubles with the neighbouring ranks (harness halo): send_lo goes to rank-1, send_hi to rank+1 */
 int itsolv_comm_halo_exchange(itsolv_ctx* ctx, const double* send_lo, const double* send_hi, double* recv_lo,
                               double* recv_hi, size_t count);

@@ -94,6 +94,7 @@ KERNEL_API = {
     "itsolv_comm_size": (C.c_int, [C.c_void_p]),
     "itsolv_comm_barrier": (C.c_int, [C.c_void_p]),
     "itsolv_comm_allreduce_host": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t, C.c_int]),
+    "itsolv_comm_halo_exchange_multi": (C.c_int, [C.c_void_p, c_void_pp, C.c_int, C.c_size_t, C.c_int, C.c_void_p]),
     "itsolv_comm_halo_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "itsolv_distribution": (None, [C.c_size_t, C.c_int, c_int64_p]),
     "itsolv_fill_f64": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_size_t]),

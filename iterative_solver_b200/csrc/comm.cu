@@ -11,6 +11,8 @@
 #include "common.cuh"
 #include "gi_finalize.cuh"
 
+#define ITSOLV_MAX_ROOTS_HALO 64
+
 namespace itsolv {
 
 // minimal NCCL surface (ABI-stable since NCCL 2.x)
@@ -75,6 +77,7 @@ static NcclApi* nccl_api() {
 }
 
 constexpr size_t kPeerSlotDoubles = size_t(ITSOLV_MAX_PANEL) * ITSOLV_MAX_PANEL;
+constexpr size_t kHaloSlotDoubles = 4096; // boundary rows of a whole working set: w * b <= 4096
 
 struct Comm {
   ncclComm_t comm = nullptr;
@@ -86,7 +89,13 @@ struct Comm {
   bool peers_ready = false;
   unsigned int* d_error = nullptr;        // sticky failure word of the fused all-reduce (GiPeers::error)
   unsigned long long timeout_ns = 600ull * 1000000000ull;
-  size_t exchange_bytes() const { return 2 * size_t(size) * kPeerSlotDoubles * sizeof(double) + 2 * size_t(size) * 8 + 64; }
+  // layout of an exchange buffer: all-reduce slots, all-reduce sequence words, then the halo area of the harness operator
+  // ([parity][side: 0 = rows from the rank below, 1 = from the rank above][kHaloSlotDoubles]) and its sequence words
+  size_t allreduce_bytes() const { return 2 * size_t(size) * kPeerSlotDoubles * sizeof(double) + 2 * size_t(size) * 8 + 64; }
+  size_t halo_data_offset() const { return (allreduce_bytes() + 255) & ~size_t(255); }
+  size_t halo_flag_offset() const { return halo_data_offset() + 4 * kHaloSlotDoubles * sizeof(double); }
+  size_t exchange_bytes() const { return halo_flag_offset() + 4 * 8 + 64; }
+  unsigned long long halo_seq = 0;
 };
 
 #define ITSOLV_NCCL(call)                                                                                              \
@@ -114,6 +123,72 @@ bool comm_peers(itsolv_ctx* ctx, GiPeers* peers) {
     peers->flags[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->peer_base[r]) + data_bytes);
   }
   return true;
+}
+
+struct HaloParams {
+  const double* x[ITSOLV_MAX_ROOTS_HALO];
+  double* out;              // [w][2 b]: per vector the b rows from below, then the b rows from above
+  double* below_data;       // halo area of rank - 1 (null at the lower end): my first rows go to its side 1
+  double* above_data;       // halo area of rank + 1 (null at the upper end): my last rows go to its side 0
+  unsigned long long* below_flags;
+  unsigned long long* above_flags;
+  double* my_data;
+  unsigned long long* my_flags;
+  unsigned int* error;
+  unsigned long long timeout_ns, seq;
+  size_t nloc;
+  int w, b;
+};
+
+/*!
+ * Boundary rows of all w vectors of a working set to the two neighbouring shards in one launch: stores into the
+ * neighbours' halo areas over NVLink peer memory, a sequence word per side, then the rows the neighbours stored here are
+ * copied to `out`. One CTA; replaces w grouped ncclSend/ncclRecv pairs per operator application.
+ */
+__global__ void __launch_bounds__(256) halo_exchange_kernel(const __grid_constant__ HaloParams p) {
+  const int tid = threadIdx.x;
+  const int parity = int(p.seq & 1ull);
+  const int cnt = p.w * p.b;
+  __shared__ int s_ok;
+  if (tid == 0)
+    s_ok = *reinterpret_cast<volatile unsigned int*>(p.error) == 0u ? 1 : 0;
+  __syncthreads();
+  if (s_ok) {
+    for (int e = tid; e < cnt; e += blockDim.x) {
+      const int k = e / p.b, j = e % p.b;
+      if (p.below_data)
+        p.below_data[(size_t(parity) * 2 + 1) * kHaloSlotDoubles + e] = p.x[k][j];
+      if (p.above_data)
+        p.above_data[(size_t(parity) * 2 + 0) * kHaloSlotDoubles + e] = p.x[k][p.nloc - size_t(p.b) + j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0 && p.below_flags)
+      *reinterpret_cast<volatile unsigned long long*>(p.below_flags + parity * 2 + 1) = p.seq;
+    if (tid == 1 && p.above_flags)
+      *reinterpret_cast<volatile unsigned long long*>(p.above_flags + parity * 2 + 0) = p.seq;
+    // wait for the rows of the neighbours: side 0 is written by the rank below, side 1 by the rank above
+    if (tid < 2 && (tid == 0 ? p.below_data != nullptr : p.above_data != nullptr)) {
+      const unsigned long long* mine = p.my_flags + parity * 2 + tid;
+      const unsigned long long t0 = global_timer_ns();
+      unsigned int spins = 0;
+      while (ld_volatile_sys(mine) != p.seq) {
+        if (p.timeout_ns != 0ull && (++spins & 0x3FFu) == 0u && global_timer_ns() - t0 > p.timeout_ns) {
+          s_ok = 0;
+          *reinterpret_cast<volatile unsigned int*>(p.error) = 1u;
+          break;
+        }
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+  }
+  for (int e = tid; e < cnt; e += blockDim.x) {
+    const int k = e / p.b, j = e % p.b;
+    double* o = p.out + size_t(k) * 2 * p.b;
+    o[j] = (s_ok && p.below_data) ? __ldcv(p.my_data + (size_t(parity) * 2 + 0) * kHaloSlotDoubles + e) : 0.0;
+    o[p.b + j] = (s_ok && p.above_data) ? __ldcv(p.my_data + (size_t(parity) * 2 + 1) * kHaloSlotDoubles + e) : 0.0;
+  }
 }
 
 void comm_destroy(itsolv_ctx* ctx) {
@@ -268,6 +343,48 @@ int itsolv_comm_allreduce_host(itsolv_ctx* ctx, double* values, size_t count, in
 int itsolv_comm_barrier(itsolv_ctx* ctx) {
   double one = 1;
   return itsolv_comm_allreduce_host(ctx, &one, 1, 0);
+}
+
+int itsolv_comm_halo_exchange_multi(itsolv_ctx* ctx, const double* const* x, int w, size_t nloc, int b, double* out) {
+  ++ctx->write_epoch;
+  if (!ctx->comm || ctx->comm->size == 1 || b <= 0 || w <= 0)
+    return 0;
+  Comm* c = ctx->comm;
+  ITSOLV_REQUIRE(nloc >= size_t(b), "itsolv_comm_halo_exchange_multi: shard shorter than the half bandwidth");
+  if (c->peers_ready && ctx->opt_p2p_allreduce >= 0 && w <= ITSOLV_MAX_ROOTS_HALO &&
+      size_t(w) * size_t(b) <= kHaloSlotDoubles) {
+    HaloParams p{};
+    for (int k = 0; k < w; ++k)
+      p.x[k] = x[k];
+    p.out = out;
+    auto data_of = [&](int r) { return reinterpret_cast<double*>(static_cast<char*>(c->peer_base[r]) + c->halo_data_offset()); };
+    auto flags_of = [&](int r) {
+      return reinterpret_cast<unsigned long long*>(static_cast<char*>(c->peer_base[r]) + c->halo_flag_offset());
+    };
+    p.below_data = c->rank > 0 ? data_of(c->rank - 1) : nullptr;
+    p.below_flags = c->rank > 0 ? flags_of(c->rank - 1) : nullptr;
+    p.above_data = c->rank < c->size - 1 ? data_of(c->rank + 1) : nullptr;
+    p.above_flags = c->rank < c->size - 1 ? flags_of(c->rank + 1) : nullptr;
+    p.my_data = data_of(c->rank);
+    p.my_flags = flags_of(c->rank);
+    p.error = c->d_error;
+    p.timeout_ns = c->timeout_ns;
+    p.seq = ++c->halo_seq;
+    p.nloc = nloc;
+    p.w = w;
+    p.b = b;
+    halo_exchange_kernel<<<1, 256, 0, ctx->stream>>>(p);
+    ITSOLV_CUDA(cudaGetLastError());
+    ctx->counters.launches += 1;
+    return 0;
+  }
+  // no peer mapping: one grouped ncclSend/ncclRecv exchange per vector
+  for (int k = 0; k < w; ++k) {
+    double* h = out + size_t(k) * 2 * size_t(b);
+    if (itsolv_comm_halo_exchange(ctx, x[k], x[k] + (nloc - size_t(b)), h, h + b, size_t(b)))
+      return 1;
+  }
+  return 0;
 }
 
 int itsolv_comm_halo_exchange(itsolv_ctx* ctx, const double* send_lo, const double* send_hi, double* recv_lo,

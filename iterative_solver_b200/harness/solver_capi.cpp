@@ -128,9 +128,9 @@ public:
     }
     const double *lo = nullptr, *hi = nullptr;
     if (nranks > 1 && b > 0) {
-      // b boundary rows travel to the neighbouring shards (ncclSend/ncclRecv over NVLink)
-      check(itsolv_comm_halo_exchange(ctx, v.data(), v.data() + (nloc - size_t(b)), halo, halo + b, size_t(b)),
-            "halo exchange");
+      // b boundary rows travel to the neighbouring shards (peer stores over NVLink, or ncclSend/ncclRecv)
+      const double* xv = v.data();
+      check(itsolv_comm_halo_exchange_multi(ctx, &xv, 1, nloc, b, halo), "halo exchange");
       lo = rank > 0 ? halo : nullptr;
       hi = rank < nranks - 1 ? halo + b : nullptr;
     }
@@ -153,9 +153,12 @@ public:
       for (size_t k = 0; k < w; ++k) {
         x[k] = parameters[k].get().data();
         y[k] = actions[k].get().data();
-        if (nranks > 1 && b > 0) {
+      }
+      if (nranks > 1 && b > 0) {
+        // boundary rows of the whole working set in one exchange
+        check(itsolv_comm_halo_exchange_multi(ctx, x.data(), int(w), nloc, b, halos.data()), "halo exchange");
+        for (size_t k = 0; k < w; ++k) {
           double* h = halos.data() + 2 * size_t(b) * k;
-          check(itsolv_comm_halo_exchange(ctx, x[k], x[k] + (nloc - size_t(b)), h, h + b, size_t(b)), "halo exchange");
           lo[k] = rank > 0 ? h : nullptr;
           hi[k] = rank < nranks - 1 ? h + b : nullptr;
         }

@@ -25,8 +25,10 @@
 #define ITSOLV_B200_HOST_FUSEDDAVIDSON_H
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <iostream>
 #include <limits>
+#include <list>
 #include <map>
 #include <numeric>
 #include <stdexcept>
@@ -127,8 +129,34 @@ public:
       for (size_t j = 0; j < dims.nX; ++j)
         Sxq(j, i) = Sqx(i, j);
     }
+    if (std::getenv("ITSOLV_CHECK_BLOCKS")) { // diagnostics: the same blocks from the reference's own routine
+      auto ref = its::subspace::xspace::update_qspace_data(params, actions, this->cparamsp(), qparams, qactions, dparams,
+                                                           dactions, its::cwrap(this->m_rhs), dims, handlers,
+                                                           *this->m_logger, this->m_hermitian, ada);
+      report_block_difference("update_qspace", ref, nd, {EqnData::S, EqnData::H});
+    }
     this->qspace.update(params, actions, nd.qq, nd.qx, nd.xq, dims, this->data);
     this->update_dimensions();
+  }
+
+  //! diagnostics (ITSOLV_CHECK_BLOCKS): largest difference between two sets of new equation-data blocks
+  static void report_block_difference(const char* where, const its::subspace::xspace::NewData& a,
+                                      const its::subspace::xspace::NewData& b,
+                                      std::initializer_list<its::subspace::EqnData> which) {
+    auto diff = [](const Matrix<double>& x, const Matrix<double>& y) {
+      if (x.rows() != y.rows() || x.cols() != y.cols())
+        return -1.0;
+      double d = 0;
+      for (size_t i = 0; i < x.rows(); ++i)
+        for (size_t j = 0; j < x.cols(); ++j)
+          d = std::max(d, std::abs(x(i, j) - y(i, j)));
+      return d;
+    };
+    std::cerr << where << ": largest absolute block differences";
+    for (auto e : which)
+      std::cerr << " [" << int(e) << "] qq " << diff(a.qq.at(e), b.qq.at(e)) << " qx " << diff(a.qx.at(e), b.qx.at(e))
+                << " xq " << diff(a.xq.at(e), b.xq.at(e));
+    std::cerr << std::endl;
   }
 
   /*!
@@ -191,6 +219,14 @@ public:
         for (size_t j = 0; j < nPQ; ++j)
           ov.xq[EqnData::S](j, i) = ov.qx[EqnData::S](i, j);
     }
+    if (std::getenv("ITSOLV_CHECK_BLOCKS")) { // diagnostics: the same blocks from the reference's own routines
+      auto rov = xsp::update_dspace_overlap_data(pparams, qparams, dparams, its::cwrap(this->m_rhs), handlers.qp(),
+                                                 handlers.qq(), *this->m_logger);
+      auto ract = xsp::update_dspace_action_data(pparams, qparams, qactions, dparams, dactions, handlers.qp(),
+                                                 handlers.qq(), *this->m_logger);
+      report_block_difference("update_dspace overlap", rov, ov, {EqnData::S});
+      report_block_difference("update_dspace action", ract, act, {EqnData::H});
+    }
     xsp::copy_dspace_eqn_data(ov, this->data, EqnData::S, dim);
     xsp::copy_dspace_eqn_data(act, this->data, EqnData::H, dim);
     this->data[EqnData::rhs].resize({dim.nX, dim.nRHS});
@@ -225,6 +261,27 @@ public:
   using Base::solve;
   //! false: solve() is the reference's own loop and only add_vector / solution / end_iteration are batched
   void set_fuse_solve(bool on) { m_fuse_solve = on; }
+  /*!
+   * Diagnostics: |a - A q| / |a| for every (parameter, action) pair the subspace holds (Q first, then D). The algorithm
+   * relies on the stored actions being the operator applied to the stored parameters; the solver's own error estimates
+   * cannot see a violation.
+   */
+  std::vector<double> pair_consistency(const its::Problem<R>& problem) {
+    std::vector<double> out;
+    auto& xs = *this->m_xspace;
+    auto check_set = [&](const CVecRef<R>& par, const CVecRef<R>& act) {
+      for (size_t i = 0; i < par.size(); ++i) {
+        R ap(par[i].get()), diff(act[i].get());
+        problem.action(CVecRef<R>{par[i]}, VecRef<R>{std::ref(ap)});
+        diff.axpy(-1.0, ap);
+        out.push_back(std::sqrt(std::abs(diff.dot(diff)) / std::max(std::abs(act[i].get().dot(act[i].get())), 1e-300)));
+      }
+    };
+    check_set(xs.cparamsq(), xs.cactionsq());
+    out.push_back(-1.0); // separator between Q and D
+    check_set(xs.cparamsd(), xs.cactionsd());
+    return out;
+  }
   /*!
    * The reference's one-call driver (IterativeSolverTemplate.h:322-408), statement for statement, with three changes that
    * do not alter what is computed:
@@ -308,6 +365,12 @@ public:
       }
       if (this->m_verbosity >= its::Verbosity::Iteration)
         this->report();
+    }
+    if (std::getenv("ITSOLV_CHECK_PAIRS")) {
+      std::cerr << "pair consistency |a - A q|/|a| (Q | D):";
+      for (double v : pair_consistency(problem))
+        std::cerr << (v < 0 ? std::string(" |") : " " + its::Logger::scientific(v));
+      std::cerr << std::endl;
     }
     if (this->m_verbosity == its::Verbosity::Summary)
       this->report();
@@ -607,7 +670,15 @@ protected:
       auto wdparams = its::wrap(dparams);
       auto wdactions = its::wrap(dactions);
       xspace.update_dspace(wdparams, wdactions);
+      const auto eigenvalues_before = subspace_solver.eigenvalues();
       subspace_solver.solve(xspace, solutions.rows());
+      if (std::getenv("ITSOLV_CHECK_BLOCKS")) {
+        double worst = 0;
+        for (size_t i = 0; i < eigenvalues_before.size() && i < subspace_solver.eigenvalues().size(); ++i)
+          worst = std::max(worst, std::abs(eigenvalues_before[i] - subspace_solver.eigenvalues()[i]));
+        std::cerr << "eigenvalue change due to the new D space: " << worst << " (nQ " << xspace.dimensions().nQ << ", nD "
+                  << xspace.dimensions().nD << ")" << std::endl;
+      }
     }
     auto wresidual = its::wrap(residuals.begin(), residuals.begin() + this->working_set().size());
     const auto dims = xspace.dimensions();
@@ -655,18 +726,63 @@ protected:
         return GP(i, x - dims.oP);
       return x >= dims.oD ? G(i, nN0 + nQ + (x - dims.oD)) : G(i, nN0 + (x - dims.oQ));
     };
-    for (size_t i = 0; i < nN; ++i) {
-      for (size_t j = 0; j <= i; ++j)
-        ov(nX + i, nX + j) = ov(nX + j, nX + i) = G(i, j);
-      for (size_t x = 0; x < nX; ++x)
-        ov(nX + i, x) = ov(x, nX + i) = g0(i, x);
+    auto fill_ov = [&]() {
+      for (size_t i = 0; i < nN; ++i) {
+        for (size_t j = 0; j <= i; ++j)
+          ov(nX + i, nX + j) = ov(nX + j, nX + i) = G(i, j);
+        for (size_t x = 0; x < nX; ++x)
+          ov(nX + i, x) = ov(x, nX + i) = g0(i, x);
+      }
+    };
+    fill_ov();
+    /*
+     * When two or more of the new vectors lie in the span of P+Q+D (preconditioned residuals of nearly converged roots:
+     * they are dominated by the root's own Ritz vector), the overlap matrix has a null space of that dimension, the null
+     * vectors the redundancy test looks at (reference propose_rspace.h:482-512) are an arbitrary basis of it, and WHICH
+     * vectors the test drops follows the rounding pattern of the overlaps. The reference measures them on the normalised
+     * vectors as stored, and that pattern (the rounding of every element by the scaling) is what its decisions follow,
+     * identically on the CPU and on these handlers. Overlaps of the unscaled vectors multiplied by the factors on the host
+     * are the same numbers to 4e-16, but decide differently; the run then keeps the wrong member of such a set, the D space
+     * built from it no longer reproduces the converged roots beyond ~1e-7, and they re-enter the working set
+     * (profiles/notes_r02.md). So in that case - and only then - the vectors are normalised first and the overlaps measured
+     * again, exactly as the reference does; otherwise the scaling stays folded into the projection kernel.
+     */
+    bool remeasured = false;
+    auto null_space = [&]() {
+      return its::svd_system(ov.rows(), ov.cols(), molpro::linalg::array::Span<double>(&ov(0, 0), ov.size()),
+                             fused_svd_thresh(), true);
+    };
+    auto svd = nN > 0 ? null_space() : std::list<its::SVD<double>>{};
+    if (nP == 0 && svd.size() > 1) {
+      m_dense->scal_batch(factor, wresidual);
+      factor.assign(nN, 1.0);
+      G = m_dense->gemm_inner(its::cwrap(wresidual), cols);
+      fill_ov();
+      remeasured = true;
+      svd = null_space();
+    }
+    // the selection rule of redundant_parameters (reference propose_rspace.h:496-510) on that null space: for every
+    // null vector, the remaining new vector with the largest component
+    std::vector<int> redundant;
+    {
+      std::vector<int> rspace_indices(nN);
+      std::iota(rspace_indices.begin(), rspace_indices.end(), 0);
+      for (const auto& singular_system : svd) {
+        if (rspace_indices.empty())
+          break;
+        size_t imax = 0;
+        for (size_t t = 1; t < rspace_indices.size(); ++t)
+          if (std::abs(singular_system.v.at(nX + rspace_indices[t])) >
+              std::abs(singular_system.v.at(nX + rspace_indices[imax])))
+            imax = t;
+        redundant.push_back(rspace_indices[imax]);
+        rspace_indices.erase(rspace_indices.begin() + imax);
+      }
     }
     // Projection against P, Q, D: sequential coefficients by forward substitution, applied in one expansion that also
-    // multiplies the normalisation factor in. The coefficients of a vector depend on that vector alone, so the expansion is
-    // launched for ALL new vectors BEFORE the redundancy test: the host's SVD below then runs while the kernel does
-    // (SURVEY.md section 8 f2). A vector the test drops is discarded after having been projected, which changes nothing
-    // for the others (each column of the expansion is its own chain of operations).
-    bool scaled = nP > 0;
+    // multiplies the normalisation factor in. It is applied to all new vectors, also those the redundancy test has marked
+    // (they are discarded right after; each column of the expansion is its own chain of operations).
+    bool scaled = nP > 0 || remeasured;
     if (nN > 0 && nX > 0) {
       Matrix<double> c({nX, nN});
       for (size_t j = 0; j < nN; ++j)
@@ -700,7 +816,6 @@ protected:
     }
     if (!scaled && nN > 0)
       m_dense->scal_batch(factor, wresidual);
-    auto redundant = det::redundant_parameters(ov, nX, nN, fused_svd_thresh(), logger);
     its::util::delete_parameters(redundant, wresidual);
     nN = wresidual.size();
     // R-R modified Gram-Schmidt: one pass per pivot, which scales the pivot, updates the later vectors and returns the

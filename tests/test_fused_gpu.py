@@ -227,16 +227,30 @@ def test_fused_solve_matches_the_reference_run_here(ctx, oracle, kw):
     assert got.iterations == want.iterations and got.converged == want.converged
     created = [got.r_creations, got.q_creations, got.p_creations, got.d_creations]
     expected = [want.r_creations, want.q_creations, want.p_creations, want.d_creations]
-    if kw["nroots"] == 16 and kw.get("nbuffers") == 8:
-        # 16 roots through 8 buffers: residuals of roots that are already converged re-enter the working set, and after
-        # normalisation they are rounding noise; whether the SVD test (threshold 1e-12, reference
-        # itsolv/propose_rspace.h:482-512) drops such a vector depends on the last bits of the Gram matrix. The
-        # reference's own solver class on the CUDA handlers differs from the CPU run in the same way.
-        assert abs(created[0] - expected[0]) <= 4 and abs(created[1] - expected[1]) <= 8
-    else:
-        assert created == expected
+    # identical counters in every configuration, also with 16 roots through 8 buffers, where several new vectors at once
+    # lie in the span of the subspace and the choice among them follows the rounding pattern of the overlaps: the fused
+    # proposal step then measures them on the normalised vectors, as the reference does (FusedDavidson.h)
+    assert created == expected
     for i in range(kw["nroots"]):
         assert abs(got.eigenvalues[i] / want.eigenvalues[i] - 1) <= 1e-10
+        assert abs(got.errors[i] - want.errors[i]) <= 1e-3 * want.errors[i] + 1e-13, "error estimates follow the same path"
+
+
+def test_error_estimates_are_true_residuals_with_a_capped_q_space(ctx):
+    """16 roots through 8 buffers with the Q space capped at 8 (BASELINE.json configs[3] in small): the residuals of the
+    exported solutions, from an operator application that is independent of the solver's stored actions, are what the
+    solver reports. (A D space that reproduces the converged roots only to 1e-7 shows up here and nowhere else: the
+    eigenvalues still agree to 1e-14.)"""
+    n = 200_000
+    spec = H.make_spec(n, kind=N.KIND_DAVIDSON, nroots=16, hermitian=1, max_size_qspace=8, nbuffers=8, fused=1)
+    res, sol = H.solve(ctx, spec, want_solutions=True)
+    assert res.converged == 1
+    for k in range(16):
+        x = torch.from_numpy(sol[k]).cuda()
+        y = torch.empty_like(x)
+        ctx.banded_apply(x, y, n, 0, 4, 1e-3)
+        true = float((y - res.eigenvalues[k] * x).norm() / x.norm())
+        assert true <= 1e-8 and true <= 3 * res.errors[k] + 1e-12
 
 
 EQUATIONS = sorted(k for k, v in GOLDEN.items()

@@ -150,7 +150,7 @@ class DeviceRows:
             self.address = 0
 
 
-def verify_solutions(kind, n, start, rows, nroots, eigenvalues, rank, world, legacy=False):
+def verify_solutions(kind, n, start, rows, nroots, eigenvalues, rank, world, legacy=False, ctx=None, detail=None):
     """residuals (and distances to the known solutions) of the solution vectors, one root at a time on the GPU;
     rows(k) returns the k-th solution as a torch tensor on the device"""
     res_norm, sol_err = [], []
@@ -162,6 +162,20 @@ def verify_solutions(kind, n, start, rows, nroots, eigenvalues, rank, world, leg
             r = y - eigenvalues[k] * x
             num, den = _allsum([float((r * r).sum()), float((x * x).sum())], world)
             res_norm.append(float(np.sqrt(num / den)))
+            if detail is not None and ctx is not None and world == 1:
+                # the same residual with the harness' own operator kernel, and where the two operators differ most
+                import torch
+                y2 = torch.empty_like(x)
+                ctx.banded_apply(x, y2, n, 0, B, EPS)
+                ctx.synchronize()
+                r2 = y2 - eigenvalues[k] * x
+                detail.setdefault("harness_operator_residual", []).append(float(r2.norm() / x.norm()))
+                d = (y - y2).abs()
+                imax = int(d.argmax())
+                detail.setdefault("operators_differ", []).append([float(d.max()), imax, float(x[imax]), float(y[imax])])
+                imax = int(r.abs().argmax())
+                detail.setdefault("largest_residual_entry", []).append([imax, float(r[imax]), float(x[imax])])
+                del y2, r2, d
             del y
         elif kind == "lineq":
             xk = known_solution(kind, k, start, nloc, x.device, legacy)
@@ -263,8 +277,12 @@ def run(ctx, name, rank, world, n=None, overrides=None, fused=None, verify=True,
     gates = {"converged": bool(res.converged)}
     if verify:
         ctx.mem_trim()  # the pool keeps every freed vector; the checker's torch temporaries need some of it back
-        res_norm, sol_err = verify_solutions(kind, spec.n, start, sol.row, nroots, eig, rank, world, legacy)
+        detail = {} if os.environ.get("ITSOLV_VERIFY_DETAIL") else None
+        res_norm, sol_err = verify_solutions(kind, spec.n, start, sol.row, nroots, eig, rank, world, legacy, ctx, detail)
         rec["independent_residual_max"] = max(res_norm)
+        rec["independent_residuals"] = res_norm
+        if detail:
+            rec["verify_detail"] = detail
         gates["residual_ok"] = max(res_norm) <= 1e-7
         if sol_err:
             rec["solution_error_max"] = max(sol_err)
