@@ -478,6 +478,11 @@ def run_configs(ctx, rank, world):
             nloc = int(pkg.distribution(n_full, world)[1])
             need = dry["peak_vectors"] * 8.0 * nloc
             ctx.mem_trim()
+            try:
+                import torch
+                torch.cuda.empty_cache()
+            except Exception:
+                pass
             free_min = float(ctx.allreduce_host(np.array([-float(ctx.mem_info()[0])]), op_max=True)[0]) * -1.0
             if need + 6e9 > free_min:
                 records.append({"config": name, "overrides": ov, "skipped": "does not fit",
