@@ -231,7 +231,10 @@ def main():
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
-    numa = D.bind_host_to_device(local_rank)  # before any pinned host buffer is allocated
+    if os.environ.get("ITSOLV_BENCH_BIND", "1") != "0":
+        numa = D.bind_host_to_device(local_rank)  # before any pinned host buffer is allocated
+    else:
+        numa = {"bound": False, "why": "ITSOLV_BENCH_BIND=0"}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = pkg.Context(local_rank)
@@ -252,19 +255,27 @@ def main():
 
     # ---- device-resident leg: operator (stored CSR) in HBM before the timed region starts
     problem = H.Problem(ctx, spec)
+    ctx.set_profiling(True)  # before the warm-up: the pool of CUDA events is built there, not in the first timed step
     for _ in range(max(args.warmup, args.min_warmup)):
         problem.solve(spec)
-    ctx.set_profiling(True)
     lib = N.kernels()
-    lib.itsolv_comm_barrier(ctx.handle)
-    torch.cuda.synchronize()
     iterations, launches = 0, 0
     agg = dict(bytes=0.0, secs=0.0, bgi=0.0, sgi=0.0, bgo=0.0, sgo=0.0, bb1=0.0, sb1=0.0, brs=0.0, srs=0.0, action=0.0,
                cgi=0, cgo=0, cb1=0, crs=0)
     with ClockSampler(local_rank) as clocks:
+        # the ranks leave this barrier together; starting the sampler thread (NVML) before it keeps its start-up time,
+        # which differs from rank to rank, out of the first timed step
+        lib.itsolv_comm_barrier(ctx.handle)
+        torch.cuda.synchronize()
         ctx.timer_start()
+        detail = []
         for _ in range(args.steps):
+            t_step = time.perf_counter()
             res = problem.solve(spec)
+            detail.append({"wall_ms": (time.perf_counter() - t_step) * 1e3, "device_ms": res.device_ms_solve,
+                           "action_ms": res.seconds_action * 1e3, "handler_ms": res.handler_device_seconds * 1e3,
+                           "gemm_inner_ms": res.seconds_gemm_inner * 1e3, "gemm_outer_ms": res.seconds_gemm_outer * 1e3,
+                           "blas1_ms": res.seconds_blas1 * 1e3, "residual_ms": res.seconds_residual * 1e3})
             iterations += res.iterations
             launches += res.kernel_launches
             agg["bytes"] += res.handler_bytes
@@ -285,6 +296,9 @@ def main():
         lib.itsolv_comm_barrier(ctx.handle)
         torch.cuda.synchronize()
     ctx.set_profiling(False)
+    if os.environ.get("ITSOLV_BENCH_RANK_DETAIL"):  # per-rank, per-step record (where a multi-GPU step spends its time)
+        with open(f"{os.environ['ITSOLV_BENCH_RANK_DETAIL']}.rank{rank}.json", "w") as f:
+            json.dump({"rank": rank, "world": world, "host_binding": numa, "steps": detail}, f)
     converged, eig = res.converged, [res.eigenvalues[i] for i in range(args.roots)]
     # the other driver path on the same operator, for the record (same timing protocol, fewer steps)
     other = None

@@ -69,9 +69,22 @@ int ItsolvB200Eigenvalues(double* eigenvalues);
 int ItsolvB200WorkingSetEigenvalues(double* eigenvalues);
 /* roots of the current working set (host array of working-set size); returns the size */
 long ItsolvB200WorkingSet(int* roots);
-/* reference IterativeSolverC.h:53-56 */
+/* reference IterativeSolverC.h:48-49: indices (global) of up to maximumNumber elements proposed for the P space from the
+ * n_roots solution and residual vectors on the device; returns their number (the solvers of this path propose none,
+ * reference IterativeSolverTemplate.h:238-241). -1 on error. */
+long ItsolvB200SuggestP(const double* solution, const double* residual, size_t maximumNumber, double threshold,
+                        size_t* indices);
+/* reference IterativeSolverC.h:51: the active solver's statistics on stdout */
+int ItsolvB200PrintStatistics(void);
+/* reference IterativeSolverC.h:53-56; HasValues is 1 for Optimize instances only, hence always 0 here */
 int ItsolvB200NonLinear(void);
+int ItsolvB200HasValues(void);
 int ItsolvB200HasEigenvalues(void);
+/* reference IterativeSolverC.h:62: the current function value of the active solver (NaN on error) */
+double ItsolvB200Value(void);
+/* NOT PROVIDED: IterativeSolverOptimizeInitialize and IterativeSolverAddValue (reference IterativeSolverC.h:21-23,31): the
+ * BFGS / steepest-descent optimiser is outside the accelerated path; the mpicomm_* helpers
+ * (:69-73) have no counterpart because the communicator belongs to the context. */
 /* reference IterativeSolverC.h:58-60: the diagonal is kept in a device vector owned by the instance */
 int ItsolvB200SetDiagonals(const double* diagonals);
 int ItsolvB200Diagonals(double* diagonals);

@@ -216,7 +216,11 @@ SOLVER_API = {
     "ItsolvB200Eigenvalues": (C.c_int, [c_double_p]),
     "ItsolvB200WorkingSetEigenvalues": (C.c_int, [c_double_p]),
     "ItsolvB200WorkingSet": (C.c_long, [C.POINTER(C.c_int)]),
+    "ItsolvB200SuggestP": (C.c_long, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, c_size_p]),
+    "ItsolvB200PrintStatistics": (C.c_int, []),
     "ItsolvB200NonLinear": (C.c_int, []),
+    "ItsolvB200HasValues": (C.c_int, []),
+    "ItsolvB200Value": (C.c_double, []),
     "ItsolvB200HasEigenvalues": (C.c_int, []),
     "ItsolvB200SetDiagonals": (C.c_int, [C.c_void_p]),
     "ItsolvB200Diagonals": (C.c_int, [C.c_void_p]),

@@ -78,13 +78,61 @@ def _openblas() -> str:
     return os.path.abspath(cands[0])
 
 
+MANIFEST = os.path.join(PKG, "reference_manifest.json")
+
+
+def reference_files() -> dict:
+    """sha256 of every file of the reference checkout the host library is built from: the solver templates and array
+    headers it instantiates and the seven translation units it compiles (paths relative to the checkout)."""
+    import hashlib
+    base = os.path.join(REFERENCE, "src", "molpro", "linalg")
+    out = {}
+    for sub, pats in (("", ("*.h", "options.cpp")), ("itsolv", ("**/*.h", "*.cpp")), ("array", ("**/*.h",))):
+        for pat in pats:
+            for path in sorted(glob.glob(os.path.join(base, sub, pat), recursive=True)):
+                with open(path, "rb") as f:
+                    out[os.path.relpath(path, REFERENCE)] = hashlib.sha256(f.read()).hexdigest()
+    return out
+
+
+def check_reference() -> None:
+    """The solver layer is the reference's own (header templates, instantiated with the CUDA containers): the checkout is a
+    build dependency, pinned by content in reference_manifest.json. A different revision is refused unless
+    ITSOLV_REFERENCE_UNPINNED=1 (the template interfaces the plugin classes implement may have moved)."""
+    import json
+    if not os.path.exists(MANIFEST):
+        return
+    pinned = json.load(open(MANIFEST))["files"]
+    found = reference_files()
+    wrong = sorted(k for k in pinned if found.get(k) != pinned[k])
+    if wrong and os.environ.get("ITSOLV_REFERENCE_UNPINNED", "0") != "1":
+        raise RuntimeError(
+            f"the reference checkout at {REFERENCE} is not the revision this package is pinned to: {len(wrong)} of "
+            f"{len(pinned)} files differ or are missing (first: {wrong[0]}). Point ITSOLV_REFERENCE at a matching checkout of "
+            "knowles-group/iterative-solver, re-pin with `python -m iterative_solver_b200.build --pin` after reviewing the "
+            "plugin classes against the new headers, or set ITSOLV_REFERENCE_UNPINNED=1")
+
+
+def pin_reference() -> None:
+    import json
+    with open(MANIFEST, "w") as f:
+        json.dump({"what": "content pin of the knowles-group/iterative-solver files libitsolv_b200_host.so is built from "
+                           "(the checkout carries no version tag)", "files": reference_files()}, f, indent=0, sort_keys=True)
+
+
 def build_host(force: bool = False) -> str:
-    """The reference-facing plugin + harness. Needs the reference headers; otherwise the prebuilt library is kept."""
+    """The reference-facing plugin + harness: the reference's solver templates instantiated with the CUDA containers.
+    The reference checkout (ITSOLV_REFERENCE, default /root/reference) is a build dependency; a box without it (the GPU
+    box) keeps the prebuilt library that travels with the tree."""
     lib = os.path.join(LIBDIR, "libitsolv_b200_host.so")
     if not os.path.isdir(os.path.join(REFERENCE, "src", "molpro")):
         if not os.path.exists(lib):
-            raise RuntimeError("libitsolv_b200_host.so is not built and the reference headers are not available")
+            raise RuntimeError(
+                "libitsolv_b200_host.so is not built and cannot be: it instantiates the solver templates of "
+                f"knowles-group/iterative-solver, and no checkout was found at {REFERENCE} (set ITSOLV_REFERENCE). The "
+                "kernel library libitsolv_b200.so (include/itsolv_b200.h) does not need it.")
         return lib
+    check_reference()
     os.makedirs(OBJDIR, exist_ok=True)
     refsrc = os.path.join(REFERENCE, "src", "molpro", "linalg")
     ref_cpp = [os.path.join(refsrc, p) for p in (
@@ -122,5 +170,9 @@ def build_all(force: bool = False) -> None:
 
 
 if __name__ == "__main__":
+    if "--pin" in sys.argv:
+        pin_reference()
+        print("pinned", len(reference_files()), "reference files in", MANIFEST)
+        sys.exit(0)
     build_all(force="--force" in sys.argv)
     print("built", os.listdir(LIBDIR))

@@ -351,7 +351,7 @@ int itsolv_comm_halo_exchange_multi(itsolv_ctx* ctx, const double* const* x, int
     return 0;
   Comm* c = ctx->comm;
   ITSOLV_REQUIRE(nloc >= size_t(b), "itsolv_comm_halo_exchange_multi: shard shorter than the half bandwidth");
-  if (c->peers_ready && ctx->opt_p2p_allreduce >= 0 && w <= ITSOLV_MAX_ROOTS_HALO &&
+  if (c->peers_ready && ctx->opt_p2p_allreduce >= 0 && ctx->opt_p2p_halo >= 0 && w <= ITSOLV_MAX_ROOTS_HALO &&
       size_t(w) * size_t(b) <= kHaloSlotDoubles) {
     HaloParams p{};
     for (int k = 0; k < w; ++k)

@@ -100,6 +100,7 @@ struct itsolv_ctx {
   int opt_ds_ring = 0;    // davidson_residual: <0 never use the cp.async ring kernel
   int opt_mgs_chain = 0;   // R-R Gram-Schmidt steps chained on the device: 0 default (on, see mgs_fused.cu), -1 off
   int opt_p2p_allreduce = 0; // <0: use ncclAllReduce even when the peer buffers are mapped
+  int opt_p2p_halo = 0;      // <0: halo rows by ncclSend/ncclRecv even when the peer buffers are mapped
 
   std::vector<std::pair<const void*, size_t>> smem_optin; // kernel -> largest dynamic shared memory size opted in
 

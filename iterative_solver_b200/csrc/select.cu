@@ -4,10 +4,11 @@
 // key = v or |v| (max) / -v or -|v| (min), so among equal keys the higher index wins. That rule is reproduced exactly
 // by a most-significant-digit radix select over the 128-bit composite (order-preserving image of key, global index):
 // histogram passes over the key bytes + the index bytes that can be non-zero, each finished by its last CTA (which picks
-// the boundary bin), all on the device with no host round trip. Only the two leading key bytes and one gather pass read
-// the vector; the gather pass moves the boundary bucket (at most 2^20 elements, else the vector keeps being read) into
-// a candidate buffer on which the remaining passes and the final compaction run. Runs once or twice per solve (initial
-// guess, P-space choice): 3 passes of 8n bytes.
+// the boundary bin), all on the device with no host round trip. After every key byte the last CTA looks at the size of
+// the boundary bucket; as soon as it fits (2^20 elements) the next pass, while it reads the vector for its own digit,
+// moves the bucket into a candidate buffer on which the remaining passes and the final compaction run. A vector whose
+// values spread over many binary exponents is read twice (8n bytes each); a shard of a sorted diagonal, whose values
+// share exponent and leading mantissa bits, four times. Runs once or twice per solve (initial guess, P-space choice).
 #include <algorithm>
 #include <cstring>
 #include <utility>
@@ -18,9 +19,10 @@
 namespace itsolv {
 
 // layout of ctx->d_select (unsigned long long words)
-enum { SEL_KEY = 0, SEL_IDX = 1, SEL_REMAINING = 2, SEL_COUNT = 3, SEL_NCAND = 4, SEL_TICKET = 5, SEL_HIST = 16 };
+// SEL_GATHER_PASS: 1 + index of the pass that moves the boundary bucket into the candidate buffer (0 = none yet)
+enum { SEL_KEY = 0, SEL_IDX = 1, SEL_REMAINING = 2, SEL_COUNT = 3, SEL_NCAND = 4, SEL_TICKET = 5, SEL_GATHER_PASS = 6, SEL_HIST = 16 };
 
-constexpr unsigned long long kSelCandCapacity = 1ull << 20; // candidates kept after the two leading key bytes
+constexpr unsigned long long kSelCandCapacity = 1ull << 20; // largest boundary bucket that is gathered
 
 struct SelParams {
   const double* x;
@@ -28,7 +30,7 @@ struct SelParams {
   size_t n;
   unsigned long long offset; // global index of x[0]
   int max, ignore_sign;
-  // candidates gathered after the first two passes (key image, global index, value); used while their number fits
+  // the gathered boundary bucket (key image, global index, value)
   const unsigned long long* cand_key;
   const unsigned long long* cand_idx;
   const double* cand_val;
@@ -67,31 +69,98 @@ __device__ __forceinline__ bool sel_digit(unsigned long long u, unsigned long lo
 }
 
 /*!
- * Histogram of digit `d` over the elements that agree with the digits fixed so far; the last CTA to finish then picks
- * the bin that holds the boundary element (walk from the top bin until `remaining` elements are covered), fixes the digit
- * and clears the histogram for the next pass. From digit 2 on the pass runs over the gathered candidates when they fit.
+ * One pass of the selection: histogram of digit `d` over the elements that agree with the digits fixed so far; the last
+ * CTA to finish then picks the bin that holds the boundary element (walk from the top bin until `remaining` elements are
+ * covered), fixes the digit and clears the histogram for the next pass.
+ *
+ * The pass reads the vector until the boundary bucket has been gathered, then the candidates. The last CTA of a key-byte
+ * pass that finds the bucket small enough (kSelCandCapacity) names the next pass (`next_d`) as the gathering pass
+ * (SEL_GATHER_PASS): that pass, still reading the vector, also sends the elements above the boundary prefix straight to
+ * the output (they are selected for certain) and the elements with the boundary prefix to the candidate buffer.
+ * A warp whose elements all fall into one bin (every warp, on a shard of a sorted diagonal) spends one atomic on them;
+ * the appends to the output and to the candidates cost one atomic per warp.
  */
-__global__ void __launch_bounds__(256) select_hist_kernel(const __grid_constant__ SelParams p, int d,
-                                                          unsigned long long* __restrict__ state) {
+__global__ void __launch_bounds__(256)
+    select_pass_kernel(const __grid_constant__ SelParams p, int d, int next_d, unsigned long long* __restrict__ state,
+                       unsigned long long* __restrict__ cand_key, unsigned long long* __restrict__ cand_idx,
+                       double* __restrict__ cand_val, long long* __restrict__ out_idx, double* __restrict__ out_val,
+                       unsigned long long capacity) {
   __shared__ unsigned int hist[256];
   __shared__ unsigned long long suffix[257];
   __shared__ int s_last;
-  hist[threadIdx.x] = 0;
-  __syncthreads();
   const unsigned long long kpre = state[SEL_KEY], ipre = state[SEL_IDX];
-  const unsigned long long ncand = state[SEL_NCAND];
-  const bool from_candidates = d >= 2 && ncand <= kSelCandCapacity;
-  const size_t count = from_candidates ? size_t(ncand) : p.n;
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x) {
-    const unsigned long long u = from_candidates ? p.cand_key[i] : sel_key(p, sel_value(p, i));
-    const unsigned long long gi = from_candidates ? p.cand_idx[i] : p.offset + i;
-    unsigned digit;
-    if (sel_digit(u, gi, d, kpre, ipre, digit))
-      atomicAdd(&hist[digit], 1u);
+  const unsigned long long gpass = state[SEL_GATHER_PASS]; // 1 + index of the gathering pass, 0: none named yet
+  const bool gather_now = gpass == (unsigned long long)(d + 1);
+  const bool from_candidates = gpass != 0 && !gather_now;
+  const size_t count = from_candidates ? size_t(state[SEL_NCAND]) : p.n;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned full = 0xFFFFFFFFu, below = (1u << lane) - 1u;
+  if (size_t(blockIdx.x) * blockDim.x < count) { // CTAs beyond the candidates only take their ticket
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int shift = 64 - 8 * (d < 8 ? d : 8); // key bytes fixed before this pass (gathering passes have d >= 1)
+    // warp-uniform trip count: every lane of a warp takes part in the votes below
+    for (size_t base = size_t(blockIdx.x) * blockDim.x + (threadIdx.x - lane); base < count;
+         base += size_t(gridDim.x) * blockDim.x) {
+      const size_t i = base + lane;
+      unsigned digit = 0;
+      bool ok = false, certain = false;
+      double value = 0;
+      unsigned long long u = 0, gi = 0;
+      if (i < count) {
+        if (from_candidates) {
+          u = p.cand_key[i];
+          gi = p.cand_idx[i];
+        } else {
+          value = sel_value(p, i);
+          u = sel_key(p, value);
+          gi = p.offset + i;
+        }
+        ok = sel_digit(u, gi, d, kpre, ipre, digit);
+        certain = gather_now && (u >> shift) > (kpre >> shift);
+      }
+      const unsigned okmask = __ballot_sync(full, ok);
+      if (gather_now) {
+        const unsigned cmask = __ballot_sync(full, certain);
+        if (cmask) {
+          const int leader = __ffs(int(cmask)) - 1;
+          unsigned long long pos = 0;
+          if (int(lane) == leader)
+            pos = atomicAdd(&state[SEL_COUNT], (unsigned long long)__popc(cmask));
+          pos = __shfl_sync(full, pos, leader) + __popc(cmask & below);
+          if (certain && pos < capacity) {
+            out_idx[pos] = (long long)gi;
+            out_val[pos] = value;
+          }
+        }
+        if (okmask) {
+          const int leader = __ffs(int(okmask)) - 1;
+          unsigned long long pos = 0;
+          if (int(lane) == leader)
+            pos = atomicAdd(&state[SEL_NCAND], (unsigned long long)__popc(okmask));
+          pos = __shfl_sync(full, pos, leader) + __popc(okmask & below);
+          if (ok && pos < kSelCandCapacity) {
+            cand_key[pos] = u;
+            cand_idx[pos] = gi;
+            cand_val[pos] = value;
+          }
+        }
+      }
+      if (okmask) {
+        const int leader = __ffs(int(okmask)) - 1;
+        const unsigned first = __shfl_sync(full, digit, leader);
+        if (__all_sync(full, !ok || digit == first)) {
+          if (int(lane) == leader)
+            atomicAdd(&hist[first], unsigned(__popc(okmask)));
+        } else if (ok) {
+          atomicAdd(&hist[digit], 1u);
+        }
+      }
+    }
+    __syncthreads();
+    if (hist[threadIdx.x])
+      atomicAdd(&state[SEL_HIST + threadIdx.x], (unsigned long long)hist[threadIdx.x]);
   }
-  __syncthreads();
-  if (hist[threadIdx.x])
-    atomicAdd(&state[SEL_HIST + threadIdx.x], (unsigned long long)hist[threadIdx.x]);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0)
@@ -115,6 +184,8 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const __grid_constant_
   }
   if (suffix[t] >= remaining && suffix[t + 1] < remaining) {
     state[SEL_REMAINING] = remaining - suffix[t + 1];
+    if (d < 8 && next_d >= 0 && gpass == 0 && suffix[t] - suffix[t + 1] <= kSelCandCapacity)
+      state[SEL_GATHER_PASS] = (unsigned long long)(next_d + 1);
     if (d < 8)
       state[SEL_KEY] = kpre | ((unsigned long long)t << (56 - 8 * d));
     else
@@ -125,51 +196,18 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const __grid_constant_
     state[SEL_TICKET] = 0;
 }
 
-/*!
- * After the two leading key bytes are fixed: elements above the boundary prefix are selected for certain and go straight
- * to the output; elements with the boundary prefix become the candidates of the remaining passes.
- */
-__global__ void __launch_bounds__(256)
-    select_gather_kernel(const __grid_constant__ SelParams p, unsigned long long* __restrict__ state,
-                         unsigned long long* __restrict__ cand_key, unsigned long long* __restrict__ cand_idx,
-                         double* __restrict__ cand_val, long long* __restrict__ out_idx, double* __restrict__ out_val,
-                         unsigned long long capacity) {
-  const unsigned long long prefix = state[SEL_KEY] >> 48;
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n; i += size_t(gridDim.x) * blockDim.x) {
-    const double value = sel_value(p, i);
-    const unsigned long long u = sel_key(p, value);
-    const unsigned long long top = u >> 48;
-    if (top > prefix) {
-      const unsigned long long pos = atomicAdd(&state[SEL_COUNT], 1ull);
-      if (pos < capacity) {
-        out_idx[pos] = (long long)(p.offset + i);
-        out_val[pos] = value;
-      }
-    } else if (top == prefix) {
-      const unsigned long long pos = atomicAdd(&state[SEL_NCAND], 1ull);
-      if (pos < kSelCandCapacity) {
-        cand_key[pos] = u;
-        cand_idx[pos] = p.offset + i;
-        cand_val[pos] = value;
-      }
-    }
-  }
-}
-
-//! elements with the boundary prefix that lie at or above the boundary (key, index) pair
+//! the elements (of the candidates, if they were gathered; elements above their prefix are in the output already) that
+//! lie at or above the boundary (key, index) pair
 __global__ void __launch_bounds__(256)
     select_compact_kernel(const __grid_constant__ SelParams p, unsigned long long* __restrict__ state,
                           long long* __restrict__ out_idx, double* __restrict__ out_val, unsigned long long capacity) {
   const unsigned long long kthr = state[SEL_KEY], ithr = state[SEL_IDX];
-  const unsigned long long ncand = state[SEL_NCAND];
-  const bool from_candidates = ncand <= kSelCandCapacity;
-  const size_t count = from_candidates ? size_t(ncand) : p.n;
+  const bool from_candidates = state[SEL_GATHER_PASS] != 0;
+  const size_t count = from_candidates ? size_t(state[SEL_NCAND]) : p.n;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x) {
     const double value = from_candidates ? p.cand_val[i] : sel_value(p, i);
     const unsigned long long u = from_candidates ? p.cand_key[i] : sel_key(p, value);
     const unsigned long long gi = from_candidates ? p.cand_idx[i] : p.offset + i;
-    if ((u >> 48) != (kthr >> 48))
-      continue; // above the prefix: already in the output; below: not selected
     if (u > kthr || (u == kthr && gi >= ithr)) {
       const unsigned long long pos = atomicAdd(&state[SEL_COUNT], 1ull);
       if (pos < capacity) {
@@ -240,7 +278,6 @@ int itsolv_select_f64(itsolv_ctx* ctx, const double* x, const double* y, size_t 
     unsigned long long init[SEL_HIST + 256];
     std::memset(init, 0, sizeof(init));
     init[SEL_REMAINING] = nloc;
-    init[SEL_NCAND] = ~0ull; // no candidates gathered yet
     ITSOLV_CUDA(cudaMemcpyAsync(ctx->d_select, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     const int grid = int(std::min<size_t>((n + 255) / 256, size_t(ctx->num_sms) * 8));
     // index bytes above the largest global index are zero for every element: skip those passes
@@ -248,20 +285,18 @@ int itsolv_select_f64(itsolv_ctx* ctx, const double* x, const double* y, size_t 
     while (idx_bytes < 8 && ((global_offset + n - 1) >> (8 * idx_bytes)) != 0)
       ++idx_bytes;
     mark_launch(ctx);
-    for (int dgt = 0; dgt < 16; ++dgt) {
-      if (dgt >= 8 && dgt - 8 < 8 - idx_bytes)
-        continue;
-      if (dgt == 2) { // two key bytes are fixed: certain elements to the output, the boundary bucket to the candidates
-        ITSOLV_CUDA(cudaMemsetAsync(ctx->d_select + SEL_NCAND, 0, sizeof(unsigned long long), ctx->stream));
-        select_gather_kernel<<<grid, 256, 0, ctx->stream>>>(p, ctx->d_select, cand_key, cand_idx, cand_val, d_idx, d_val,
-                                                            nloc);
-        ctx->counters.launches += 1;
-      }
-      // the passes over the candidates are short: a grid of one CTA per SM is plenty
-      select_hist_kernel<<<dgt < 2 ? grid : std::min(grid, ctx->num_sms), 256, 0, ctx->stream>>>(p, dgt, ctx->d_select);
+    int passes[16], npass = 0;
+    for (int dgt = 0; dgt < 16; ++dgt)
+      if (dgt < 8 || dgt - 8 >= 8 - idx_bytes)
+        passes[npass++] = dgt;
+    // whether a pass runs over the vector or over the candidates is decided on the device: the grid is always the full
+    // one, CTAs beyond the candidates return at once
+    for (int k = 0; k < npass; ++k) {
+      select_pass_kernel<<<grid, 256, 0, ctx->stream>>>(p, passes[k], k + 1 < npass ? passes[k + 1] : -1, ctx->d_select,
+                                                        cand_key, cand_idx, cand_val, d_idx, d_val, nloc);
       ctx->counters.launches += 1;
     }
-    select_compact_kernel<<<std::min(grid, ctx->num_sms), 256, 0, ctx->stream>>>(p, ctx->d_select, d_idx, d_val, nloc);
+    select_compact_kernel<<<grid, 256, 0, ctx->stream>>>(p, ctx->d_select, d_idx, d_val, nloc);
     ctx->counters.launches += 1;
     ITSOLV_CUDA(cudaGetLastError());
   }

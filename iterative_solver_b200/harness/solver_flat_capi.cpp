@@ -3,6 +3,7 @@
 // DistrArrayCUDA views of the caller's device memory in the place of DistrArraySpan views of host memory.
 #include <cctype>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <memory>
 #include <sstream>
@@ -356,6 +357,43 @@ int ItsolvB200NonLinear(void) {
   } catch (const std::exception& e) {
     g_error = e.what();
     return -1;
+  }
+}
+
+long ItsolvB200SuggestP(const double* solution, const double* residual, size_t maximumNumber, double threshold,
+                        size_t* indices) {
+  return guarded_count([&] {
+    auto& in = top();
+    const size_t nroots = in.solver->n_roots();
+    auto cc = views(in, nroots, const_cast<double*>(solution));
+    auto gg = views(in, nroots, const_cast<double*>(residual));
+    const auto result = in.solver->suggest_p(its::cwrap(cc), its::cwrap(gg), maximumNumber, threshold);
+    for (size_t i = 0; i < result.size(); ++i)
+      indices[i] = result[i];
+    return result.size();
+  });
+}
+
+int ItsolvB200PrintStatistics(void) {
+  return guarded([] { molpro::cout << top().solver->statistics() << std::endl; });
+}
+
+int ItsolvB200HasValues(void) {
+  try {
+    top();
+    return 0; // only the reference's Optimize instances carry values (IterativeSolverCMPI.cpp:229,480)
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return -1;
+  }
+}
+
+double ItsolvB200Value(void) {
+  try {
+    return top().solver->value();
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return std::numeric_limits<double>::quiet_NaN();
   }
 }
 

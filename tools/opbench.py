@@ -117,6 +117,15 @@ def run_all(ctx, lib, args, n, nvec, take, run, _ptr_array, _dbl):
         return f
 
     run("spmv_generated[b=4]", 16 * n, lambda: (lambda v: ctx.banded_apply(v[0], v[1], n, 0, 4, 1e-3))(take(2)))
+    # select (initial guess / P-space choice): values spread over many binary exponents (the diagonal i + 1 on rank 0), the
+    # shard of rank 7 of 8 of the same diagonal (one exponent, common leading mantissa bits), random values
+    if not args.only or "select" in args.only:
+        wide = torch.arange(1, n + 1, dtype=torch.float64, device="cuda")
+        shard = wide + 7.0 * n
+        run("select[4, diagonal]", 3 * 8 * n, lambda: ctx.select(wide, 4))
+        run("select[4, shard 7/8]", 3 * 8 * n, lambda: ctx.select(shard, 4, global_offset=7 * n))
+        run("select[500, random]", 3 * 8 * n, lambda: ctx.select(take(1)[0], 500))
+        del wide, shard
     run("fill", 8 * n, lambda: ctx.fill(1.0, take(1)[0]))
     run("scal", 16 * n, lambda: ctx.scal(1.0000001, take(1)[0]))
     run("copy", 16 * n, lambda: ctx.copy(*take(2)))
