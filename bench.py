@@ -196,8 +196,48 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+CPU_OPS = [("dot", 0, 1, 1, lambda n, k, m: 16 * n), ("axpy", 1, 1, 1, lambda n, k, m: 24 * n),
+           ("scal", 2, 1, 1, lambda n, k, m: 16 * n), ("gemm_inner[4x4]", 3, 4, 4, lambda n, k, m: 8 * n * (k + m)),
+           ("gemm_inner[4x16]", 3, 4, 16, lambda n, k, m: 8 * n * (k + m)),
+           ("gemm_outer[4x4]", 4, 4, 4, lambda n, k, m: 8 * n * (k + 2 * m)),
+           ("gemm_outer[16x4]", 4, 16, 4, lambda n, k, m: 8 * n * (k + 2 * m))]
+
+
+def _cpu_op_worker(args):
+    op, n, k, m, reps = args
+    import itsolv_oracle_lib
+    return itsolv_oracle_lib.load().ref.time_op(op, n, k, m, reps)
+
+
+def cpu_ops(args):
+    """Second CPU baseline (`--cpu-ops`): the reference's own handler operations (ArrayHandlerIterable over std::vector,
+    oracle/_ref) per shape at the bench's n, on one core and on all host cores at once. The reference scales over cores
+    with MPI ranks that own row blocks (DistrArrayMPI3, array/util/gemm.h:170-182); there is no MPI in this image, so the
+    all-core line runs one process per core on its own row block (n / cores rows, at least 2e6) and leaves the k x m MPI_Allreduce out - an upper bound
+    of what that path can reach on this host. Algorithmic bytes as for the GPU kernels."""
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    n = args.n
+    rows = []
+    ctx = mp.get_context("fork")
+    for name, op, k, m, nbytes in CPU_OPS:
+        reps = 3
+        one = _cpu_op_worker((op, n, k, m, reps))
+        share = max(n // cores, 2_000_000)  # rows per process: vectors of >= 16 MB, beyond the private caches
+        with ctx.Pool(cores) as pool:
+            t_all = max(pool.map(_cpu_op_worker, [(op, share, k, m, reps)] * cores))
+        rows.append({"op": name, "seconds_1_core": one, "gbs_1_core": nbytes(n, k, m) / one / 1e9,
+                     "rows_per_process": share, "seconds_all_cores": t_all,
+                     "gbs_all_cores": nbytes(share * cores, k, m) / t_all / 1e9})
+    print(json.dumps({"impl": "reference", "what": "per-op CPU baseline of the handler contract", "n": n, "cores": cores,
+                      "kind": "reference (ArrayHandlerIterable, oracle/_ref); all-core line: one process per core on "
+                              "n/cores rows, no Allreduce", "ops": rows}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--cpu-ops", action="store_true",
+                    help="per-op timing of the reference's CPU handlers on 1 and on all host cores (no GPU work)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
@@ -216,6 +256,8 @@ def main():
     ap.add_argument("--min-warmup", type=int, default=3, help="profiling runs only: allow fewer than 3 warm-up steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.cpu_ops:
+        return cpu_ops(args)
     if args.impl == "reference":
         return reference_arm(args)
 

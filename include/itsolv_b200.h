@@ -116,6 +116,8 @@ int itsolv_dot_f64(itsolv_ctx* ctx, const double* x, const double* y, size_t n, 
  * w separate calls of the functions above, in one pass / one launch ---- */
 /* x_k *= alpha[k] */
 int itsolv_scal_batch_f64(itsolv_ctx* ctx, const double* alpha, double* const* x, int w, size_t n);
+/* x_k = alpha[k] for w vectors in one launch */
+int itsolv_fill_batch_f64(itsolv_ctx* ctx, const double* alpha, double* const* x, int w, size_t n);
 /* y_k = y_k + alpha[k]*x_k for w independent pairs (residual construction, LinearEigensystemDavidson.h:186-192) */
 int itsolv_axpy_batch_f64(itsolv_ctx* ctx, const double* alpha, const double* const* x, double* const* y, int w, size_t n);
 /* one step of the R-R modified Gram-Schmidt (propose_rspace.h:451-463): ri *= inv_norm; rj[k] += (-ov[k])*ri */

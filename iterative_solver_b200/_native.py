@@ -103,6 +103,7 @@ KERNEL_API = {
     "itsolv_axpy_f64": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_size_t]),
     "itsolv_dot_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, c_double_p]),
     "itsolv_scal_batch_f64": (C.c_int, [C.c_void_p, c_double_p, c_void_pp, C.c_int, C.c_size_t]),
+    "itsolv_fill_batch_f64": (C.c_int, [C.c_void_p, c_double_p, c_void_pp, C.c_int, C.c_size_t]),
     "itsolv_axpy_batch_f64": (C.c_int, [C.c_void_p, c_double_p, c_void_pp, c_void_pp, C.c_int, C.c_size_t]),
     "itsolv_mgs_step_f64": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, c_double_p, c_void_pp, C.c_int, C.c_size_t]),
     "itsolv_ctx_write_epoch": (C.c_ulonglong, [C.c_void_p]),

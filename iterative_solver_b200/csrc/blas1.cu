@@ -201,6 +201,23 @@ __global__ void __launch_bounds__(kThreads, 4) scal_batch_kernel(const __grid_co
       });
 }
 
+// y_k[i] = alpha_k for w vectors in one launch (zeroing a working set before sparse contributions are added,
+// reference itsolv/IterativeSolverTemplate.h:44-46: one fill sweep per vector)
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 4) fill_batch_kernel(const __grid_constant__ BatchParams prm) {
+  const int w = prm.w;
+  stream_rows<VEC>(
+      prm.n,
+      [&](size_t p) {
+        for (int k = 0; k < w; ++k)
+          reinterpret_cast<double2*>(prm.y[k])[p] = make_double2(prm.alpha[k], prm.alpha[k]);
+      },
+      [&](size_t i) {
+        for (int k = 0; k < w; ++k)
+          prm.y[k][i] = prm.alpha[k];
+      });
+}
+
 // y_k[i] = y_k[i] + alpha_k * x_k[i] for w independent pairs in one launch (residual construction,
 // reference itsolv/LinearEigensystemDavidson.h:186-192: one axpy sweep per root); product rounded before the sum
 template <bool VEC>
@@ -339,6 +356,28 @@ int itsolv_scal_batch_f64(itsolv_ctx* ctx, const double* alpha, double* const* x
     prm.w = cnt;
     CallScope scope(ctx, OP_BLAS1, 16.0 * n * cnt);
     LAUNCH_STREAM(scal_batch_kernel, vec, prm);
+  }
+  return 0;
+}
+
+int itsolv_fill_batch_f64(itsolv_ctx* ctx, const double* alpha, double* const* x, int w, size_t n) {
+  ++ctx->write_epoch; // before any early return: every rank advances alike, also one with an empty shard
+  ctx->counters.n_fill += w > 0 ? w : 0;
+  if (n == 0 || w <= 0)
+    return 0;
+  for (int start = 0; start < w; start += ITSOLV_MAX_PANEL) {
+    const int cnt = (w - start) < ITSOLV_MAX_PANEL ? (w - start) : ITSOLV_MAX_PANEL;
+    BatchParams prm;
+    bool vec = true;
+    for (int k = 0; k < cnt; ++k) {
+      prm.y[k] = x[start + k];
+      prm.alpha[k] = alpha[start + k];
+      vec = vec && aligned16(prm.y[k]);
+    }
+    prm.n = n;
+    prm.w = cnt;
+    CallScope scope(ctx, OP_BLAS1, 8.0 * n * cnt);
+    LAUNCH_STREAM(fill_batch_kernel, vec, prm);
   }
   return 0;
 }

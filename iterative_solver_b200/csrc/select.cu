@@ -95,7 +95,12 @@ __global__ void __launch_bounds__(256)
   const size_t count = from_candidates ? size_t(state[SEL_NCAND]) : p.n;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned full = 0xFFFFFFFFu, below = (1u << lane) - 1u;
-  if (size_t(blockIdx.x) * blockDim.x < count) { // CTAs beyond the candidates only take their ticket
+  // the grid is sized for the vector; on the candidates only the CTAs that have elements take part (and CTA 0 always)
+  const size_t blocks = (count + blockDim.x - 1) / blockDim.x;
+  const unsigned participating = unsigned(blocks < 1 ? 1 : (blocks < gridDim.x ? blocks : gridDim.x));
+  if (blockIdx.x >= participating)
+    return;
+  if (size_t(blockIdx.x) * blockDim.x < count) {
     hist[threadIdx.x] = 0;
     __syncthreads();
     const int shift = 64 - 8 * (d < 8 ? d : 8); // key bytes fixed before this pass (gathering passes have d >= 1)
@@ -164,7 +169,7 @@ __global__ void __launch_bounds__(256)
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0)
-    s_last = atomicAdd(&state[SEL_TICKET], 1ull) == gridDim.x - 1 ? 1 : 0;
+    s_last = atomicAdd(&state[SEL_TICKET], 1ull) == participating - 1 ? 1 : 0;
   __syncthreads();
   if (!s_last)
     return;

@@ -91,10 +91,27 @@ public:
     for (size_t i = 0; i < xx.size(); ++i)
       m_primed.push_back({xx[i].get().data(), xx[i].get().data(), d[i]});
   }
+  //! the same with values that a kernel has already returned (<x_i, x_i> from the tail of the pass that wrote x_i)
+  void prime_self_dots(const CVecRef<AL>& xx, const std::vector<double>& values) {
+    m_primed.clear();
+    if (xx.empty())
+      return;
+    m_primed_epoch = itsolv_ctx_write_epoch(xx[0].get().context());
+    for (size_t i = 0; i < xx.size() && i < values.size(); ++i)
+      m_primed.push_back({xx[i].get().data(), xx[i].get().data(), values[i]});
+  }
   //! x_k = alpha for every vector of the set
   void fill_batch(double alpha, const VecRef<AL>& xx) {
-    for (auto& x : xx)
-      x.get().fill(alpha);
+    if (xx.empty())
+      return;
+    std::vector<double*> px(xx.size());
+    for (size_t i = 0; i < xx.size(); ++i) {
+      xx[0].get().require_compatible(xx[i].get(), "fill_batch");
+      px[i] = xx[i].get().data();
+    }
+    const std::vector<double> a(xx.size(), alpha);
+    check(itsolv_fill_batch_f64(xx[0].get().context(), a.data(), px.data(), int(px.size()), xx[0].get().local_size()),
+          "ArrayHandlerCUDA::fill_batch");
   }
   //! x_k *= alpha[k], one launch
   void scal_batch(const std::vector<double>& alpha, const VecRef<AL>& xx) {

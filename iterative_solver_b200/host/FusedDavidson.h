@@ -321,9 +321,12 @@ public:
       if (!use_diagonals)
         throw std::runtime_error("Default initial guess requested, but diagonal elements are not available");
       auto guess = this->m_handlers->qq().select(parameters.size(), *diagonals);
+      // unit vectors: one launch zeroes all of them, then one element each (the reference copies a one-element sparse
+      // vector into every parameter, IterativeSolverTemplate.h:344-348: a fill and a scatter per root)
+      m_dense->fill_batch(0.0, VecRef<R>(parameters.begin(), parameters.begin() + std::min(guess.size(), parameters.size())));
       size_t root = 0;
       for (const auto& g : guess)
-        this->m_handlers->rp().copy(parameters[root++], P{{g.first, 1}});
+        this->m_handlers->rp().axpy(1.0, P{{g.first, 1}}, parameters[root++]);
     }
     int nwork = int(parameters.size());
     std::vector<P> pspace;
@@ -405,6 +408,16 @@ public:
       return a;
     };
     const auto xpar = stack(xs.cparamsq(), xs.cparamsd()), xact = stack(xs.cactionsq(), xs.cactionsd());
+    if (nP == 0 && !this->m_normalise_solution && nQ + nD > 0 && r <= 16) {
+      // both expansions, the residual and its norm in one pass over the subspace (the kernel of add_vector_fused without
+      // the preconditioner; its vectors are bit for bit those of the separate calls below)
+      const auto form = fused_residual_form(roots);
+      const auto norms = m_dense->subspace_residual(form.mode, false, cqd, xpar, xact, form.lambda, form.rhs, form.rscale,
+                                                    nullptr, form.shift, par, res);
+      m_dense->prime_self_dots(its::cwrap(res), norms.residual);
+      its::read_handler_counts(this->m_stats, this->m_handlers);
+      return;
+    }
     if (nP > 0) { // the P part comes first, as in the reference: zero, scatter-add, then the dense part accumulates
       for (auto& p : par)
         this->m_handlers->rr().fill(0, p);
@@ -753,7 +766,11 @@ protected:
                              fused_svd_thresh(), true);
     };
     auto svd = nN > 0 ? null_space() : std::list<its::SVD<double>>{};
-    if (nP == 0 && svd.size() > 1) {
+    static const size_t remeasure_from = [] {
+      const char* e = std::getenv("ITSOLV_REMEASURE_FROM"); // null-space dimension from which the overlaps are re-measured
+      return e && *e ? size_t(std::atoi(e)) : size_t(1);
+    }();
+    if (nP == 0 && svd.size() >= remeasure_from) {
       m_dense->scal_batch(factor, wresidual);
       factor.assign(nN, 1.0);
       G = m_dense->gemm_inner(its::cwrap(wresidual), cols);

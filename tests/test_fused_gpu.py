@@ -231,11 +231,17 @@ def test_fused_solve_matches_the_reference_run_here(ctx, oracle, kw):
     # lie in the span of the subspace and the choice among them follows the rounding pattern of the overlaps: the fused
     # proposal step then measures them on the normalised vectors, as the reference does (FusedDavidson.h)
     assert created == expected
+    # error estimates: against the reference's class run on the same CUDA handlers (fused = 0). The CPU run is not the
+    # yardstick for them: where new vectors are dropped as redundant the choice follows the last bits of the overlaps, a
+    # GPU tree sum and the CPU's sequential sum differ there, and the residuals of roots that are already converged end
+    # anywhere between 1e-14 and 2e-9 (seen with 16 roots through 8 buffers: CPU 2.2e-9, both GPU paths 3.2e-10)
+    plain, _ = H.solve(ctx, H.make_spec(kind=N.KIND_DAVIDSON, fused=0, **kw))
+    assert [plain.r_creations, plain.q_creations, plain.p_creations, plain.d_creations] == expected
     for i in range(kw["nroots"]):
         assert abs(got.eigenvalues[i] / want.eigenvalues[i] - 1) <= 1e-10
-        # the same path: the error estimates agree to 10 %; below 1e-10 (a hundredth of the threshold) they are the
-        # rounding noise of a converged residual (1.5e-14 against 4.7e-12 was seen) and only have to stay there
-        assert abs(got.errors[i] - want.errors[i]) <= 0.1 * want.errors[i] + 1e-10, "error estimates follow the same path"
+        assert got.errors[i] <= 1e-8 and want.errors[i] <= 1e-8
+        # 10 %; below 1e-11 they are the rounding noise of a converged residual
+        assert abs(got.errors[i] - plain.errors[i]) <= 0.1 * plain.errors[i] + 1e-11, "error estimates follow the same path"
 
 
 def test_error_estimates_are_true_residuals_with_a_capped_q_space(ctx):
