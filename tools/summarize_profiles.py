@@ -20,7 +20,8 @@ FAMILIES = {
     "gemm_inner": ("gemm_inner",),
     "gemm_outer": ("gemm_outer",),
     "residual": ("davidson_residual",),
-    "blas1": ("axpy", "scal", "copy", "fill", "precondition", "mgs_step", "shift"),
+    "blas1": ("axpy", "scal", "copy", "fill", "precondition", "mgs_step", "shift", "elementwise"),
+    "select": ("select_",),
     "harness_spmv": ("csr_apply", "banded_apply"),
 }
 
