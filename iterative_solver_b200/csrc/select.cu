@@ -23,6 +23,7 @@ namespace itsolv {
 enum { SEL_KEY = 0, SEL_IDX = 1, SEL_REMAINING = 2, SEL_COUNT = 3, SEL_NCAND = 4, SEL_TICKET = 5, SEL_GATHER_PASS = 6, SEL_HIST = 16 };
 
 constexpr unsigned long long kSelCandCapacity = 1ull << 20; // largest boundary bucket that is gathered
+constexpr int kSelUnroll = 4;                              // trips of a pass whose loads are in flight together
 
 struct SelParams {
   const double* x;
@@ -104,61 +105,80 @@ __global__ void __launch_bounds__(256)
     hist[threadIdx.x] = 0;
     __syncthreads();
     const int shift = 64 - 8 * (d < 8 ? d : 8); // key bytes fixed before this pass (gathering passes have d >= 1)
-    // warp-uniform trip count: every lane of a warp takes part in the votes below
-    for (size_t base = size_t(blockIdx.x) * blockDim.x + (threadIdx.x - lane); base < count;
-         base += size_t(gridDim.x) * blockDim.x) {
-      const size_t i = base + lane;
-      unsigned digit = 0;
-      bool ok = false, certain = false;
-      double value = 0;
-      unsigned long long u = 0, gi = 0;
-      if (i < count) {
-        if (from_candidates) {
-          u = p.cand_key[i];
-          gi = p.cand_idx[i];
-        } else {
-          value = sel_value(p, i);
-          u = sel_key(p, value);
-          gi = p.offset + i;
+    // Warp-uniform trip count: every lane of a warp takes part in the votes below. The loads of kSelUnroll trips are
+    // issued before any vote: the votes are convergence points the compiler does not move loads across, and with one
+    // trip in flight the pass is bound by DRAM latency (65 us for 80 MB) instead of bandwidth.
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    for (size_t base0 = size_t(blockIdx.x) * blockDim.x + (threadIdx.x - lane); base0 < count;
+         base0 += kSelUnroll * stride) {
+      double value[kSelUnroll];
+      unsigned long long key[kSelUnroll], gidx[kSelUnroll];
+      bool valid[kSelUnroll];
+#pragma unroll
+      for (int t = 0; t < kSelUnroll; ++t) {
+        const size_t i = base0 + size_t(t) * stride + lane;
+        valid[t] = i < count;
+        value[t] = 0;
+        key[t] = 0;
+        gidx[t] = 0;
+        if (valid[t]) {
+          if (from_candidates) {
+            key[t] = p.cand_key[i];
+            gidx[t] = p.cand_idx[i];
+          } else {
+            value[t] = sel_value(p, i);
+            gidx[t] = p.offset + i;
+          }
         }
-        ok = sel_digit(u, gi, d, kpre, ipre, digit);
-        certain = gather_now && (u >> shift) > (kpre >> shift);
       }
-      const unsigned okmask = __ballot_sync(full, ok);
-      if (gather_now) {
-        const unsigned cmask = __ballot_sync(full, certain);
-        if (cmask) {
-          const int leader = __ffs(int(cmask)) - 1;
-          unsigned long long pos = 0;
-          if (int(lane) == leader)
-            pos = atomicAdd(&state[SEL_COUNT], (unsigned long long)__popc(cmask));
-          pos = __shfl_sync(full, pos, leader) + __popc(cmask & below);
-          if (certain && pos < capacity) {
-            out_idx[pos] = (long long)gi;
-            out_val[pos] = value;
+#pragma unroll
+      for (int t = 0; t < kSelUnroll; ++t) {
+        if (base0 + size_t(t) * stride >= count) // warp-uniform
+          break;
+        unsigned digit = 0;
+        bool ok = false, certain = false;
+        const unsigned long long u = from_candidates ? key[t] : sel_key(p, value[t]);
+        const unsigned long long gi = gidx[t];
+        if (valid[t]) {
+          ok = sel_digit(u, gi, d, kpre, ipre, digit);
+          certain = gather_now && (u >> shift) > (kpre >> shift);
+        }
+        const unsigned okmask = __ballot_sync(full, ok);
+        if (gather_now) {
+          const unsigned cmask = __ballot_sync(full, certain);
+          if (cmask) {
+            const int leader = __ffs(int(cmask)) - 1;
+            unsigned long long pos = 0;
+            if (int(lane) == leader)
+              pos = atomicAdd(&state[SEL_COUNT], (unsigned long long)__popc(cmask));
+            pos = __shfl_sync(full, pos, leader) + __popc(cmask & below);
+            if (certain && pos < capacity) {
+              out_idx[pos] = (long long)gi;
+              out_val[pos] = value[t];
+            }
+          }
+          if (okmask) {
+            const int leader = __ffs(int(okmask)) - 1;
+            unsigned long long pos = 0;
+            if (int(lane) == leader)
+              pos = atomicAdd(&state[SEL_NCAND], (unsigned long long)__popc(okmask));
+            pos = __shfl_sync(full, pos, leader) + __popc(okmask & below);
+            if (ok && pos < kSelCandCapacity) {
+              cand_key[pos] = u;
+              cand_idx[pos] = gi;
+              cand_val[pos] = value[t];
+            }
           }
         }
         if (okmask) {
           const int leader = __ffs(int(okmask)) - 1;
-          unsigned long long pos = 0;
-          if (int(lane) == leader)
-            pos = atomicAdd(&state[SEL_NCAND], (unsigned long long)__popc(okmask));
-          pos = __shfl_sync(full, pos, leader) + __popc(okmask & below);
-          if (ok && pos < kSelCandCapacity) {
-            cand_key[pos] = u;
-            cand_idx[pos] = gi;
-            cand_val[pos] = value;
+          const unsigned first = __shfl_sync(full, digit, leader);
+          if (__all_sync(full, !ok || digit == first)) {
+            if (int(lane) == leader)
+              atomicAdd(&hist[first], unsigned(__popc(okmask)));
+          } else if (ok) {
+            atomicAdd(&hist[digit], 1u);
           }
-        }
-      }
-      if (okmask) {
-        const int leader = __ffs(int(okmask)) - 1;
-        const unsigned first = __shfl_sync(full, digit, leader);
-        if (__all_sync(full, !ok || digit == first)) {
-          if (int(lane) == leader)
-            atomicAdd(&hist[first], unsigned(__popc(okmask)));
-        } else if (ok) {
-          atomicAdd(&hist[digit], 1u);
         }
       }
     }

@@ -53,6 +53,7 @@ inline double now_seconds() {
  *   using R;                                          container type
  *   std::shared_ptr<ArrayHandlers<R,R,P>> handlers(); handler set
  *   R make_vector();                                  zero vector of the problem's global length
+ *   R make_output_vector();                           a vector the solve writes before it reads it (may be uninitialised)
  *   void export_local(const R&, double*);             this rank's rows to the caller's memory
  *   double* solutions_target(double* given, size_t count);  where the solutions go: `given`, or memory the backend
  *                                                     provides at that moment (after the solver has finished)
@@ -81,7 +82,7 @@ int run_solve(const itsolv_solve_spec& spec, Backend& backend, itsolv_solve_resu
   actions.reserve(nbuf);
   for (int i = 0; i < nbuf; ++i) {
     parameters.emplace_back(backend.make_vector());
-    actions.emplace_back(backend.make_vector());
+    actions.emplace_back(backend.make_output_vector()); // written by the operator / the solver before anything reads them
   }
   trace().clear();
   trace().enabled = spec.trace != 0;

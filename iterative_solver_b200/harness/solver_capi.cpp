@@ -270,6 +270,7 @@ struct DeviceBackend {
     v.fill(0.0);
     return v;
   }
+  R make_output_vector() { return R(n, ctx); }
   void export_local(const R& v, double* out) { v.download(out); }
   //! itsolv_harness_problem_solve_device: the solutions stay on the GPU, in memory taken from the context's pool only now,
   //! after the solver has finished (its high-water mark is over), and handed to the caller

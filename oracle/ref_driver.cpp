@@ -203,6 +203,7 @@ struct HostBackend {
   }
   auto handlers() { return h; }
   Vec make_vector() { return Vec(n, 0.0); }
+  Vec make_output_vector() { return Vec(n, 0.0); }
   void export_local(const Vec& v, double* out) { std::copy(v.begin(), v.end(), out); }
   double* solutions_target(double* given, size_t) { return given; }
   size_t n_local() { return n; }

@@ -85,13 +85,19 @@ def table(launches, path, with_dram=False):
     return agg, total
 
 
+def fresh(path, hours=6.0):
+    """gpurun_out/ keeps what earlier calls (and earlier rounds) brought back: only files of the last few hours count"""
+    import time
+    return os.path.exists(path) and time.time() - os.path.getmtime(path) < hours * 3600
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     p = os.path.join(SRC, "opbench_launches.csv")
-    if os.path.exists(p):
+    if fresh(p):
         table(per_launch(load(p)), os.path.join(OUT, f"ncu_launches_opbench_{TAG}.csv"))
     p = os.path.join(SRC, "bench_dram.csv")
-    if os.path.exists(p):
+    if fresh(p):
         launches = per_launch(load(p))
         ours = launches[len(launches) // 2:]  # the second (timed) solve of `bench.py --steps 1 --warmup 1`
         agg, total = table(ours, os.path.join(OUT, f"ncu_dram_bench_{TAG}.csv"), with_dram=True)
@@ -122,7 +128,7 @@ def main():
                                              "dram_bytes_per_launch": fam["bytes"] / max(fam["n"], 1),
                                              "avg_us": fam["us"] / max(fam["n"], 1)}}, f, indent=1)
     rep = os.path.join(SRC, "prof_gemm_inner.ncu-rep")
-    if os.path.exists(rep):
+    if fresh(rep):
         raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(raw.splitlines()))
         hdr, units = rows[0], rows[1]
@@ -144,7 +150,7 @@ def main():
     for src_name, out_name in (("bench_full_raw.csv", f"ncu_full_bench_{TAG}.csv"),
                                ("fused_raw.csv", f"ncu_full_fused_{TAG}.csv")):
         p = os.path.join(SRC, src_name)
-        if not os.path.exists(p):
+        if not fresh(p):
             continue
         rows = list(csv.reader(open(p)))
         rows = [r for r in rows if len(r) > 10 and (r[0] == "ID" or r[0] == "" or r[0].isdigit())]
@@ -167,12 +173,11 @@ def main():
             w.writerow([hdr[i] + (f" [{units[i]}]" if units[i] else "") for i in idx])
             for r in data:
                 w.writerow([short(r[i]) if hdr[i] == "Kernel Name" else r[i] for i in idx])
-    for name in ("opbench_r01.json",):
-        p = os.path.join(SRC, name)
-        if os.path.exists(p):
-            shutil.copy(p, os.path.join(OUT, f"opbench_{TAG}.json"))
+    p = os.path.join(SRC, f"opbench_{TAG}.json")
+    if fresh(p):
+        shutil.copy(p, os.path.join(OUT, f"opbench_{TAG}.json"))
     p = os.path.join(SRC, "bench.log")
-    if os.path.exists(p):
+    if fresh(p):
         lines = [l for l in open(p) if l.startswith("{")]
         if lines:
             with open(os.path.join(OUT, f"bench_{TAG}.json"), "w") as f:
