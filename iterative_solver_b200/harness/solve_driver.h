@@ -80,8 +80,11 @@ int run_solve(const itsolv_solve_spec& spec, Backend& backend, itsolv_solve_resu
   std::vector<R> parameters, actions;
   parameters.reserve(nbuf);
   actions.reserve(nbuf);
+  // Davidson and LinearEquations start from a guess that is written in full (unit vectors by the solver, or a copy of
+  // the right-hand sides); DIIS starts from the zero vector
+  const bool guess_overwrites = spec.kind != ITSOLV_KIND_DIIS;
   for (int i = 0; i < nbuf; ++i) {
-    parameters.emplace_back(backend.make_vector());
+    parameters.emplace_back(guess_overwrites ? backend.make_output_vector() : backend.make_vector());
     actions.emplace_back(backend.make_output_vector()); // written by the operator / the solver before anything reads them
   }
   trace().clear();

@@ -313,10 +313,12 @@ public:
       this->m_logger->max_trace_level = its::Logger::Info;
       this->m_logger->data_dump = true;
     }
-    const bool use_diagonals = problem.diagonals(actions.at(0));
-    std::unique_ptr<R> diagonals;
-    if (use_diagonals)
-      diagonals.reset(new R{this->m_handlers->qr().copy(actions.at(0))});
+    // the reference asks for the diagonal in actions[0] and keeps a copy (IterativeSolverTemplate.h:333-336); here the
+    // problem writes it into the kept vector directly
+    std::unique_ptr<R> diagonals(new R(actions.at(0).get().size(), actions.at(0).get().context()));
+    const bool use_diagonals = problem.diagonals(*diagonals);
+    if (!use_diagonals)
+      diagonals.reset();
     if (generate_initial_guess) {
       if (!use_diagonals)
         throw std::runtime_error("Default initial guess requested, but diagonal elements are not available");
@@ -563,7 +565,12 @@ protected:
       } else {
         if (root < i)
           throw std::logic_error("incorrect ordering of roots");
-        if (root > i)
+        // the residual of root `root` moves to position i. Positions from the working-set size on are scratch until the
+        // next action() and the roots ascend, so where both vectors own their storage the allocations change hands
+        // instead of 8n bytes being copied (a later root is never at a position that an earlier exchange touched)
+        if (root > i && actions[i].get().owns() && actions[root].get().owns())
+          actions[i].get().swap(actions[root].get());
+        else if (root > i)
           this->m_handlers->rr().copy(actions[i], actions[root]);
       }
       m_written_norms.push_back(written[root]);
