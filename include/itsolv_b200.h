@@ -135,6 +135,15 @@ int itsolv_mgs_step_dots_f64(itsolv_ctx* ctx, double inv_norm, double* ri, const
  * itsolv_mgs_chain_supported: 1 when the chain can run (option MGS_CHAIN, sums delivered by the kernels themselves). */
 int itsolv_mgs_chain_supported(itsolv_ctx* ctx, int w, size_t n);
 int itsolv_mgs_chain_f64(itsolv_ctx* ctx, double* const* r, int w, size_t n, double thresh, double* rows);
+/* The projection of a working set against the subspace and its R-R Gram-Schmidt as ONE chain: y_j = (yscale ? yscale[j] *
+ * y_j : y_j) + sum_i alpha[i*m+j] x_i for all m new vectors (itsolv_gemm_outer_scaled_f64 / itsolv_gemm_outer_f64 bit for
+ * bit), whose tail returns the first Gram row of the w vectors that stay (keep[0..w), ascending column indices; the others
+ * were found redundant, reference propose_rspace.h:482-512) and starts the pivot steps of itsolv_mgs_chain_f64 on them.
+ * rows: as itsolv_mgs_chain_f64. k <= 128, m <= 8. */
+int itsolv_project_mgs_chain_supported(itsolv_ctx* ctx, int k, int m, int w, size_t n);
+int itsolv_project_mgs_chain_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* x,
+                                 double* const* y, const double* yscale, const int* keep, int w, size_t n, double thresh,
+                                 double* rows);
 /* counter that every call which may write a vector advances (and DistrArrayCUDA::data() non-const): results cached
  * on the host side (ArrayHandlerCUDA's primed dots) are valid only while it stands still */
 unsigned long long itsolv_ctx_write_epoch(itsolv_ctx* ctx);

@@ -115,6 +115,9 @@ KERNEL_API = {
                                            C.c_size_t, c_double_p]),
     "itsolv_mgs_chain_supported": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t]),
     "itsolv_mgs_chain_f64": (C.c_int, [C.c_void_p, c_void_pp, C.c_int, C.c_size_t, C.c_double, c_double_p]),
+    "itsolv_project_mgs_chain_supported": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t]),
+    "itsolv_project_mgs_chain_f64": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_int, c_void_pp, c_void_pp, c_double_p,
+                                               C.POINTER(C.c_int), C.c_int, C.c_size_t, C.c_double, c_double_p]),
     "itsolv_gemm_outer_scaled_f64": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_int, c_void_pp, c_void_pp,
                                                C.c_size_t, c_double_p]),
     "itsolv_precondition_f64": (C.c_int, [C.c_void_p, c_void_pp, C.c_int, C.c_void_p, c_double_p, C.c_size_t]),

@@ -170,6 +170,10 @@ class Context:
         a = np.ascontiguousarray(alpha, dtype=np.float64)
         self._check(self.lib.itsolv_scal_batch_f64(self.handle, _dbl(a), _ptr_array(xs), len(xs), xs[0].numel()))
 
+    def fill_batch(self, alpha: Sequence[float], xs: Sequence):
+        a = np.ascontiguousarray(alpha, dtype=np.float64)
+        self._check(self.lib.itsolv_fill_batch_f64(self.handle, _dbl(a), _ptr_array(xs), len(xs), xs[0].numel()))
+
     def axpy_batch(self, alpha: Sequence[float], xs: Sequence, ys: Sequence):
         a = np.ascontiguousarray(alpha, dtype=np.float64)
         self._check(self.lib.itsolv_axpy_batch_f64(self.handle, _dbl(a), _ptr_array(xs), _ptr_array(ys), len(ys),

@@ -11,10 +11,16 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "gi_finalize.cuh"
 
 namespace itsolv {
 
+void fill_finalize(itsolv_ctx* ctx, int grid_bound, int km, GiFinalize* f, bool* host_direct); // gemm_inner.cu
+int launch_reduce_partials(itsolv_ctx* ctx, int grid, int km);                             // gemm_inner.cu
+int finish_with_peers(itsolv_ctx* ctx, int km, bool* host_direct);                         // gemm_inner.cu
+
 constexpr int kGoThreads = 256;
+constexpr int kGoMaxDots = 8; // columns of the variant that also returns a row of inner products of what it wrote
 constexpr int kGoUnroll = 4;
 
 struct GoParams {
@@ -26,6 +32,11 @@ struct GoParams {
   int ld; // leading dimension of alpha in shared memory (m rounded up to a multiple of MJ)
   int beta_zero;
   int scaled; // row k of the staged coefficients holds a factor per y: y_j is multiplied by it (rounded) before the sums
+  // DOTS variant (m <= MJ <= kGoMaxDots): <y_pivot, y_col[t]> of the values written, t < ndots, finished like the sums of
+  // the Gram kernels (last CTA, peer all-reduce, mapped host memory, optional chain coefficients; gi_finalize.cuh)
+  int dot_pivot, ndots;
+  int dot_col[kGoMaxDots];
+  GiFinalize fin;
 };
 
 template <class RV>
@@ -42,6 +53,10 @@ struct RowOps<double2> {
     acc.x = __dmul_rn(acc.x, s);
     acc.y = __dmul_rn(acc.y, s);
   }
+  static __device__ __forceinline__ void dot_to(double& d, const double2& a, const double2& b) {
+    d = fma(a.x, b.x, d);
+    d = fma(a.y, b.y, d);
+  }
 };
 template <>
 struct RowOps<double> {
@@ -49,6 +64,7 @@ struct RowOps<double> {
   static __device__ __forceinline__ double zero() { return 0.0; }
   static __device__ __forceinline__ void fma_to(double& acc, double a, const double& x) { acc = fma(a, x, acc); }
   static __device__ __forceinline__ void scale(double& acc, double s) { acc = __dmul_rn(acc, s); }
+  static __device__ __forceinline__ void dot_to(double& d, const double& a, const double& b) { d = fma(a, b, d); }
 };
 
 //! MJ consecutive coefficients of one alpha row; the address is warp-uniform (broadcast) and 16-byte aligned for MJ >= 2
@@ -67,8 +83,8 @@ __device__ __forceinline__ void load_alpha_row(const double* __restrict__ arow, 
 }
 
 //! one thread, one row group `r` (index in units of RV), all column chunks
-template <int MJ, class RV, bool SCALED>
-__device__ __forceinline__ void expand_rows(const GoParams& p, const double* __restrict__ sa, size_t r) {
+template <int MJ, class RV, bool SCALED, bool DOTS>
+__device__ __forceinline__ void expand_rows(const GoParams& p, const double* __restrict__ sa, size_t r, double (&dots)[MJ]) {
   using Ops = RowOps<RV>;
   for (int jc = 0; jc < p.m; jc += MJ) {
     RV acc[MJ];
@@ -113,10 +129,20 @@ __device__ __forceinline__ void expand_rows(const GoParams& p, const double* __r
     for (int b = 0; b < MJ; ++b)
       if (jc + b < p.m)
         reinterpret_cast<RV*>(p.y[jc + b])[r] = acc[b];
+    if constexpr (DOTS) { // one column chunk (m <= MJ): products of the pivot column with every column, from the written values
+      RV first = acc[0];
+#pragma unroll
+      for (int b = 1; b < MJ; ++b)
+        if (b == p.dot_pivot)
+          first = acc[b];
+#pragma unroll
+      for (int b = 0; b < MJ; ++b)
+        Ops::dot_to(dots[b], first, acc[b]);
+    }
   }
 }
 
-template <int MJ, bool VEC, bool SCALED>
+template <int MJ, bool VEC, bool SCALED, bool DOTS>
 __global__ void __launch_bounds__(kGoThreads, 2) gemm_outer_kernel(const __grid_constant__ GoParams p) {
   extern __shared__ __align__(16) double sa[]; // k (+1 when scaled) x ld, zero padded columns
   for (int e = threadIdx.x; e < (p.k + p.scaled) * p.ld; e += blockDim.x) {
@@ -124,39 +150,83 @@ __global__ void __launch_bounds__(kGoThreads, 2) gemm_outer_kernel(const __grid_
     sa[e] = j < p.m ? p.alpha[size_t(i) * p.m + j] : 0.0;
   }
   __syncthreads();
+  double dots[MJ];
+#pragma unroll
+  for (int b = 0; b < MJ; ++b)
+    dots[b] = 0.0;
   const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = size_t(gridDim.x) * blockDim.x;
   if (VEC) {
     const size_t npairs = p.n / 2;
     for (size_t r = tid; r < npairs; r += nthreads)
-      expand_rows<MJ, double2, SCALED>(p, sa, r);
+      expand_rows<MJ, double2, SCALED, DOTS>(p, sa, r, dots);
     if ((p.n & 1) && tid == 0)
-      expand_rows<MJ, double, SCALED>(p, sa, p.n - 1);
+      expand_rows<MJ, double, SCALED, DOTS>(p, sa, p.n - 1, dots);
   } else {
     for (size_t r = tid; r < p.n; r += nthreads)
-      expand_rows<MJ, double, SCALED>(p, sa, r);
+      expand_rows<MJ, double, SCALED, DOTS>(p, sa, r, dots);
+  }
+  if constexpr (DOTS) {
+    __shared__ double s_part[kGoThreads / 32][MJ];
+    __shared__ int s_is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int b = 0; b < MJ; ++b) {
+      double v = dots[b];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+        v += __shfl_down_sync(0xffffffffu, v, off);
+      if (lane == 0)
+        s_part[warp][b] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < p.ndots) {
+      const int col = p.dot_col[threadIdx.x];
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < kGoThreads / 32; ++w)
+        sum += s_part[w][col];
+      p.fin.partials[size_t(blockIdx.x) * p.ndots + threadIdx.x] = sum;
+    }
+    gi_finalize(p.fin, p.ndots, &s_is_last);
   }
 }
+
+//! request for the DOTS variant: <y_pivot, y_cols[t]> of the written values, delivered as fill_finalize() decides
+struct GoDots {
+  int pivot, ncols;
+  const int* cols;
+  bool* direct;
+};
 
 using GoKernel = void (*)(const GoParams);
 template <int MJ>
 static GoKernel go_pick_vec(bool vec, bool scaled) {
   if (scaled)
-    return vec ? gemm_outer_kernel<MJ, true, true> : gemm_outer_kernel<MJ, false, true>;
-  return vec ? gemm_outer_kernel<MJ, true, false> : gemm_outer_kernel<MJ, false, false>;
+    return vec ? gemm_outer_kernel<MJ, true, true, false> : gemm_outer_kernel<MJ, false, true, false>;
+  return vec ? gemm_outer_kernel<MJ, true, false, false> : gemm_outer_kernel<MJ, false, false, false>;
 }
-static GoKernel go_pick(int mj, bool vec, bool scaled) {
+template <int MJ>
+static GoKernel go_pick_dots(bool vec, bool scaled) {
+  if constexpr (MJ <= kGoMaxDots) {
+    if (scaled)
+      return vec ? gemm_outer_kernel<MJ, true, true, true> : gemm_outer_kernel<MJ, false, true, true>;
+    return vec ? gemm_outer_kernel<MJ, true, false, true> : gemm_outer_kernel<MJ, false, false, true>;
+  }
+  return nullptr;
+}
+static GoKernel go_pick(int mj, bool vec, bool scaled, bool dots = false) {
   switch (mj) {
   case 1:
-    return go_pick_vec<1>(vec, scaled);
+    return dots ? go_pick_dots<1>(vec, scaled) : go_pick_vec<1>(vec, scaled);
   case 2:
-    return go_pick_vec<2>(vec, scaled);
+    return dots ? go_pick_dots<2>(vec, scaled) : go_pick_vec<2>(vec, scaled);
   case 4:
-    return go_pick_vec<4>(vec, scaled);
+    return dots ? go_pick_dots<4>(vec, scaled) : go_pick_vec<4>(vec, scaled);
   case 8:
-    return go_pick_vec<8>(vec, scaled);
+    return dots ? go_pick_dots<8>(vec, scaled) : go_pick_vec<8>(vec, scaled);
   case 16:
-    return go_pick_vec<16>(vec, scaled);
+    return dots ? nullptr : go_pick_vec<16>(vec, scaled);
   }
   return nullptr;
 }
@@ -168,7 +238,7 @@ using namespace itsolv;
 extern "C" {
 
 static int gemm_outer_impl(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* xx,
-                           double* const* yy, size_t n, int beta_zero, const double* yscale);
+                           double* const* yy, size_t n, int beta_zero, const double* yscale, const GoDots* dots = nullptr);
 
 int itsolv_gemm_outer_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* xx,
                           double* const* yy, size_t n, int beta_zero) {
@@ -187,7 +257,7 @@ int itsolv_gemm_outer_scaled_f64(itsolv_ctx* ctx, const double* alpha, int k, in
 }
 
 static int gemm_outer_impl(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* xx,
-                           double* const* yy, size_t n, int beta_zero, const double* yscale) {
+                           double* const* yy, size_t n, int beta_zero, const double* yscale, const GoDots* dots) {
   ctx->counters.n_gemm_outer++;
   ++ctx->write_epoch; // before any early return: every rank advances alike, also one with an empty shard
   if (m <= 0)
@@ -266,10 +336,10 @@ static int gemm_outer_impl(itsolv_ctx* ctx, const double* alpha, int k, int m, c
       int mj = 1;
       while (mj < mb && mj < 16)
         mj *= 2;
-      if (ctx->opt_go_cols > 0)
+      if (ctx->opt_go_cols > 0 && !dots)
         mj = ctx->opt_go_cols;
       p.ld = ((mb + mj - 1) / mj) * mj;
-      GoKernel kernel = go_pick(mj, vec, scaled);
+      GoKernel kernel = go_pick(mj, vec, scaled, dots != nullptr);
       ITSOLV_REQUIRE(kernel != nullptr, "gemm_outer: column tile not instantiated");
       const size_t smem = size_t(kb + p.scaled) * p.ld * sizeof(double);
       if (ensure_dynamic_smem(ctx, reinterpret_cast<const void*>(kernel), smem))
@@ -281,15 +351,56 @@ static int gemm_outer_impl(itsolv_ctx* ctx, const double* alpha, int k, int m, c
       size_t grid = std::min<size_t>((units + kGoThreads - 1) / kGoThreads, size_t(ctx->num_sms) * per_sm);
       if (grid == 0)
         grid = 1;
+      p.dot_pivot = p.ndots = 0;
+      if (dots) { // one block (checked by the caller): the row of inner products is finished by this launch's tail
+        p.dot_pivot = dots->pivot;
+        p.ndots = dots->ncols;
+        for (int t = 0; t < dots->ncols; ++t)
+          p.dot_col[t] = dots->cols[t];
+        if (ensure_partials(ctx, grid * size_t(dots->ncols)))
+          return 1;
+        fill_finalize(ctx, ctx->num_sms * 6, dots->ncols, &p.fin, dots->direct);
+      }
       mark_launch(ctx);
       kernel<<<int(grid), kGoThreads, smem, ctx->stream>>>(p);
       ITSOLV_CUDA(cudaGetLastError());
       ctx->counters.launches += 1;
       if (stage_done(ctx, slot))
         return 1;
+      if (dots && !p.fin.fused) {
+        if (launch_reduce_partials(ctx, int(grid), dots->ncols))
+          return 1;
+        if (finish_with_peers(ctx, dots->ncols, dots->direct))
+          return 1;
+      }
     }
   }
   return 0;
 }
 
 } // extern "C"
+
+namespace itsolv {
+
+bool gemm_outer_dots_supported(int k, int m) { return k >= 1 && k <= ITSOLV_MAX_PANEL && m >= 1 && m <= kGoMaxDots; }
+
+//! y_j = (yscale ? yscale_j * y_j : y_j) + sum_i alpha(i,j) x_i for all m columns, and from the written values the row
+//! {<y_pivot, y_cols[t]>}: the projection of a working set together with the first Gram row of its R-R Gram-Schmidt
+//! (mgs_fused.cu). The operands must not alias (the caller's working set never does).
+int gemm_outer_with_dots(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* xx, double* const* yy,
+                         size_t n, const double* yscale, int pivot, const int* cols, int ncols, bool* direct) {
+  ITSOLV_REQUIRE(gemm_outer_dots_supported(k, m) && n > 0, "gemm_outer_with_dots: shape not supported");
+  ITSOLV_REQUIRE(ncols >= 1 && ncols <= m && pivot >= 0 && pivot < m, "gemm_outer_with_dots: invalid columns");
+  for (int j = 0; j < m; ++j) {
+    for (int i = 0; i < k; ++i)
+      ITSOLV_REQUIRE(xx[i] != yy[j], "gemm_outer_with_dots: a target is also a source");
+    for (int j2 = 0; j2 < j; ++j2)
+      ITSOLV_REQUIRE(yy[j2] != yy[j], "gemm_outer_with_dots: the same target twice");
+  }
+  if (yscale)
+    ctx->counters.n_scal += m;
+  GoDots dots{pivot, ncols, cols, direct};
+  return gemm_outer_impl(ctx, alpha, k, m, xx, yy, n, 0, yscale, &dots);
+}
+
+} // namespace itsolv

@@ -211,6 +211,9 @@ namespace itsolv {
 
 int gemm_inner_device(itsolv_ctx* ctx, const double* const* xx, int k, const double* const* yy, int m, size_t n,
                       bool* host_direct); // gemm_inner.cu
+bool gemm_outer_dots_supported(int k, int m); // gemm_outer.cu
+int gemm_outer_with_dots(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* xx, double* const* yy,
+                         size_t n, const double* yscale, int pivot, const int* cols, int ncols, bool* direct); // gemm_outer.cu
 int wait_host_result(itsolv_ctx* ctx);   // gemm_inner.cu: waits for the newest sequence word
 
 //! launch one step; the sums are delivered as fill_finalize() decides (no waiting here)
@@ -340,6 +343,62 @@ int itsolv_mgs_chain_f64(itsolv_ctx* ctx, double* const* r, int w, size_t n, dou
     offset += size_t(m + 1);
   }
   // one wait for the whole chain: the sequence word of the last launch implies all earlier ones (stream order)
+  if (wait_host_result(ctx))
+    return 1;
+  for (size_t e = 0; e < offset; ++e)
+    rows[e] = ctx->h_result[e];
+  return 0;
+}
+
+int itsolv_project_mgs_chain_supported(itsolv_ctx* ctx, int k, int m, int w, size_t n) {
+  return (w >= 1 && w <= m && gemm_outer_dots_supported(k, m) && itsolv_mgs_chain_supported(ctx, w, n)) ? 1 : 0;
+}
+
+int itsolv_project_mgs_chain_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* x,
+                                 double* const* y, const double* yscale, const int* keep, int w, size_t n, double thresh,
+                                 double* rows) {
+  ITSOLV_REQUIRE(itsolv_project_mgs_chain_supported(ctx, k, m, w, n), "itsolv_project_mgs_chain_f64: not available for this call");
+  ITSOLV_REQUIRE(alpha && x && y && keep && rows, "itsolv_project_mgs_chain_f64: null argument");
+  for (int i = 0; i < w; ++i)
+    ITSOLV_REQUIRE(keep[i] >= 0 && keep[i] < m && (i == 0 || keep[i] > keep[i - 1]),
+                   "itsolv_project_mgs_chain_f64: the kept columns must ascend");
+  double* r[kMfMaxLater + 1];
+  for (int i = 0; i < w; ++i)
+    r[i] = y[keep[i]];
+  ctx->counters.n_scal += w;
+  ctx->counters.n_axpy += w * (w - 1) / 2;
+  ctx->counters.n_dot += w * (w + 1) / 2 + w;
+  double* chain = ctx->d_result + 12288;
+  size_t offset = 0;
+  bool direct = false;
+  {
+    // the projection of all m new vectors; its tail returns the first pivot's norm and overlaps with the later kept
+    // vectors (the Gram row that itsolv_mgs_chain_f64 spends a launch on) and prepares step 0
+    ctx->result_offset = offset;
+    ctx->chain_out = chain;
+    ctx->chain_offset = 0;
+    ctx->chain_count = w;
+    ctx->chain_thresh = thresh;
+    if (gemm_outer_with_dots(ctx, alpha, k, m, x, y, n, yscale, keep[0], keep, w, &direct))
+      return 1;
+    ITSOLV_REQUIRE(direct, "itsolv_project_mgs_chain_f64: the Gram row was not delivered by the kernel");
+    offset += size_t(w);
+  }
+  for (int i = 0; i < w; ++i) {
+    const int later = w - i - 1;
+    CallScope scope(ctx, OP_BLAS1, 16.0 * double(n) * (later + 1));
+    ctx->result_offset = offset;
+    if (later > 0) {
+      ctx->chain_out = chain + 32 * (i + 1);
+      ctx->chain_offset = 1;
+      ctx->chain_count = later;
+      ctx->chain_thresh = thresh;
+    }
+    if (mgs_step_launch(ctx, 1.0, r[i], nullptr, r + i + 1, later, n, chain + 32 * i, &direct))
+      return 1;
+    ITSOLV_REQUIRE(direct, "itsolv_project_mgs_chain_f64: the sums were not delivered by the kernel");
+    offset += size_t(later + 1);
+  }
   if (wait_host_result(ctx))
     return 1;
   for (size_t e = 0; e < offset; ++e)

@@ -756,16 +756,18 @@ protected:
     };
     fill_ov();
     /*
-     * When two or more of the new vectors lie in the span of P+Q+D (preconditioned residuals of nearly converged roots:
-     * they are dominated by the root's own Ritz vector), the overlap matrix has a null space of that dimension, the null
-     * vectors the redundancy test looks at (reference propose_rspace.h:482-512) are an arbitrary basis of it, and WHICH
-     * vectors the test drops follows the rounding pattern of the overlaps. The reference measures them on the normalised
-     * vectors as stored, and that pattern (the rounding of every element by the scaling) is what its decisions follow,
+     * When new vectors lie in the span of P+Q+D (preconditioned residuals of nearly converged roots: they are dominated
+     * by the root's own Ritz vector), the overlap matrix has a null space; with two or more such vectors the null vectors
+     * the redundancy test looks at (reference propose_rspace.h:482-512) are an arbitrary basis of it, and WHICH vectors
+     * the test drops follows the rounding pattern of the overlaps. The reference measures them on the normalised vectors
+     * as stored, and that pattern (the rounding of every element by the scaling) is what its decisions follow,
      * identically on the CPU and on these handlers. Overlaps of the unscaled vectors multiplied by the factors on the host
      * are the same numbers to 4e-16, but decide differently; the run then keeps the wrong member of such a set, the D space
      * built from it no longer reproduces the converged roots beyond ~1e-7, and they re-enter the working set
-     * (profiles/notes_r02.md). So in that case - and only then - the vectors are normalised first and the overlaps measured
-     * again, exactly as the reference does; otherwise the scaling stays folded into the projection kernel.
+     * (profiles/notes_r02.md). So whenever the test finds anything redundant - and only then - the vectors are normalised
+     * first and the overlaps measured again, exactly as the reference does; otherwise the scaling stays folded into the
+     * projection kernel. (ITSOLV_REMEASURE_FROM = null-space dimension from which this happens, default 1; the failure
+     * above needed 2.)
      */
     bool remeasured = false;
     auto null_space = [&]() {
@@ -774,7 +776,7 @@ protected:
     };
     auto svd = nN > 0 ? null_space() : std::list<its::SVD<double>>{};
     static const size_t remeasure_from = [] {
-      const char* e = std::getenv("ITSOLV_REMEASURE_FROM"); // null-space dimension from which the overlaps are re-measured
+      const char* e = std::getenv("ITSOLV_REMEASURE_FROM");
       return e && *e ? size_t(std::atoi(e)) : size_t(1);
     }();
     if (nP == 0 && svd.size() >= remeasure_from) {

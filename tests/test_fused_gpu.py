@@ -38,6 +38,8 @@ def test_batched_kernels_bit_exact(ctx, oracle, n):
     assert np.array_equal(host(ys), want)
     ctx.scal_batch(alpha, xs)
     assert np.array_equal(host(xs), np.stack([oracle.c.scal(alpha[k], X[k].copy()) for k in range(5)]))
+    ctx.fill_batch(alpha, xs)
+    assert np.array_equal(host(xs), np.repeat(alpha[:, None], n, axis=1))
     # one R-R Gram-Schmidt step == scal of the pivot followed by axpys onto the later vectors
     R = rng.standard_normal((4, n))
     ov = rng.standard_normal(3)
