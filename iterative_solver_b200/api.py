@@ -200,6 +200,20 @@ class Context:
         self._check(self.lib.itsolv_mgs_chain_f64(self.handle, _ptr_array(rs), w, rs[0].numel(), thresh, _dbl(rows)))
         return rows
 
+    def project_mgs_chain(self, alpha: np.ndarray, xx: Sequence, yy: Sequence, yscale, keep: Sequence[int],
+                          thresh: float = 1e-10) -> np.ndarray:
+        """projection of all yy against xx (scaled by yscale when given) and the Gram-Schmidt chain of yy[keep] as one chain
+        of launches (itsolv_project_mgs_chain_f64); returns the rows of inner products as mgs_chain does"""
+        k, m, w = len(xx), len(yy), len(keep)
+        a = np.ascontiguousarray(alpha, dtype=np.float64).reshape(k, m)
+        s = np.ascontiguousarray(yscale, dtype=np.float64) if yscale is not None else None
+        kp = (C.c_int * w)(*[int(i) for i in keep])
+        rows = np.zeros(w + w * (w + 1) // 2)
+        self._check(self.lib.itsolv_project_mgs_chain_f64(self.handle, _dbl(a), k, m, _ptr_array(xx), _ptr_array(yy),
+                                                          _dbl(s) if s is not None else None, kp, w, yy[0].numel(), thresh,
+                                                          _dbl(rows)))
+        return rows
+
     def dot(self, x, y) -> float:
         r = C.c_double()
         self._check(self.lib.itsolv_dot_f64(self.handle, _ptr(x), _ptr(y), x.numel(), C.byref(r)))

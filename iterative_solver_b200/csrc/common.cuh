@@ -99,6 +99,7 @@ struct itsolv_ctx {
   int opt_blas1_ctas = 0; // CTAs per SM for streaming kernels
   int opt_ds_ring = 0;    // davidson_residual: <0 never use the cp.async ring kernel
   int opt_mgs_chain = 0;   // R-R Gram-Schmidt steps chained on the device: 0 default (on, see mgs_fused.cu), -1 off
+  int opt_project_chain = 0; // <0: the projection of a working set does not carry the first Gram row of the chain
   int opt_p2p_allreduce = 0; // <0: use ncclAllReduce even when the peer buffers are mapped
   int opt_p2p_halo = 0;      // <0: halo rows by ncclSend/ncclRecv even when the peer buffers are mapped
 

@@ -244,6 +244,7 @@ static int ctx_init(itsolv_ctx* ctx, int device, cudaStream_t stream, bool own) 
   ctx->opt_blas1_ctas = env_int("ITSOLV_BLAS1_CTAS", 0);
   ctx->opt_p2p_allreduce = env_int("ITSOLV_P2P_ALLREDUCE", 0);
   ctx->opt_p2p_halo = env_int("ITSOLV_P2P_HALO", 0);
+  ctx->opt_project_chain = env_int("ITSOLV_PROJECT_CHAIN", 0);
   ctx->opt_ds_ring = env_int("ITSOLV_DS_RING", 0);
   ctx->opt_mgs_chain = env_int("ITSOLV_MGS_CHAIN", 0);
   return 0;
@@ -329,7 +330,7 @@ int itsolv_ctx_set_option(itsolv_ctx* ctx, const char* name, int value) {
                {"GI_DIRECT", &ctx->opt_gi_direct},   {"GI_DIRECT_CTAS", &ctx->opt_gi_direct_ctas},
                {"GI_MMA", &ctx->opt_gi_mma},       {"GO_COLS", &ctx->opt_go_cols},
                {"GO_CTAS", &ctx->opt_go_ctas},       {"BLAS1_CTAS", &ctx->opt_blas1_ctas},
-               {"P2P_ALLREDUCE", &ctx->opt_p2p_allreduce}, {"P2P_HALO", &ctx->opt_p2p_halo}, {"DS_RING", &ctx->opt_ds_ring},
+               {"P2P_ALLREDUCE", &ctx->opt_p2p_allreduce}, {"P2P_HALO", &ctx->opt_p2p_halo}, {"PROJECT_CHAIN", &ctx->opt_project_chain}, {"DS_RING", &ctx->opt_ds_ring},
                {"MGS_CHAIN", &ctx->opt_mgs_chain}};
   for (auto& t : table)
     if (std::strcmp(t.n, name) == 0) {

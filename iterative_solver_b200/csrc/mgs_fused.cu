@@ -351,7 +351,10 @@ int itsolv_mgs_chain_f64(itsolv_ctx* ctx, double* const* r, int w, size_t n, dou
 }
 
 int itsolv_project_mgs_chain_supported(itsolv_ctx* ctx, int k, int m, int w, size_t n) {
-  return (w >= 1 && w <= m && gemm_outer_dots_supported(k, m) && itsolv_mgs_chain_supported(ctx, w, n)) ? 1 : 0;
+  return (ctx->opt_project_chain >= 0 && w >= 1 && w <= m && gemm_outer_dots_supported(k, m) &&
+          itsolv_mgs_chain_supported(ctx, w, n))
+             ? 1
+             : 0;
 }
 
 int itsolv_project_mgs_chain_f64(itsolv_ctx* ctx, const double* alpha, int k, int m, const double* const* x,

@@ -291,6 +291,50 @@ public:
       m_observer('g', 1, rows.size(), rows.data());
     return rows;
   }
+  //! can the projection of `m` new vectors against `k` subspace vectors and the Gram-Schmidt chain of the `kept` ones run
+  //! as one chain (rank-independent decision)
+  bool project_mgs_chain_supported(size_t k, size_t m, const VecRef<AL>& kept) const {
+    if (kept.empty())
+      return false;
+    const auto& first = kept[0].get();
+    const size_t nranks = size_t(itsolv_comm_size(first.context()));
+    return first.size() >= nranks && itsolv_project_mgs_chain_supported(first.context(), int(k), int(m), int(kept.size()),
+                                                                         first.size() / nranks) != 0;
+  }
+  /*!
+   * gemm_outer (with `yscale`: gemm_outer_scaled) of all new vectors yy, and the Gram-Schmidt chain of the vectors
+   * yy[keep[.]] that stay, as one chain of launches: the projection's tail returns the first Gram row
+   * (itsolv_project_mgs_chain_f64). Returns the rows of inner products in the layout of mgs_chain().
+   */
+  std::vector<double> project_mgs_chain(const Matrix<value_type>& alphas, const CVecRef<AR>& xx, const VecRef<AL>& yy,
+                                        const std::vector<double>* yscale, const std::vector<int>& keep, double thresh) {
+    const size_t nx = alphas.rows(), ny = alphas.cols(), w = keep.size();
+    if (nx > xx.size() || ny > yy.size() || (yscale && ny > yscale->size()) || w == 0 || w > ny)
+      throw std::out_of_range("project_mgs_chain: dimensions of alphas do not match xx, yy, yscale, keep");
+    this->m_counter->gemm_outer++;
+    this->m_counter->scal += int(w) + (yscale ? int(ny) : 0);
+    this->m_counter->axpy += int(w * (w - 1) / 2);
+    this->m_counter->dot += int(w * (w + 1) / 2 + w);
+    std::vector<const double*> px(nx);
+    std::vector<double*> py(ny);
+    const AL& first = yy[0].get();
+    for (size_t i = 0; i < nx; ++i) {
+      first.require_compatible(xx[i].get(), "project_mgs_chain");
+      px[i] = xx[i].get().data();
+    }
+    for (size_t j = 0; j < ny; ++j) {
+      first.require_compatible(yy[j].get(), "project_mgs_chain");
+      py[j] = yy[j].get().data();
+    }
+    std::vector<double> rows(w + w * (w + 1) / 2);
+    check(itsolv_project_mgs_chain_f64(first.context(), alphas.data().data(), int(nx), int(ny), px.data(), py.data(),
+                                       yscale ? yscale->data() : nullptr, keep.data(), int(w), first.local_size(), thresh,
+                                       rows.data()),
+          "ArrayHandlerCUDA::project_mgs_chain");
+    if (m_observer)
+      m_observer('g', 1, rows.size(), rows.data());
+    return rows;
+  }
   //! yy[j] = yscale[j] * yy[j] + sum_i alphas(i,j) xx[i]: scal_batch followed by gemm_outer, in one pass
   void gemm_outer_scaled(const Matrix<value_type>& alphas, const CVecRef<AR>& xx, const VecRef<AL>& yy,
                          const std::vector<double>& yscale) {

@@ -809,6 +809,7 @@ protected:
     // multiplies the normalisation factor in. It is applied to all new vectors, also those the redundancy test has marked
     // (they are discarded right after; each column of the expansion is its own chain of operations).
     bool scaled = nP > 0 || remeasured;
+    std::vector<double> chain_rows; // of the Gram-Schmidt chain, when it has run together with the projection
     if (nN > 0 && nX > 0) {
       Matrix<double> c({nX, nN});
       for (size_t j = 0; j < nN; ++j)
@@ -833,10 +834,23 @@ protected:
           for (size_t i = 0; i < nD; ++i)
             cd(nQ + i, j) = c(dims.oD + i, j);
         }
-        if (scaled)
+        // the vectors that stay after the redundancy test, in their order
+        std::vector<int> keep;
+        VecRef<R> kept;
+        for (size_t j = 0; j < nN; ++j)
+          if (std::find(redundant.begin(), redundant.end(), int(j)) == redundant.end()) {
+            keep.push_back(int(j));
+            kept.push_back(wresidual[j]);
+          }
+        if (m_dense->project_mgs_chain_supported(nQ + nD, nN, kept)) {
+          // projection and R-R Gram-Schmidt as one chain: the first Gram row comes from the projection kernel's tail
+          chain_rows = m_dense->project_mgs_chain(cd, xdense, wresidual, scaled ? nullptr : &factor, keep,
+                                                  fused_norm_thresh());
+        } else if (scaled) {
           m_dense->gemm_outer(cd, xdense, wresidual);
-        else
+        } else {
           m_dense->gemm_outer_scaled(cd, xdense, wresidual, factor);
+        }
         scaled = true;
       }
     }
@@ -849,11 +863,11 @@ protected:
     std::vector<int> null_params;
     std::vector<double> final_dot(nN, -1.0); // <r_i, r_i> after the step, where known
     std::vector<double> row;                  // {<r_i, r_i>, <r_i, r_j> for j > i} of the current pivot
-    const bool chained = nN > 0 && m_dense->mgs_chain_supported(wresidual);
+    const bool chained = nN > 0 && (!chain_rows.empty() || m_dense->mgs_chain_supported(wresidual));
     if (chained) {
       // all pivot steps as one chain of launches: the coefficients of a step are formed on the device by the tail of
       // the launch before it, with this loop's arithmetic; the decisions are repeated here from the returned sums
-      const auto rows = m_dense->mgs_chain(wresidual, fused_norm_thresh());
+      const auto rows = !chain_rows.empty() ? chain_rows : m_dense->mgs_chain(wresidual, fused_norm_thresh());
       size_t at = 0;
       for (size_t i = 0; i < nN; ++i) {
         const double rr = i == 0 ? rows[0] : rows[at + 1]; // <r_i, r_i> before its own step

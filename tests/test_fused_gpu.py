@@ -322,6 +322,34 @@ def test_mgs_chain_equals_the_steps_one_by_one(ctx, n, w):
     assert rows.size == w + w * (w + 1) // 2 and abs(rows[0] - R[0] @ R[0]) <= 1e-12 * (R[0] @ R[0])
 
 
+@pytest.mark.parametrize("n,k,m,keep,scaled", [(50001, 12, 4, [0, 1, 2, 3], True), (20000, 5, 4, [1, 3], True),
+                                               (4097, 3, 1, [0], False), (70002, 24, 8, [0, 2, 3, 5, 6, 7], True),
+                                               (33, 2, 3, [2], False), (100000, 128, 6, [0, 1, 2, 3, 4, 5], False)])
+def test_projection_with_the_first_gram_row_in_its_tail(ctx, n, k, m, keep, scaled):
+    """itsolv_project_mgs_chain_f64 against gemm_outer(_scaled) followed by itsolv_mgs_chain_f64 on the kept vectors: the
+    projected vectors that are not kept are bit-identical; the first Gram row comes from a different kernel (summation
+    order), so the orthonormalised vectors agree to rounding and the rows to 1e-12"""
+    rng = np.random.default_rng(n + k + m)
+    X = rng.standard_normal((k, n))
+    Y = rng.standard_normal((m, n)) + 0.2 * rng.standard_normal(n)[None, :]
+    alpha = 0.05 * rng.standard_normal((k, m))
+    scale = rng.uniform(0.5, 2.0, m)
+    xs, a, b = dev_rows(X), dev_rows(Y), dev_rows(Y)
+    rows = ctx.project_mgs_chain(alpha, xs, a, scale if scaled else None, keep)
+    if scaled:
+        ctx.gemm_outer_scaled(alpha, xs, b, scale)
+    else:
+        ctx.gemm_outer(alpha, xs, b)
+    want_rows = ctx.mgs_chain([b[i] for i in keep])
+    A, B = host(a), host(b)
+    dropped = [j for j in range(m) if j not in keep]
+    assert np.array_equal(A[dropped], B[dropped])
+    assert np.abs(A[keep] - B[keep]).max() <= 1e-13
+    assert np.abs(rows - want_rows).max() <= 1e-12 * max(1.0, np.abs(want_rows).max())
+    Q = A[keep]
+    assert np.abs(Q @ Q.T - np.eye(len(keep))).max() <= 1e-12
+
+
 def test_mgs_chain_leaves_a_null_pivot_alone(ctx):
     rng = np.random.default_rng(11)
     R = rng.standard_normal((4, 6000))
@@ -346,17 +374,24 @@ def test_fused_solve_with_chained_gram_schmidt_matches_reference_golden(ctx, nam
     old = ctx.set_option("MGS_CHAIN", 1)
     try:
         res, sol = H.solve(ctx, H.make_spec(fused=1, **want["spec"]), want_solutions=True)
+        projected, _ = H.solve(ctx, H.make_spec(fused=1, **want["spec"]))
+        # without the first Gram row in the projection's tail: the chain and the steps one by one are the same launches
+        # with the same coefficients, bit for bit
+        ctx.set_option("PROJECT_CHAIN", -1)
         plain, _ = H.solve(ctx, H.make_spec(fused=1, **want["spec"]))
         ctx.set_option("MGS_CHAIN", -1)  # the steps one by one, coefficients formed on the host
         unchained, _ = H.solve(ctx, H.make_spec(fused=1, **want["spec"]))
         assert unchained.kernel_launches == plain.kernel_launches  # the same launches, only the waiting differs
+        assert projected.kernel_launches <= plain.kernel_launches  # one launch fewer per projected working set
     finally:
         ctx.set_option("MGS_CHAIN", old)
+        ctx.set_option("PROJECT_CHAIN", 0)
     assert res.iterations == want["iterations"] and res.converged == want["converged"]
     assert [res.r_creations, res.q_creations, res.p_creations, res.d_creations] == want["creations"]
     ev = np.array([res.eigenvalues[i] for i in range(res.nroots)])
     assert np.abs(ev / np.array(want["eigenvalues"]) - 1).max() <= 1e-10
     # bit-identical vectors along the way: the same eigenvalues as without the chain, to the last bit
     assert [plain.eigenvalues[i] for i in range(res.nroots)] == [unchained.eigenvalues[i] for i in range(res.nroots)]
+    assert np.abs(ev / np.array([plain.eigenvalues[i] for i in range(res.nroots)]) - 1).max() <= 1e-12
     for s, chk in zip(sol, want["solution_checksums"]):
         assert abs(np.sum(s) - chk) <= 1e-7 * max(1.0, np.abs(s).sum())
