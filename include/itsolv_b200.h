@@ -186,6 +186,10 @@ int itsolv_davidson_residual_f64(itsolv_ctx* ctx, const double* coef, int k, int
  *   mode 0   r_j = sum_i c_ij a_i - lambda_j x_j                       (LinearEigensystemDavidson.h:186-192; as above)
  *   mode 1   r_j = (sum_i c_ij a_i - rhs_j) * rscale_j                 (LinearEquationsDavidson.h:173-184: axpy(-1, rhs) then
  *                                                                        scal(1/|rhs|), each operation rounded)
+ *   mode 2   r_j = sum_i c_ij a_i                                     (NonLinearEquationsDIIS: solution() of the
+ *                                                                        extrapolated parameters and residual)
+ *   mode 3   as 2, and what is stored in out_x[j] is x_j - out_r[j]      (its end_iteration, NonLinearEquationsDIIS.h:103-119:
+ *                                                                        axpy(-1, preconditioned residual, parameters))
  * accumulate != 0: the expansions start from the present contents of out_x[j] / out_r[j] instead of zero - the P-space
  * parts (IterativeSolverTemplate.h:44-64 puts them first; the caller's apply_p contribution, :210-211) - out_x is then
  * required. With a diagonal the residuals are preconditioned as above (shift = 0 for linear equations).

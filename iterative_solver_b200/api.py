@@ -267,12 +267,15 @@ class Context:
         return n2, n2w
 
     def subspace_residual(self, coef: np.ndarray, q: Sequence, a: Sequence, out_r: Sequence, lam=None, rhs=None,
-                          rscale=None, diag=None, shift=None, out_x: Sequence | None = None, accumulate: bool = False):
+                          rscale=None, diag=None, shift=None, out_x: Sequence | None = None, accumulate: bool = False,
+                          mode: int | None = None):
         """itsolv_subspace_residual_f64. Eigenproblem form with `lam` (r = sum c a - lam x), linear-equations form with
-        `rhs` and `rscale` (r = (sum c a - rhs) * rscale); `accumulate`: continue from the contents of out_x / out_r.
+        `rhs` and `rscale` (r = (sum c a - rhs) * rscale); `accumulate`: continue from the contents of out_x / out_r;
+        `mode` 2: r = sum c a as it is, 3: the same and out_x = x - out_r (the DIIS step).
         Returns (<r_j, r_j> before preconditioning, <out_r_j, out_r_j>)."""
         k, m = len(q), len(out_r)
-        mode = 0 if rhs is None else 1
+        if mode is None:
+            mode = 0 if rhs is None else 1
         c = np.ascontiguousarray(coef, dtype=np.float64).reshape(k, m)
         l = np.ascontiguousarray(lam, dtype=np.float64) if lam is not None else None
         s = np.ascontiguousarray(rscale, dtype=np.float64) if rscale is not None else None

@@ -49,7 +49,8 @@ struct DsParams {
   size_t n;
   int k, m, ld;
   int write_x;
-  int mode;       // 0: eigenproblem residual, 1: linear equations residual
+  int mode;       // 0: eigenproblem residual, 1: linear equations residual, 2: r_j = sum_i c_ij a_i as it is (DIIS)
+  int update_x;   // the stored x_j is x_j - out_r_j (the DIIS step with the preconditioned residual, mode 3 of the entry)
   int accumulate; // the expansions start from the present contents of out_x / out_r (P-space parts) instead of zero
 };
 
@@ -74,6 +75,9 @@ struct DsOps<double2> {
     acc = fma(r.x, r.x, acc);
     acc = fma(r.y, r.y, acc);
   }
+  static __device__ __forceinline__ double2 sub(const double2& x, const double2& r) {
+    return make_double2(__dsub_rn(x.x, r.x), __dsub_rn(x.y, r.y));
+  }
   static __device__ __forceinline__ double2 precondition(const double2& r, const double2& d, double shift) {
     return make_double2(div_rn(r.x, __dadd_rn(__dsub_rn(d.x, shift), 1e-15)),
                         div_rn(r.y, __dadd_rn(__dsub_rn(d.y, shift), 1e-15)));
@@ -90,6 +94,7 @@ struct DsOps<double> {
     return __dmul_rn(__dadd_rn(r, -b), s);
   }
   static __device__ __forceinline__ void square_to(double& acc, const double& r) { acc = fma(r, r, acc); }
+  static __device__ __forceinline__ double sub(const double& x, const double& r) { return __dsub_rn(x, r); }
   static __device__ __forceinline__ double precondition(const double& r, const double& d, double shift) {
     return div_rn(r, __dadd_rn(__dsub_rn(d, shift), 1e-15));
   }
@@ -137,7 +142,16 @@ template <class RV>
 __device__ __forceinline__ RV ds_residual(const DsParams& p, int j, size_t r, const RV& ar, const RV& ax) {
   if (p.mode == 1)
     return DsOps<RV>::residual_lineq(ar, reinterpret_cast<const RV*>(p.rhs[j])[r], p.rscale[j]);
+  if (p.mode == 2)
+    return ar;
   return DsOps<RV>::residual(ar, -p.lambda[j], ax);
+}
+
+//! what is stored as x_j: the expansion, or (update_x) the expansion minus the residual that was just written - the
+//! rounding of axpy(-1, out_r, x)
+template <class RV>
+__device__ __forceinline__ RV ds_solution(const DsParams& p, const RV& ax, const RV& out) {
+  return p.update_x ? DsOps<RV>::sub(ax, out) : ax;
 }
 
 //! one thread, rows `r` (in units of RV): both expansions, residual, square, preconditioner
@@ -192,8 +206,6 @@ __device__ __forceinline__ void ds_rows(const DsParams& p, const double* __restr
 #pragma unroll
   for (int b = 0; b < MJ; ++b) {
     if (b < p.m) {
-      if (p.write_x)
-        reinterpret_cast<RV*>(p.out_x[b])[r] = ax[b];
       RV res = ds_residual<RV>(p, b, r, ar[b], ax[b]);
       nrm.add(b, res);
       if (p.diag) {
@@ -201,6 +213,8 @@ __device__ __forceinline__ void ds_rows(const DsParams& p, const double* __restr
         nrm.add(MJ + b, res);
       }
       reinterpret_cast<RV*>(p.out_r[b])[r] = res;
+      if (p.write_x)
+        reinterpret_cast<RV*>(p.out_x[b])[r] = ds_solution<RV>(p, ax[b], res);
     }
   }
 }
@@ -368,8 +382,6 @@ __global__ void __launch_bounds__(kDsThreads, 2) davidson_residual_ring_kernel(c
 #pragma unroll
       for (int b = 0; b < MJ; ++b) {
         if (b < p.m) {
-          if (p.write_x)
-            reinterpret_cast<double2*>(p.out_x[b])[cr] = ax[b];
           double2 res = ds_residual<double2>(p, b, cr, ar[b], ax[b]);
           nrm.add(b, res);
           if (p.diag) {
@@ -377,6 +389,8 @@ __global__ void __launch_bounds__(kDsThreads, 2) davidson_residual_ring_kernel(c
             nrm.add(MJ + b, res);
           }
           reinterpret_cast<double2*>(p.out_r[b])[cr] = res;
+          if (p.write_x)
+            reinterpret_cast<double2*>(p.out_x[b])[cr] = ds_solution<double2>(p, ax[b], res);
         }
       }
       cr += nthreads;
@@ -536,8 +550,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) davidson_residual_tile_kernel
       for (int b = 0; b < kTileGroupRoots; ++b) {
         const int j = g * kTileGroupRoots + b;
         if (j < p.m) {
-          if (p.write_x)
-            reinterpret_cast<double2*>(p.out_x[j])[prow] = ax[b];
           double2 res = ds_residual<double2>(p, j, prow, ar[b], ax[b]);
           double t = mysq[b * kTileConsumers];
           Ops::square_to(t, res);
@@ -549,6 +561,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) davidson_residual_tile_kernel
             mysq[(kTileGroupRoots + b) * kTileConsumers] = t;
           }
           reinterpret_cast<double2*>(p.out_r[j])[prow] = res;
+          if (p.write_x)
+            reinterpret_cast<double2*>(p.out_x[j])[prow] = ds_solution<double2>(p, ax[b], res);
         }
       }
     }
@@ -580,8 +594,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) davidson_residual_tile_kernel
         for (int b = 0; b < kTileGroupRoots; ++b) {
           const int j = g * kTileGroupRoots + b;
           if (j < p.m) {
-            if (p.write_x)
-              p.out_x[j][r] = x1[b];
             double res = ds_residual<double>(p, j, r, r1[b], x1[b]);
             double t = mysq[b * kTileConsumers];
             DsOps<double>::square_to(t, res);
@@ -593,6 +605,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) davidson_residual_tile_kernel
               mysq[(kTileGroupRoots + b) * kTileConsumers] = t;
             }
             p.out_r[j][r] = res;
+            if (p.write_x)
+              p.out_x[j][r] = ds_solution<double>(p, x1[b], res);
           }
         }
       }
@@ -680,10 +694,15 @@ int itsolv_subspace_residual_f64(itsolv_ctx* ctx, int mode, int accumulate, cons
                                  double* norm2_out) {
   ITSOLV_REQUIRE(k >= 1 && k <= ITSOLV_MAX_PANEL, "davidson_residual: 1 <= k <= ITSOLV_MAX_PANEL subspace vectors");
   ITSOLV_REQUIRE(m >= 1, "davidson_residual: m >= 1 roots");
-  ITSOLV_REQUIRE(mode == 0 || mode == 1, "subspace_residual: mode 0 (eigenproblem) or 1 (linear equations)");
-  ITSOLV_REQUIRE(out_r != nullptr && q != nullptr && a != nullptr && coef != nullptr && (mode == 1 || lambda != nullptr),
+  ITSOLV_REQUIRE(mode >= 0 && mode <= 3,
+                 "subspace_residual: mode 0 (eigenproblem), 1 (linear equations), 2 (plain expansion), 3 (2 + DIIS step)");
+  const int update_x = mode == 3 ? 1 : 0;
+  if (mode == 3)
+    mode = 2;
+  ITSOLV_REQUIRE(out_r != nullptr && q != nullptr && a != nullptr && coef != nullptr && (mode != 0 || lambda != nullptr),
                  "davidson_residual: null argument");
-  ITSOLV_REQUIRE(mode == 0 || (rhs != nullptr && rscale != nullptr), "subspace_residual: right-hand sides and scales");
+  ITSOLV_REQUIRE(mode != 1 || (rhs != nullptr && rscale != nullptr), "subspace_residual: right-hand sides and scales");
+  ITSOLV_REQUIRE(!update_x || out_x != nullptr, "subspace_residual: the DIIS step needs the solution vectors");
   ITSOLV_REQUIRE(!accumulate || out_x != nullptr, "subspace_residual: accumulation needs the solution vectors");
   ITSOLV_REQUIRE(diag == nullptr || shift != nullptr, "davidson_residual: shifts are needed with a diagonal");
   if (mode == 1)
@@ -740,6 +759,7 @@ int itsolv_subspace_residual_f64(itsolv_ctx* ctx, int mode, int accumulate, cons
       p.diag = diag;
       p.write_x = out_x ? 1 : 0;
       p.mode = mode;
+      p.update_x = update_x;
       p.accumulate = accumulate ? 1 : 0;
       char *h = nullptr, *d = nullptr;
       int slot = 0;

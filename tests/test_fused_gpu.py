@@ -139,6 +139,30 @@ def test_subspace_residual_linear_equations_form(ctx, oracle, n, k, m, precondit
     assert np.abs(n2w - want_n2w).max() <= 1e-12 * want_n2w.max()
 
 
+@pytest.mark.parametrize("n,k,m", [(1, 1, 1), (33, 5, 1), (4097, 3, 1), (50001, 8, 1), (20000, 6, 2), (70001, 24, 16)])
+@pytest.mark.parametrize("step", [False, True])
+def test_subspace_residual_diis_form(ctx, oracle, n, k, m, step):
+    """modes 2 and 3 of itsolv_subspace_residual_f64 against the reference's DIIS sequence (IterativeSolverTemplate.h:
+    191-215, NonLinearEquationsDIIS.h:103-119): two expansions from zero, <r, r>, precondition_default with a zero shift,
+    and with the step axpy(-1, preconditioned residual, parameters). Vectors bit for bit."""
+    rng = np.random.default_rng(13 * n + 7 * k + m)
+    Q, A = rng.standard_normal((k, n)), rng.standard_normal((k, n))
+    coef = rng.standard_normal((k, m))
+    diag = np.arange(1, n + 1, dtype=np.float64)
+    want_x = oracle.c.gemm_outer(coef, Q, np.zeros((m, n)), fma=True)
+    want_r = oracle.c.gemm_outer(coef, A, np.zeros((m, n)), fma=True)
+    want_n2 = np.array([oracle.c.dot(want_r[j], want_r[j]) for j in range(m)])
+    if step:
+        want_r = oracle.c.precondition(want_r, np.zeros(m), diag)
+        want_x = np.stack([oracle.c.axpy(-1.0, want_r[j], want_x[j]) for j in range(m)])
+    out_r = [torch.full((n,), np.nan, dtype=torch.float64, device="cuda") for _ in range(m)]
+    out_x = [torch.full((n,), np.nan, dtype=torch.float64, device="cuda") for _ in range(m)]
+    n2, _ = ctx.subspace_residual(coef, dev_rows(Q), dev_rows(A), out_r, out_x=out_x, mode=3 if step else 2,
+                                  diag=dev_rows(diag[None])[0] if step else None, shift=np.zeros(m))
+    assert np.array_equal(host(out_r), want_r) and np.array_equal(host(out_x), want_x)
+    assert np.abs(n2 - want_n2).max() <= 1e-12 * want_n2.max()
+
+
 @pytest.mark.parametrize("n,k,m", [(33, 5, 3), (4097, 9, 4), (50001, 12, 8), (20001, 7, 16)])
 def test_subspace_residual_continues_from_the_p_space_parts(ctx, oracle, n, k, m):
     """accumulate: x_j and r_j start from what the output vectors hold (the P-space parts, which the reference adds first
