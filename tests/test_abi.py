@@ -88,3 +88,28 @@ def test_no_cpu_fallback_without_a_device():
     from iterative_solver_b200 import BackendError, Context
     with pytest.raises(BackendError):
         Context(0)
+
+
+def test_the_reference_checkout_is_pinned_by_content(tmp_path, monkeypatch):
+    """The host library instantiates the reference's templates: build.py refuses a checkout that differs from
+    reference_manifest.json and says what to do (an explicit, versioned build dependency)."""
+    import json
+    import shutil
+
+    from iterative_solver_b200 import build as B
+    pinned = json.load(open(B.MANIFEST))["files"]
+    assert len(pinned) > 50 and all(len(v) == 64 for v in pinned.values())
+    if not os.path.isdir(os.path.join(B.REFERENCE, "src", "molpro")):
+        pytest.skip("no reference checkout on this box (the prebuilt library travels with the tree)")
+    assert B.reference_files() == pinned
+    B.check_reference()
+    # a checkout with one header changed
+    other = tmp_path / "reference"
+    shutil.copytree(os.path.join(B.REFERENCE, "src", "molpro", "linalg"), other / "src" / "molpro" / "linalg")
+    victim = other / "src" / "molpro" / "linalg" / "itsolv" / "IterativeSolver.h"
+    victim.write_text(victim.read_text() + "\n// changed\n")
+    monkeypatch.setattr(B, "REFERENCE", str(other))
+    with pytest.raises(RuntimeError, match="not the revision this package is pinned to"):
+        B.check_reference()
+    monkeypatch.setenv("ITSOLV_REFERENCE_UNPINNED", "1")
+    B.check_reference()

@@ -103,3 +103,29 @@ def test_two_rank_plumbing_over_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {r} ok" in o
+
+
+def test_the_configurations_a_bench_run_covers_fit_their_gpus():
+    """bench.config_plan: which of BASELINE.json's configurations run at N GPUs, against the measured high-water marks
+    (profiles/memory_table_r02.jsonl, vectors of 8 n / N bytes, 180 GB per GPU with 6 GB kept free as run_configs does)"""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import config_runs as CR
+    peaks = {}
+    for line in open(os.path.join(ROOT, "profiles", "memory_table_r02.jsonl")):
+        r = json.loads(line)
+        peaks[(r["nroots"], r["nbuffers"], r["max_size_qspace"])] = r["peak_vectors"]
+    for world in (1, 2, 4, 8):
+        plan = dict(bench.config_plan(world))
+        assert ("c4" in plan) == (world > 1) and ("c3" in plan) == (world <= 2)
+        if "c4" in plan:
+            base = CR.CONFIGS["c4"]
+            shape = {**base, **plan["c4"]}
+            key = (shape["nroots"], shape.get("nbuffers", shape["nroots"]), shape["max_size_qspace"])
+            need = peaks[key] * 8.0 * base["n"] / world
+            assert need + 6e9 <= 180e9, (world, key, need)
+            assert world < 8 or plan["c4"] == {}  # the stated shape on 8 GPUs
