@@ -499,4 +499,109 @@ double ref_time_handler_op(int op, size_t n, int k, int m, int reps) {
   return (now_seconds() - t0) / reps;
 }
 
+/*
+ * The protocol of the reference's own end-to-end eigensolver test on a dense matrix (reference
+ * test/itsolv/test_LinearEigensystem.cpp: test_eigen :245-344, initialize_subspace :224-243, set_options :190-212, update
+ * :96-104, initial_guess :146-157, initial_pspace / apply_p :159-188), with the reference's LinearEigensystemDavidson on
+ * std::vector containers: unit-vector guess on the lowest diagonal elements (or a P space of `np` such unit vectors), then
+ * action / add_vector / update / end_iteration until the working set is empty. hmat: n x n row-major.
+ * Out: eigenvalues[nroot], errors[nroot], solutions[nroot][n], stats = {iterations, r_creations, loop count n_iter}.
+ */
+int ref_dense_eigen(size_t n, const double* hmat, int nroot, int np, int hermitian, int n_working_vectors_max,
+                    double* eigenvalues, double* errors, double* solutions, int64_t* stats) {
+  return ref_guarded([&] {
+    auto H = [&](size_t i, size_t j) { return hmat[i * n + j]; };
+    auto dense = std::make_shared<la::ArrayHandlerIterable<Vec, Vec>>();
+    auto sparse = std::make_shared<la::ArrayHandlerIterableSparse<Vec, PMap>>();
+    auto handlers = std::make_shared<its::ArrayHandlers<Vec, Vec, PMap>>(
+        dense, dense, std::make_shared<la::ArrayHandlerSparse<PMap, PMap>>(), dense, sparse, dense, sparse);
+    its::LinearEigensystemDavidson<Vec, Vec, PMap> solver(handlers);
+    solver.set_n_roots(size_t(nroot));
+    solver.set_convergence_threshold(1.0e-8);
+    solver.set_max_size_qspace(std::max(6 * nroot, std::min(int(n), std::min(1000, 6 * nroot)) - np));
+    solver.set_reset_D(8);
+    solver.set_hermiticity(hermitian != 0);
+    solver.set_verbosity(its::Verbosity::None);
+    auto action = [&](const std::vector<Vec>& x, std::vector<Vec>& g) {
+      for (size_t k = 0; k < x.size(); ++k)
+        for (size_t i = 0; i < n; ++i) {
+          double a = 0;
+          for (size_t j = 0; j < n; ++j)
+            a += H(i, j) * x[k][j];
+          g[k][i] = a;
+        }
+    };
+    auto update = [&](std::vector<Vec>& g, const std::vector<double>& shift) {
+      for (size_t k = 0; k < g.size() && k < shift.size(); ++k)
+        for (size_t i = 0; i < n; ++i)
+          g[k][i] *= -1. / (1e-12 - shift[k] + H(i, i));
+    };
+    const size_t nroots = size_t(nroot);
+    std::vector<Vec> x(nroots, Vec(n, 0.0)), g(nroots, Vec(n, 0.0));
+    std::vector<double> diagonals(n);
+    for (size_t i = 0; i < n; ++i)
+      diagonals[i] = H(i, i);
+    auto take_lowest = [&]() {
+      const size_t at = size_t(std::min_element(diagonals.begin(), diagonals.end()) - diagonals.begin());
+      diagonals[at] = 1e99;
+      return at;
+    };
+    if (np > 0) {
+      std::vector<PMap> pspace;
+      for (int p = 0; p < np; ++p)
+        pspace.push_back(PMap{{take_lowest(), 1.0}});
+      std::vector<double> PP;
+      for (const auto& i : pspace)
+        for (const auto& j : pspace)
+          PP.push_back(H(i.begin()->first, j.begin()->first));
+      auto apply_p = [&](const std::vector<std::vector<double>>& pvectors, const its::CVecRef<PMap>& ps,
+                         const its::VecRef<Vec>& act) {
+        for (size_t i = 0; i < pvectors.size(); ++i)
+          for (size_t pi = 0; pi < ps.size(); ++pi)
+            for (const auto& pel : ps[pi].get())
+              for (size_t j = 0; j < n; ++j)
+                act[i].get()[j] += H(j, pel.first) * pel.second * pvectors[i][pi];
+      };
+      solver.add_p(its::cwrap(pspace), la::Span<double>(PP.data(), PP.size()), its::wrap(x), its::wrap(g), apply_p);
+    } else {
+      for (int root = 0; root < nroot; ++root)
+        x[size_t(root)][take_lowest()] = 1;
+      action(x, g);
+      solver.add_vector(x, g);
+    }
+    const size_t nguess = size_t(std::max(nroot, n_working_vectors_max > 0 ? n_working_vectors_max : nroot));
+    x.resize(nguess, Vec(n, 0.0));
+    g.resize(nguess, Vec(n, 0.0));
+    update(g, solver.working_set_eigenvalues());
+    solver.end_iteration(x, g);
+    int64_t n_iter = 2;
+    for (int iter = 1; iter < 100; ++iter, ++n_iter) {
+      action(x, g);
+      if (solver.add_vector(x, g) == 0)
+        break;
+      update(g, solver.working_set_eigenvalues());
+      if (solver.end_iteration(x, g) == 0)
+        break;
+    }
+    const auto ev = solver.eigenvalues();
+    const auto err = solver.errors();
+    for (int i = 0; i < nroot; ++i) {
+      eigenvalues[i] = ev.at(size_t(i));
+      errors[i] = err.at(size_t(i));
+    }
+    std::vector<int> roots;
+    for (int i = 0; i < nroot; ++i)
+      roots.push_back(i);
+    const size_t nr = size_t(nroot);
+    std::vector<Vec> par(nr, Vec(n, 0.0)), res(nr, Vec(n, 0.0));
+    solver.solution(roots, par, res);
+    for (int i = 0; i < nroot; ++i)
+      std::copy(par[size_t(i)].begin(), par[size_t(i)].end(), solutions + size_t(i) * n);
+    stats[0] = int64_t(solver.statistics().iterations);
+    stats[1] = int64_t(solver.statistics().r_creations);
+    stats[2] = n_iter;
+  });
+}
+
 } // extern "C"
+

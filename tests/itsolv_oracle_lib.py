@@ -167,6 +167,7 @@ class RefOracle:
         lib.ref_distribution.argtypes = [C.c_size_t, C.c_int, i64p]
         lib.ref_time_handler_op.restype = C.c_double
         lib.ref_time_handler_op.argtypes = [C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int]
+        lib.ref_dense_eigen.argtypes = [C.c_size_t, dp, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, i64p]
 
     def solve(self, spec, want_solutions=False):
         res = self.N.SolveResult()
@@ -176,6 +177,20 @@ class RefOracle:
         if rc:
             raise RuntimeError(self.lib.ref_last_error().decode())
         return res, sol
+
+    def dense_eigen(self, hmat, nroot, np_=0, hermitian=True, n_working_vectors_max=0):
+        """the reference's end-to-end eigensolver test protocol (test/itsolv/test_LinearEigensystem.cpp:245-344) on a dense
+        matrix; returns eigenvalues, errors, solutions [nroot x n], (iterations, r_creations, n_iter)"""
+        h = np.ascontiguousarray(hmat, dtype=np.float64)
+        n = h.shape[0]
+        ev, err, sol = np.zeros(nroot), np.zeros(nroot), np.zeros((nroot, n))
+        stats = np.zeros(3, dtype=np.int64)
+        i64p = C.POINTER(C.c_int64)
+        rc = self.lib.ref_dense_eigen(n, _d(h), nroot, np_, int(hermitian), n_working_vectors_max, _d(ev), _d(err), _d(sol),
+                                      stats.ctypes.data_as(i64p))
+        if rc:
+            raise RuntimeError("ref_dense_eigen failed")
+        return ev, err, sol, tuple(int(v) for v in stats)
 
     def read_trace(self):
         ne, nv = self.lib.ref_trace_entries(), self.lib.ref_trace_values()
@@ -285,5 +300,10 @@ def load():
         build()
     c = COracle(C.CDLL(c_path))
     ref = RefOracle(C.CDLL(ref_path)) if os.path.exists(ref_path) else None
-    _cache = SimpleNamespace(c=c, ref=ref)
+    # the same reference templates with the PRODUCT's host algebra (oracle/Makefile): a CPU test vehicle
+    ph_path = os.path.join(REF_DIR, "libitsolv_ref_producthelper.so")
+    if not os.path.exists(ph_path) and os.path.isdir("/root/reference"):
+        build()
+    ref_product_helper = RefOracle(C.CDLL(ph_path)) if os.path.exists(ph_path) else None
+    _cache = SimpleNamespace(c=c, ref=ref, ref_product_helper=ref_product_helper)
     return _cache

@@ -146,3 +146,92 @@ def test_config0_example_problem_against_numpy(oracle):
         assert np.abs(got - ev[:got.size]).max() <= 1e-12
     assert golden["example_davidson_n20_r1"]["iterations"] == 5  # BASELINE.md probe: 5 iterations, 0.999813133574363
     assert abs(golden["example_davidson_n20_r1"]["eigenvalues"][0] - 0.999813133574363) < 1e-14
+
+
+def _reference_eigen_cases():
+    """the matrices of the reference's own end-to-end eigensolver tests (test/itsolv/test_LinearEigensystem.cpp): the
+    Hamiltonian files (file_eigen :346-351; phenol is not in the checkout), all-ones matrices with diagonal i*param
+    (load_matrix :41-50; n_eigen :353-362, small_eigen :378-386), their non-hermitian variants (nonhermitian_eigen
+    :364-376) and the symmetry-blocked ones (symmetry_eigen :388-409)"""
+    ham = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hamiltonians.npz"))
+    cases = [(name, ham[name]) for name in ("he", "hf", "bh")]
+
+    def ones(n, param=1.0, non_hermiticity=0.0):
+        h = np.ones((n, n))
+        h[np.diag_indices(n)] = np.arange(n) * param
+        if non_hermiticity:
+            h[np.tril_indices(n, -1)] *= 1 - non_hermiticity
+        return h
+
+    cases.append(("ones100", ones(100)))
+    for n in range(1, 5):
+        cases.append((f"ones{n}", ones(n)))
+    for param in (1.0, 0.1):
+        for nh in (0.1, 0.2):
+            cases.append((f"ones6_p{param}_nh{nh}", ones(6, param, nh)))
+    for n in range(2, 6):
+        h = ones(n)
+        for i in range(n):
+            for j in range(n):
+                if (i % 3 == 0) != (j % 3 == 0):
+                    h[j, i] = 0
+        cases.append((f"sym{n}", h))
+    return cases
+
+
+@pytest.mark.parametrize("helper", ["literal", "product"])
+@pytest.mark.parametrize("name,hmat", _reference_eigen_cases(), ids=[c[0] for c in _reference_eigen_cases()])
+def test_reference_build_passes_the_references_own_eigensolver_test(oracle, name, hmat, helper):
+    """oracle/_ref (the reference's templates + the literal restatement of its Eigen translation unit) driven through the
+    protocol and the assertions of the reference's test_eigen (test/itsolv/test_LinearEigensystem.cpp:245-344): errors,
+    eigenvalues against a dense diagonalisation, number of R vectors, true residuals, overlap with the dense eigenvectors.
+    `product`: the same templates linked with the PRODUCT's host algebra (iterative_solver_b200/host/helper_lapack.cpp) -
+    the subspace solver that runs under the CUDA path, under the reference's own test, on the CPU"""
+    ref = oracle.ref if helper == "literal" else oracle.ref_product_helper
+    if ref is None:
+        pytest.skip("oracle/_ref is not built")
+    n = hmat.shape[0]
+    hermitian = np.abs(hmat - hmat.T).max() < 1e-10
+    if hermitian:
+        want_ev, want_vec = np.linalg.eigh(hmat)
+    else:
+        w, v = np.linalg.eig(hmat)
+        assert np.abs(w.imag).max() < 1e-12
+        order = np.argsort(w.real)
+        want_ev, want_vec = w.real[order], v.real[:, order]
+    for nroot in range(1, min(n, 28) + 1, max(1, n // 10)):
+        for np_ in range(0, min(n, 100) + 1, max(nroot, n // 5)):
+            if np_ > 0 and not hermitian:
+                break
+            if 0 < np_ < nroot:
+                continue  # "P space must be empty or at least as large as number of roots sought"
+            ev, err, sol, (iterations, r_creations, n_iter) = ref.dense_eigen(hmat, nroot, np_, hermitian)
+            where = f"{name}: {nroot} roots, P space {np_}"
+            assert (np.abs(err) <= 2e-8).all(), where
+            assert np.abs(ev - want_ev[:nroot]).max() <= 2e-9, where
+            assert r_creations <= (nroot + 1) * n_iter, where
+            for k in range(nroot):
+                assert np.linalg.norm(hmat @ sol[k] - ev[k] * sol[k]) <= 1e-8, where
+                if hermitian and (k == 0 or want_ev[k] - want_ev[k - 1] > 1e-6) and \
+                        (k + 1 == n or want_ev[k + 1] - want_ev[k] > 1e-6):
+                    assert abs(abs(sol[k] @ want_vec[:, k]) - 1) <= 1e-8, where
+
+
+def test_golden_solves_with_the_products_host_algebra(oracle):
+    """the golden solves (made with the oracle's literal host algebra) run again on the CPU with the PRODUCT's host
+    algebra under the same reference templates: same iteration counts, convergence, creation counters and eigenvalues -
+    whatever the fast restatement changes (dgemm products, index sort, symmetric solver, dsyevd) stays below what the
+    solver's decisions can see"""
+    if oracle.ref_product_helper is None:
+        pytest.skip("oracle/_ref is not built")
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "solve_golden.json")))
+    for name, want in golden.items():
+        if want["spec"]["n"] > 100000:
+            continue  # seconds each on the CPU; the smaller cases cover every solver and option
+        res, _ = oracle.ref_product_helper.solve(H.make_spec(**want["spec"]))
+        assert res.iterations == want["iterations"] and res.converged == want["converged"], name
+        assert [res.r_creations, res.q_creations, res.p_creations, res.d_creations] == want["creations"], name
+        if want.get("eigenvalues"):
+            ev = np.array([res.eigenvalues[i] for i in range(len(want["eigenvalues"]))])
+            assert np.abs(ev / np.array(want["eigenvalues"]) - 1).max() <= 1e-10, name
+
