@@ -28,6 +28,7 @@
 #include <molpro/linalg/array/ArrayHandlerSparse.h>
 #include <molpro/linalg/array/util/Distribution.h>
 #include <molpro/linalg/itsolv/subspace/gram_schmidt.h>
+#include <molpro/linalg/itsolv/subspace/util.h>
 
 namespace {
 using Vec = std::vector<double>;
@@ -601,6 +602,152 @@ int ref_dense_eigen(size_t n, const double* hmat, int nroot, int np, int hermiti
     stats[1] = int64_t(solver.statistics().r_creations);
     stats[2] = n_iter;
   });
+}
+
+/*
+ * The reference's LinearEquations test (test/itsolv/test_LinearEquations.cpp:17-98, symmetric_system): a dense problem
+ * with diagonals(), the library's own precondition_default for iterable containers (IterativeSolver.h:34-55), right-hand
+ * sides added one by one, solve() with the default initial guess and threshold 1e-10, then solution() for all roots.
+ * matrix: n x n row-major; rhs: nroot x n; out: solutions nroot x n, stats = {iterations, converged}.
+ */
+int ref_dense_lineq(size_t n, const double* matrix, int nroot, const double* rhs, double threshold, double* solutions,
+                    int64_t* stats) {
+  return ref_guarded([&] {
+    struct DenseProblem : its::Problem<Vec> {
+      size_t n;
+      const double* m;
+      void action(const its::CVecRef<Vec>& parameters, const its::VecRef<Vec>& act) const override {
+        for (size_t v = 0; v < parameters.size(); ++v)
+          for (size_t i = 0; i < n; ++i) {
+            double a = 0;
+            for (size_t j = 0; j < n; ++j)
+              a += m[i * n + j] * parameters[v].get()[j];
+            act[v].get()[i] = a;
+          }
+      }
+      bool diagonals(Vec& d) const override {
+        for (size_t i = 0; i < n; ++i)
+          d[i] = m[i * n + i];
+        return true;
+      }
+    } problem;
+    problem.n = n;
+    problem.m = matrix;
+    auto dense = std::make_shared<la::ArrayHandlerIterable<Vec, Vec>>();
+    auto sparse = std::make_shared<la::ArrayHandlerIterableSparse<Vec, PMap>>();
+    auto handlers = std::make_shared<its::ArrayHandlers<Vec, Vec, PMap>>(
+        dense, dense, std::make_shared<la::ArrayHandlerSparse<PMap, PMap>>(), dense, sparse, dense, sparse);
+    its::LinearEquationsDavidson<Vec, Vec, PMap> solver(handlers);
+    for (int root = 0; root < nroot; ++root)
+      solver.add_equations(Vec(rhs + size_t(root) * n, rhs + size_t(root + 1) * n));
+    const size_t nr = size_t(nroot);
+    std::vector<Vec> parameters(nr, Vec(n, 0.0)), actions(nr, Vec(n, 0.0));
+    solver.set_convergence_threshold(threshold);
+    solver.set_verbosity(its::Verbosity::None);
+    const bool ok = solver.solve(parameters, actions, problem, true);
+    std::vector<int> roots;
+    for (int i = 0; i < nroot; ++i)
+      roots.push_back(i);
+    solver.solution(roots, parameters, actions);
+    for (size_t r = 0; r < nr; ++r)
+      std::copy(parameters[r].begin(), parameters[r].end(), solutions + r * n);
+    stats[0] = int64_t(solver.statistics().iterations);
+    stats[1] = ok ? 1 : 0;
+  });
+}
+
+/*
+ * The reference's NonLinearEquations test (test/itsolv/test_NonLinearEquations.cpp:18-121, small_quadratic_form): DIIS
+ * with convergence_threshold 1e-8 and max_size_qspace 6 on f = (x-1).h.(x-1)/2, h all ones with diagonal (i+2)*param;
+ * start x = e_0; per iteration action, add_vector, update (division by the diagonal) when the working set is not
+ * empty, end_iteration. Out: solution[n], residual[n], stats = {iterations, r_creations, n_iter}, error.
+ */
+int ref_dense_diis(size_t n, double param, double* solution, double* residual, int64_t* stats, double* error) {
+  return ref_guarded([&] {
+    auto H = [&](size_t i, size_t j) { return i == j ? double(i + 2) * param : 1.0; };
+    auto dense = std::make_shared<la::ArrayHandlerIterable<Vec, Vec>>();
+    auto sparse = std::make_shared<la::ArrayHandlerIterableSparse<Vec, PMap>>();
+    auto handlers = std::make_shared<its::ArrayHandlers<Vec, Vec, PMap>>(
+        dense, dense, std::make_shared<la::ArrayHandlerSparse<PMap, PMap>>(), dense, sparse, dense, sparse);
+    its::NonLinearEquationsDIIS<Vec, Vec, PMap> solver(handlers);
+    solver.set_convergence_threshold(1e-8);
+    solver.set_max_size_qspace(6);
+    solver.set_verbosity(its::Verbosity::None);
+    Vec x(n, 0.0), g(n, 0.0);
+    x.front() = 1;
+    int nwork = 1;
+    int64_t n_iter = 1;
+    for (int iter = 1; iter < 1000 && nwork > 0; ++iter, ++n_iter) {
+      for (size_t i = 0; i < n; ++i) {
+        double a = 0;
+        for (size_t j = 0; j < n; ++j)
+          a += H(i, j) * (x[j] - 1.0);
+        g[i] = a;
+      }
+      if (solver.add_vector(x, g, 0.0))
+        for (size_t i = 0; i < n; ++i)
+          g[i] = g[i] / H(i, i);
+      nwork = int(solver.end_iteration(x, g));
+    }
+    Vec par(n, 0.0), res(n, 0.0);
+    solver.solution(par, res);
+    std::copy(par.begin(), par.end(), solution);
+    std::copy(res.begin(), res.end(), residual);
+    stats[0] = int64_t(solver.statistics().iterations);
+    stats[1] = int64_t(solver.statistics().r_creations);
+    stats[2] = n_iter;
+    *error = solver.errors().front();
+  });
+}
+
+/*
+ * Small functions of the reference that the drivers (the reference's own and the fused ones) call unmodified, exposed
+ * for the known-answer tests the reference holds for them (test/itsolv/subspace/test_util.cpp): Gram-Schmidt on an
+ * overlap matrix (:109-152), eye_order (:76-107), overlap (:26-74), parameter_batches (:175-188).
+ */
+int ref_gram_schmidt(size_t n, const double* s, double* t, double* norms) {
+  return ref_guarded([&] {
+    its::subspace::Matrix<double> S(std::vector<double>(s, s + n * n), {n, n});
+    its::subspace::Matrix<double> T;
+    const auto result = its::subspace::util::gram_schmidt(S, T);
+    if (result.size() != n || T.rows() != n || T.cols() != n)
+      throw std::runtime_error("gram_schmidt: unexpected shape");
+    std::copy(T.data().begin(), T.data().end(), t);
+    std::copy(result.begin(), result.end(), norms);
+  });
+}
+
+int ref_eye_order(size_t n, const double* m, int64_t* order) {
+  return ref_guarded([&] {
+    its::subspace::Matrix<double> M(std::vector<double>(m, m + n * n), {n, n});
+    const auto o = its::subspace::util::eye_order(M);
+    for (size_t i = 0; i < o.size(); ++i)
+      order[i] = int64_t(o[i]);
+  });
+}
+
+//! overlap of k vectors of length n with themselves: the one-set form (k(k+1)/2 dots) and the two-set form (gemm_inner)
+int ref_overlap(int k, size_t n, const double* x, double* one_set, double* two_sets) {
+  return ref_guarded([&] {
+    std::vector<Vec> xs;
+    for (int i = 0; i < k; ++i)
+      xs.push_back(to_vec(x + size_t(i) * n, n));
+    la::ArrayHandlerIterable<Vec, Vec> h;
+    const auto a = its::subspace::util::overlap(its::cwrap(xs), h);
+    const auto b = its::subspace::util::overlap(its::cwrap(xs), its::cwrap(xs), h);
+    std::copy(a.data().begin(), a.data().end(), one_set);
+    std::copy(b.data().begin(), b.data().end(), two_sets);
+  });
+}
+
+//! pairs (begin, end) of detail::parameter_batches(nsol, nparam); returns the number of batches
+int ref_parameter_batches(size_t nsol, size_t nparam, int64_t* pairs, int capacity) {
+  const auto batches = its::detail::parameter_batches(nsol, nparam);
+  for (size_t i = 0; i < batches.size() && int(i) < capacity; ++i) {
+    pairs[2 * i] = int64_t(batches[i].first);
+    pairs[2 * i + 1] = int64_t(batches[i].second);
+  }
+  return int(batches.size());
 }
 
 } // extern "C"

@@ -168,6 +168,12 @@ class RefOracle:
         lib.ref_time_handler_op.restype = C.c_double
         lib.ref_time_handler_op.argtypes = [C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int]
         lib.ref_dense_eigen.argtypes = [C.c_size_t, dp, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, i64p]
+        lib.ref_dense_lineq.argtypes = [C.c_size_t, dp, C.c_int, dp, C.c_double, dp, i64p]
+        lib.ref_gram_schmidt.argtypes = [C.c_size_t, dp, dp, dp]
+        lib.ref_eye_order.argtypes = [C.c_size_t, dp, i64p]
+        lib.ref_overlap.argtypes = [C.c_int, C.c_size_t, dp, dp, dp]
+        lib.ref_parameter_batches.argtypes = [C.c_size_t, C.c_size_t, i64p, C.c_int]
+        lib.ref_dense_diis.argtypes = [C.c_size_t, C.c_double, dp, dp, i64p, C.POINTER(C.c_double)]
 
     def solve(self, spec, want_solutions=False):
         res = self.N.SolveResult()
@@ -191,6 +197,51 @@ class RefOracle:
         if rc:
             raise RuntimeError("ref_dense_eigen failed")
         return ev, err, sol, tuple(int(v) for v in stats)
+
+    def gram_schmidt(self, s):
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        n = s.shape[0]
+        t, norms = np.zeros((n, n)), np.zeros(n)
+        assert self.lib.ref_gram_schmidt(n, _d(s), _d(t), _d(norms)) == 0
+        return t, norms
+
+    def eye_order(self, m):
+        m = np.ascontiguousarray(m, dtype=np.float64)
+        order = np.zeros(m.shape[0], dtype=np.int64)
+        assert self.lib.ref_eye_order(m.shape[0], _d(m), order.ctypes.data_as(C.POINTER(C.c_int64))) == 0
+        return order.tolist()
+
+    def overlap(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        k, n = x.shape
+        a, b = np.zeros((k, k)), np.zeros((k, k))
+        assert self.lib.ref_overlap(k, n, _d(x), _d(a), _d(b)) == 0
+        return a, b
+
+    def parameter_batches(self, nsol, nparam):
+        pairs = np.zeros(64, dtype=np.int64)
+        nb = self.lib.ref_parameter_batches(nsol, nparam, pairs.ctypes.data_as(C.POINTER(C.c_int64)), 32)
+        return [(int(pairs[2 * i]), int(pairs[2 * i + 1])) for i in range(nb)]
+
+    def dense_lineq(self, matrix, rhs, threshold=1e-10):
+        """the reference's LinearEquations test protocol (test/itsolv/test_LinearEquations.cpp:59-98)"""
+        m = np.ascontiguousarray(matrix, dtype=np.float64)
+        b = np.ascontiguousarray(rhs, dtype=np.float64)
+        sol = np.zeros_like(b)
+        stats = np.zeros(2, dtype=np.int64)
+        if self.lib.ref_dense_lineq(m.shape[0], _d(m), b.shape[0], _d(b), threshold, _d(sol),
+                                    stats.ctypes.data_as(C.POINTER(C.c_int64))):
+            raise RuntimeError("ref_dense_lineq failed")
+        return sol, int(stats[0]), bool(stats[1])
+
+    def dense_diis(self, n, param):
+        """the reference's NonLinearEquations test protocol (test/itsolv/test_NonLinearEquations.cpp:62-110)"""
+        sol, res = np.zeros(n), np.zeros(n)
+        stats = np.zeros(3, dtype=np.int64)
+        err = C.c_double()
+        if self.lib.ref_dense_diis(n, param, _d(sol), _d(res), stats.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(err)):
+            raise RuntimeError("ref_dense_diis failed")
+        return sol, res, tuple(int(v) for v in stats), err.value
 
     def read_trace(self):
         ne, nv = self.lib.ref_trace_entries(), self.lib.ref_trace_values()

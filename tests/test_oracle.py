@@ -235,3 +235,60 @@ def test_golden_solves_with_the_products_host_algebra(oracle):
             ev = np.array([res.eigenvalues[i] for i in range(len(want["eigenvalues"]))])
             assert np.abs(ev / np.array(want["eigenvalues"]) - 1).max() <= 1e-10, name
 
+
+@pytest.mark.parametrize("helper", ["literal", "product"])
+def test_reference_build_passes_the_references_own_linear_equations_test(oracle, helper):
+    """test/itsolv/test_LinearEquations.cpp:59-98 (symmetric_system): matrix(i,j) = i+j+1 (+1 on the diagonal), right-hand
+    sides whose solutions are the constant vectors root+1, n = 3..33, up to 13 roots, threshold 1e-10, solutions to 1e-5"""
+    ref = oracle.ref if helper == "literal" else oracle.ref_product_helper
+    if ref is None:
+        pytest.skip("oracle/_ref is not built")
+    for n in range(3, 34, 3):
+        i = np.arange(n)
+        matrix = (i[:, None] + i[None, :] + 1.0) + np.eye(n)
+        for nroot in range(1, min(n, 13) + 1):
+            expected = np.repeat(np.arange(1.0, nroot + 1)[:, None], n, axis=1)
+            rhs = (np.arange(1, nroot + 1)[:, None] * (n * (n + 1) // 2 + i[None, :] * n + 1)).astype(np.float64)
+            assert np.array_equal(expected @ matrix, rhs)
+            sol, iterations, converged = ref.dense_lineq(matrix, rhs)
+            assert np.abs(sol - expected).max() <= 1e-5, (n, nroot, iterations, converged)
+
+
+@pytest.mark.parametrize("helper", ["literal", "product"])
+def test_reference_build_passes_the_references_own_diis_test(oracle, helper):
+    """test/itsolv/test_NonLinearEquations.cpp:62-121 (small_quadratic_form): DIIS on a quadratic form, n = 2..50"""
+    ref = oracle.ref if helper == "literal" else oracle.ref_product_helper
+    if ref is None:
+        pytest.skip("oracle/_ref is not built")
+    for n in range(2, 51):
+        sol, res, (iterations, r_creations, n_iter), error = ref.dense_diis(n, 10.0)
+        assert error <= 2e-8, n
+        assert r_creations <= 2 * n_iter, n
+        assert np.linalg.norm(res) <= 1e-8, n
+        assert np.abs(sol - 1.0).max() <= 1e-8, n
+
+
+def test_kats_of_the_small_subspace_functions(oracle):
+    """known answers of test/itsolv/subspace/test_util.cpp for functions of the reference that both the reference's and
+    the fused drivers call unmodified: gram_schmidt on an overlap matrix (s_3x3 :124-140, s_4x4_duplicate :142-152),
+    eye_order (:84-107), overlap (:26-58), parameter_batches (:175-188)"""
+    if oracle.ref is None:
+        pytest.skip("oracle/_ref is not built")
+    t, norms = oracle.ref.gram_schmidt(np.array([[14, 25, 31], [25, 45, 56], [31, 56, 70]], dtype=float))
+    assert np.abs(t - np.array([[1, 0, 0], [-25 / 14, 1, 0], [1, -9 / 5, 1]])).max() <= 1e-14
+    assert np.abs(norms - np.sqrt([14, 5 / 14, 1 / 5])).max() <= 1e-13
+    t, norms = oracle.ref.gram_schmidt(np.array([[1, 1, 1, 1], [1, 2, 2, 2], [1, 2, 2, 2], [1, 2, 2, 3]], dtype=float))
+    assert np.abs(t - np.array([[1, 0, 0, 0], [-1, 1, 0, 0], [0, -1, 1, 0], [0, -1, 0, 1]])).max() <= 1e-14
+    assert np.abs(norms - np.array([1, 1, 0, 1])).max() <= 1e-13
+    assert oracle.ref.eye_order(np.eye(3)) == [0, 1, 2]
+    assert oracle.ref.eye_order(np.array([[0, 1, 0], [0, 0, 1], [1, 0, 0]], dtype=float)) == [2, 0, 1]
+    assert oracle.ref.eye_order(np.array([[0.1, 0.5, 0.2], [0.2, 0.1, 0.5], [0.5, 0.2, 0.1]])) == [2, 0, 1]
+    alphas = np.array([1.0, 2.0, 3.0])
+    a, b = oracle.ref.overlap(np.repeat(alphas[:, None], 5, axis=1))
+    want = 5 * alphas[:, None] * alphas[None, :]
+    assert np.array_equal(a, want) and np.array_equal(b, want)
+    assert oracle.ref.parameter_batches(3, 3) == [(0, 3)]
+    assert oracle.ref.parameter_batches(2, 3) == [(0, 2)]
+    assert oracle.ref.parameter_batches(9, 3) == [(0, 3), (3, 6), (6, 9)]
+    assert oracle.ref.parameter_batches(4, 3) == [(0, 3), (3, 4)]
+
