@@ -29,6 +29,7 @@
 #include <molpro/linalg/array/util/Distribution.h>
 #include <molpro/linalg/itsolv/subspace/gram_schmidt.h>
 #include <molpro/linalg/itsolv/subspace/util.h>
+#include <molpro/linalg/itsolv/DSpaceResetter.h>
 
 namespace {
 using Vec = std::vector<double>;
@@ -748,6 +749,23 @@ int ref_parameter_batches(size_t nsol, size_t nparam, int64_t* pairs, int capaci
     pairs[2 * i + 1] = int64_t(batches[i].second);
   }
   return int(batches.size());
+}
+
+//! detail::max_overlap_with_R of the D-space resetter (reference itsolv/DSpaceResetter.h; KATs test/itsolv/
+//! testDSpaceResetter.cpp:44-76): for nq Q vectors against nr R vectors of length n, the indices it returns
+int ref_max_overlap_with_R(int nr, int nq, size_t n, const double* r, const double* q, int64_t* indices) {
+  return ref_guarded([&] {
+    std::vector<Vec> rs, qs;
+    for (int i = 0; i < nr; ++i)
+      rs.push_back(to_vec(r + size_t(i) * n, n));
+    for (int i = 0; i < nq; ++i)
+      qs.push_back(to_vec(q + size_t(i) * n, n));
+    la::ArrayHandlerIterable<Vec, Vec> h;
+    its::Logger logger;
+    const auto out = its::detail::max_overlap_with_R(its::cwrap(rs), its::cwrap(qs), h, logger);
+    for (size_t i = 0; i < out.size(); ++i)
+      indices[i] = int64_t(out[i]);
+  });
 }
 
 } // extern "C"

@@ -173,6 +173,7 @@ class RefOracle:
         lib.ref_eye_order.argtypes = [C.c_size_t, dp, i64p]
         lib.ref_overlap.argtypes = [C.c_int, C.c_size_t, dp, dp, dp]
         lib.ref_parameter_batches.argtypes = [C.c_size_t, C.c_size_t, i64p, C.c_int]
+        lib.ref_max_overlap_with_R.argtypes = [C.c_int, C.c_int, C.c_size_t, dp, dp, i64p]
         lib.ref_dense_diis.argtypes = [C.c_size_t, C.c_double, dp, dp, i64p, C.POINTER(C.c_double)]
 
     def solve(self, spec, want_solutions=False):
@@ -222,6 +223,14 @@ class RefOracle:
         pairs = np.zeros(64, dtype=np.int64)
         nb = self.lib.ref_parameter_batches(nsol, nparam, pairs.ctypes.data_as(C.POINTER(C.c_int64)), 32)
         return [(int(pairs[2 * i]), int(pairs[2 * i + 1])) for i in range(nb)]
+
+    def max_overlap_with_R(self, r, q):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, r.shape[1])
+        out = np.zeros(max(1, q.shape[0]), dtype=np.int64)
+        assert self.lib.ref_max_overlap_with_R(r.shape[0], q.shape[0], r.shape[1], _d(r), _d(q),
+                                               out.ctypes.data_as(C.POINTER(C.c_int64))) == 0
+        return out[:q.shape[0]].tolist()
 
     def dense_lineq(self, matrix, rhs, threshold=1e-10):
         """the reference's LinearEquations test protocol (test/itsolv/test_LinearEquations.cpp:59-98)"""

@@ -291,4 +291,10 @@ def test_kats_of_the_small_subspace_functions(oracle):
     assert oracle.ref.parameter_batches(2, 3) == [(0, 2)]
     assert oracle.ref.parameter_batches(9, 3) == [(0, 3), (3, 6), (6, 9)]
     assert oracle.ref.parameter_batches(4, 3) == [(0, 3), (3, 4)]
+    # D-space resetter: which Q vector overlaps most with each R vector (test/itsolv/testDSpaceResetter.cpp:44-76)
+    eye = np.eye(3)
+    assert oracle.ref.max_overlap_with_R(eye, eye) == [2, 1, 0]
+    assert oracle.ref.max_overlap_with_R(eye, eye[[0, 2]]) == [1, 0]
+    assert oracle.ref.max_overlap_with_R(eye, eye[[1]]) == [0]
+    assert oracle.ref.max_overlap_with_R(eye, np.zeros((0, 3))) == []
 
