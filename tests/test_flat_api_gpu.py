@@ -222,3 +222,46 @@ def test_the_references_own_eigensolver_test_on_the_gpu(ctx, name, hmat):
                     assert abs(abs(sol[k] @ want_vec[:, k]) - 1) <= 1e-8, where
         finally:
             check(lib, lib.ItsolvB200Finalize())
+
+
+@pytest.mark.parametrize("options", [b"", b"fused=1"])
+def test_the_references_own_linear_equations_test_on_the_gpu(ctx, options):
+    """test/itsolv/test_LinearEquations.cpp:59-98 (symmetric_system) with the CUDA containers underneath, through the flat
+    interface: matrix(i,j) = i+j+1 (+1 on the diagonal), right-hand sides whose solutions are the constant vectors
+    root+1, n = 3..33, up to 13 right-hand sides, threshold 1e-10, solutions to 1e-5"""
+    lib = N.host()
+    for n in range(3, 34, 6):
+        i = np.arange(n)
+        matrix = (i[:, None] + i[None, :] + 1.0) + np.eye(n)
+        Md = torch.from_numpy(matrix).cuda()
+        diag = torch.from_numpy(np.ascontiguousarray(np.diag(matrix))).cuda()
+        for nroot in sorted({1, 2, min(n, 8), min(n, 13)}):
+            expected = np.repeat(np.arange(1.0, nroot + 1)[:, None], n, axis=1)
+            rhs = torch.from_numpy(expected @ matrix).cuda().contiguous()
+            lo, hi = C.c_size_t(), C.c_size_t()
+            check(lib, lib.ItsolvB200LinearEquationsInitialize(ctx.handle, n, nroot, C.byref(lo), C.byref(hi), rhs.data_ptr(),
+                                                              0.0, 1e-10, HUGE, 1, 0, options))
+            try:
+                params = torch.zeros((nroot, n), dtype=torch.float64, device="cuda")
+                for k in range(nroot):  # what solve() generates with generate_initial_guess = true
+                    params[k, k] = 1.0
+                action = torch.zeros_like(params)
+                check(lib, lib.ItsolvB200SetDiagonals(diag.data_ptr()))
+                nwork = nroot
+                for _ in range(200):
+                    if nwork <= 0:
+                        break
+                    action[:nwork] = params[:nwork] @ Md.T
+                    nwork = lib.ItsolvB200AddVector(nroot, params.data_ptr(), action.data_ptr())
+                    assert nwork >= 0, lib.ItsolvB200LastError().decode()
+                    while lib.ItsolvB200EndIterationNeeded() == 1:
+                        if nwork > 0:
+                            check(lib, lib.ItsolvB200PreconditionDefault(nwork, action.data_ptr()))
+                        nwork = lib.ItsolvB200EndIteration(nroot, params.data_ptr(), action.data_ptr())
+                        assert nwork >= 0, lib.ItsolvB200LastError().decode()
+                assert nwork == 0, (n, nroot)
+                roots = (C.c_int * nroot)(*range(nroot))
+                check(lib, lib.ItsolvB200Solution(nroot, roots, params.data_ptr(), action.data_ptr()))
+                assert np.abs(params.cpu().numpy() - expected).max() <= 1e-5, (n, nroot)
+            finally:
+                check(lib, lib.ItsolvB200Finalize())
