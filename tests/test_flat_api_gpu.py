@@ -265,3 +265,42 @@ def test_the_references_own_linear_equations_test_on_the_gpu(ctx, options):
                 assert np.abs(params.cpu().numpy() - expected).max() <= 1e-5, (n, nroot)
             finally:
                 check(lib, lib.ItsolvB200Finalize())
+
+
+@pytest.mark.parametrize("options", [b"max_size_qspace=6", b"max_size_qspace=6,fused=1"])
+def test_the_references_own_diis_test_on_the_gpu(ctx, options):
+    """test/itsolv/test_NonLinearEquations.cpp:62-121 (small_quadratic_form) with the CUDA containers underneath, through
+    the flat interface: f = (x-1).h.(x-1)/2 with h all ones and diagonal 10 (i+2), start at e_0, update by the diagonal"""
+    lib = N.host()
+    for n in range(2, 51, 4):
+        h = np.ones((n, n))
+        h[np.diag_indices(n)] = 10.0 * (np.arange(n) + 2)
+        Hd = torch.from_numpy(h).cuda()
+        diag = torch.from_numpy(np.ascontiguousarray(np.diag(h))).cuda()
+        lo, hi = C.c_size_t(), C.c_size_t()
+        check(lib, lib.ItsolvB200NonLinearEquationsInitialize(ctx.handle, n, C.byref(lo), C.byref(hi), 1e-8, 0, options))
+        try:
+            x = torch.zeros((1, n), dtype=torch.float64, device="cuda")
+            g = torch.zeros_like(x)
+            x[0, 0] = 1.0
+            nwork = 1
+            for _ in range(1000):
+                if nwork <= 0:
+                    break
+                g[0] = Hd @ (x[0] - 1.0)
+                added = lib.ItsolvB200AddVector(1, x.data_ptr(), g.data_ptr())
+                assert added >= 0, lib.ItsolvB200LastError().decode()
+                if added:
+                    g[0] = g[0] / diag
+                nwork = lib.ItsolvB200EndIteration(1, x.data_ptr(), g.data_ptr())
+                assert nwork >= 0, lib.ItsolvB200LastError().decode()
+            assert nwork == 0, n
+            err = np.zeros(1)
+            check(lib, lib.ItsolvB200Errors(err.ctypes.data_as(N.c_double_p)))
+            assert err[0] <= 2e-8, n
+            root = (C.c_int * 1)(0)
+            check(lib, lib.ItsolvB200Solution(1, root, x.data_ptr(), g.data_ptr()))
+            assert float(g.norm()) <= 1e-8, n
+            assert float((x - 1.0).abs().max()) <= 1e-8, n
+        finally:
+            check(lib, lib.ItsolvB200Finalize())
